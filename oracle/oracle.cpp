@@ -1762,4 +1762,50 @@ double orc_batch_rollout(void** envs, int64_t n, int64_t first_env_id, int64_t t
   return std::chrono::duration<double>(t_end - t_start).count();
 }
 
+// ---- batch helpers for lock-step parity tests (no reference counterpart)
+void orc_batch_step(void** envs, int64_t n, const uint8_t* keys, int auto_reset, int threads, int32_t* rc_out) {
+  if (threads < 1) threads = 1;
+  auto work = [&](int tid) {
+    int64_t lo = n * tid / threads, hi = n * (tid + 1) / threads;
+    for (int64_t i = lo; i < hi; ++i) {
+      int rc = auto_reset ? orc_step_auto(envs[i], keys[i]) : orc_react(envs[i], keys[i]);
+      if (rc_out) rc_out[i] = rc;
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < threads; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+}
+void orc_batch_reset(void** envs, int64_t n, int threads, int32_t* rc_out) {
+  if (threads < 1) threads = 1;
+  auto work = [&](int tid) {
+    int64_t lo = n * tid / threads, hi = n * (tid + 1) / threads;
+    for (int64_t i = lo; i < hi; ++i) {
+      int rc = orc_reset(envs[i]);
+      if (rc_out) rc_out[i] = rc;
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < threads; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+}
+void orc_batch_get_obs(void** envs, int64_t n, uint8_t* screen, uint8_t* history, uint32_t* status, uint32_t* message,
+                       uint8_t* is_terminal) {
+  for (int64_t i = 0; i < n; ++i) {
+    Env* e = (Env*)envs[i];
+    size_t C = e->screen.size();
+    int32_t term = 0;
+    uint32_t msg = 0;
+    orc_get_obs(envs[i], screen ? screen + i * C : nullptr, history ? history + i * C : nullptr,
+                status ? status + i * 10 : nullptr, &msg, &term);
+    if (message) message[i] = msg;
+    if (is_terminal) is_terminal[i] = (uint8_t)term;
+  }
+}
+void orc_batch_hash(void** envs, int64_t n, uint64_t* out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = orc_state_hash(envs[i]);
+}
+
 }  // extern "C"

@@ -135,6 +135,13 @@ double orc_batch_rollout(void** envs, int64_t n, int64_t first_env_id, int64_t t
                          int threads, int compose_only_on_redraw, uint64_t* digest);
 uint64_t orc_state_hash(void* env);
 
+/* Lock-step helpers for the parity tests: one call steps / resets / reads n envs. */
+void orc_batch_step(void** envs, int64_t n, const uint8_t* keys, int auto_reset, int threads, int32_t* rc_out);
+void orc_batch_reset(void** envs, int64_t n, int threads, int32_t* rc_out);
+void orc_batch_get_obs(void** envs, int64_t n, uint8_t* screen, uint8_t* history, uint32_t* status, uint32_t* message,
+                       uint8_t* is_terminal);
+void orc_batch_hash(void** envs, int64_t n, uint64_t* out);
+
 #ifdef __cplusplus
 }
 #endif

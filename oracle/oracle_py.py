@@ -285,6 +285,10 @@ def lib():
         L.orc_batch_rollout.restype = C.c_double
         L.orc_batch_rollout.argtypes = [C.POINTER(vp), C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                         C.POINTER(C.c_uint64)]
+        L.orc_batch_step.argtypes = [C.POINTER(vp), C.c_int64, vp, C.c_int, C.c_int, vp]
+        L.orc_batch_reset.argtypes = [C.POINTER(vp), C.c_int64, C.c_int, vp]
+        L.orc_batch_get_obs.argtypes = [C.POINTER(vp), C.c_int64, vp, vp, vp, vp, vp]
+        L.orc_batch_hash.argtypes = [C.POINTER(vp), C.c_int64, vp]
         _lib = L
     return _lib
 
@@ -409,3 +413,61 @@ def batch_rollout(envs, first_env_id, t0, steps, threads):
     dig = C.c_uint64()
     secs = L.orc_batch_rollout(arr, len(envs), first_env_id, t0, steps, threads, 0, C.byref(dig))
     return secs, dig.value
+
+
+class OracleBatch:
+    """N independent oracle envs stepped in lockstep (the CPU side of the parity tests and of
+    bench.py's cpu_baseline). Seeds: env i gets seeds[i]."""
+
+    def __init__(self, config, n, max_steps=1000, seeds=None, threads=None):
+        self.L = lib()
+        self.envs = [OracleEnv(config, max_steps, seed=(seeds[i] if seeds is not None else None), reset=False)
+                     for i in range(n)]
+        self.n = n
+        self.w, self.h, self.C = self.envs[0].w, self.envs[0].h, self.envs[0].C
+        self.ptrs = (C.c_void_p * n)(*[e.ptr for e in self.envs])
+        self.threads = threads or min(os.cpu_count() or 1, 16)
+        self.rc = np.zeros(n, np.int32)
+
+    def seed(self, seeds):
+        for e, s in zip(self.envs, seeds):
+            e.set_seed(int(s))
+
+    def reset(self):
+        self.L.orc_batch_reset(self.ptrs, self.n, self.threads, self.rc.ctypes.data)
+        return self.rc
+
+    def step(self, keys, auto_reset=True):
+        keys = np.ascontiguousarray(keys, np.uint8)
+        self.L.orc_batch_step(self.ptrs, self.n, keys.ctypes.data, int(auto_reset), self.threads, self.rc.ctypes.data)
+        return self.rc
+
+    def obs(self):
+        n, Cc = self.n, self.C
+        screen = np.zeros((n, Cc), np.uint8)
+        hist = np.zeros((n, Cc), np.uint8)
+        status = np.zeros((n, 10), np.uint32)
+        msg = np.zeros(n, np.uint32)
+        term = np.zeros(n, np.uint8)
+        self.L.orc_batch_get_obs(self.ptrs, n, screen.ctypes.data, hist.ctypes.data, status.ctypes.data,
+                                 msg.ctypes.data, term.ctypes.data)
+        return dict(screen=screen, history=hist, status=status, message=msg, done=term)
+
+    def hashes(self):
+        out = np.zeros(self.n, np.uint64)
+        self.L.orc_batch_hash(self.ptrs, self.n, out.ctypes.data)
+        return out
+
+
+KEYS11 = np.frombuffer(b".hjklnbuy>s", np.uint8)
+
+
+def synthetic_actions(t, env_ids):
+    """SURVEY §8d action stream: a[i,t] = splitmix64(0x9E3779B97F4A7C15*(t+1) ^ i) % 11 -> ASCII key."""
+    with np.errstate(over="ignore"):
+        x = (np.uint64(0x9E3779B97F4A7C15) * np.uint64(t + 1)) ^ np.asarray(env_ids, np.uint64)
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        x = x ^ (x >> np.uint64(31))
+    return KEYS11[(x % np.uint64(11)).astype(np.int64)]

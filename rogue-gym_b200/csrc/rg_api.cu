@@ -1,0 +1,539 @@
+// rg_api.cu — the extern "C" boundary declared in include/rogue_b200.h.
+//
+// Host side of the batch driver: what ThreadConductor (python/src/thread_impls.rs:14-88) and
+// GameStateImpl (python/src/state_impls.rs) do with N threads and 2N channels is here one
+// device arena, one stream and one kernel launch per call. There is no CPU implementation
+// behind these entry points: without a CUDA device every compute call returns RG_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/rogue_b200.h"
+#include "rg_launch.h"
+#include "rg_types.h"
+
+using rg::DevBatch;
+using rg::EnvState;
+
+struct rg_batch {
+  rg_params P;
+  int64_t n = 0;
+  int64_t max_steps = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  DevBatch d{};
+  rg_params* dP = nullptr;
+  uint8_t* d_actions = nullptr;
+  uint8_t* d_hist_bytes = nullptr;  // lazily allocated [N][C]
+  uint64_t* d_u64 = nullptr;        // [2N] scratch: seeds / hashes
+  int* d_out3 = nullptr;
+  uint32_t* h_errflag = nullptr;    // pinned
+  uint8_t* h_error = nullptr;       // pinned [N]
+  std::vector<void*> dev_allocs;
+  std::string err;
+  int64_t launches = 0;
+};
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int set_err(rg_batch* b, int code, const std::string& m) {
+  if (b) b->err = m;
+  g_last_error = m;
+  return code;
+}
+int cuda_fail(rg_batch* b, cudaError_t e, const char* what) {
+  return set_err(b, RG_ERR_CUDA, std::string("CUDA failure in ") + what + ": " + cudaGetErrorString(e));
+}
+#define RG_CUDA(b, call)                                  \
+  do {                                                    \
+    cudaError_t e__ = (call);                             \
+    if (e__ != cudaSuccess) return cuda_fail(b, e__, #call); \
+  } while (0)
+
+template <class T>
+cudaError_t dev_alloc(rg_batch* b, T** p, size_t count) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(count * sizeof(T), 16));
+  if (e != cudaSuccess) return e;
+  b->dev_allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return cudaSuccess;
+}
+
+const char* status_text(int code) {
+  switch (code) {
+    case RG_ERR_INVALID_INPUT: return "Invliad input key";
+    case RG_ERR_IGNORED_INPUT: return "Ignored input code";
+    case RG_ERR_PANIC: return "worker panicked (a state in which the reference implementation panics)";
+    case RG_ERR_SETTING: return "Invalid Setting / InvalidTileError";
+    default: return "unknown error";
+  }
+}
+
+bool same_except_seed(rg_params a, rg_params b) {
+  a.has_seed = b.has_seed = 0;
+  a.seed_lo = b.seed_lo = a.seed_hi = b.seed_hi = 0;
+  return memcmp(&a, &b, sizeof(a)) == 0;
+}
+
+int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64_t n_envs, int64_t max_steps, int device,
+                rg_batch** out) {
+  if (!out) return set_err(nullptr, RG_ERR_ARG, "rg_create: out is null");
+  *out = nullptr;
+  if (n_envs < 1) return set_err(nullptr, RG_ERR_ARG, "rg_create: n_envs must be >= 1");
+  if (max_steps < 0) return set_err(nullptr, RG_ERR_ARG, "rg_create: max_steps must be >= 0");
+  char ebuf[256];
+  int rc = rg_validate_params(&P, ebuf, sizeof(ebuf));
+  if (rc != RG_OK) return set_err(nullptr, rc, ebuf);
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return set_err(nullptr, RG_ERR_CUDA,
+                   std::string("no CUDA device available (this library has no CPU path): ") +
+                       (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0"));
+  if (device < 0 || device >= ndev) return set_err(nullptr, RG_ERR_ARG, "rg_create: invalid device ordinal");
+  rg_batch* b = new rg_batch();
+  b->P = P;
+  b->n = n_envs;
+  b->max_steps = max_steps;
+  b->device = device;
+  auto fail = [&](int code) {
+    std::string keep = b->err;
+    rg_destroy(b);
+    g_last_error = keep;
+    return code;
+  };
+#define RG_TRY(call)                                                 \
+  do {                                                               \
+    cudaError_t e__ = (call);                                        \
+    if (e__ != cudaSuccess) return fail(cuda_fail(b, e__, #call));   \
+  } while (0)
+  RG_TRY(cudaSetDevice(device));
+  RG_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  DevBatch& d = b->d;
+  d.n = n_envs;
+  d.W = P.width;
+  d.H = P.height;
+  d.C = d.W * d.H;
+  d.CP = (d.C + 15) / 16 * 16;
+  d.HB = ((d.CP / 8) + 15) / 16 * 16;
+  d.WW = (d.W + 31) / 32;
+  d.max_steps = max_steps;
+  const size_t N = (size_t)n_envs;
+  RG_TRY(dev_alloc(b, &b->dP, 1));
+  RG_TRY(cudaMemcpy(b->dP, &P, sizeof(P), cudaMemcpyHostToDevice));
+  d.P = b->dP;
+  RG_TRY(dev_alloc(b, &d.surface, N * d.CP));
+  RG_TRY(dev_alloc(b, &d.attr, N * d.CP));
+  RG_TRY(dev_alloc(b, &d.screen, N * d.CP));
+  RG_TRY(dev_alloc(b, &d.hist, N * d.HB));
+  RG_TRY(dev_alloc(b, &d.walk, N * (size_t)d.H * d.WW));
+  RG_TRY(dev_alloc(b, &d.dist, N * (size_t)rg::NCACHE * d.CP));
+  RG_TRY(dev_alloc(b, &d.st, N));
+  RG_TRY(dev_alloc(b, &d.status, N * 10));
+  RG_TRY(dev_alloc(b, &d.reward, N));
+  RG_TRY(dev_alloc(b, &d.done, N));
+  RG_TRY(dev_alloc(b, &d.message, N));
+  RG_TRY(dev_alloc(b, &d.error, N));
+  RG_TRY(dev_alloc(b, &d.errflag, 1));
+  RG_TRY(dev_alloc(b, &b->d_actions, N));
+  RG_TRY(dev_alloc(b, &b->d_u64, 2 * N));
+  RG_TRY(dev_alloc(b, &b->d_out3, 4));
+  RG_TRY(cudaMallocHost(&b->h_errflag, sizeof(uint32_t)));
+  RG_TRY(cudaMallocHost(&b->h_error, N));
+  RG_TRY(cudaMemsetAsync(d.st, 0, N * sizeof(EnvState), b->stream));
+  RG_TRY(cudaMemsetAsync(d.screen, ' ', N * d.CP, b->stream));
+  RG_TRY(cudaMemsetAsync(d.hist, 0, N * d.HB, b->stream));
+  RG_TRY(cudaMemsetAsync(d.error, 0, N, b->stream));
+  RG_TRY(cudaMemsetAsync(d.errflag, 0, sizeof(uint32_t), b->stream));
+  RG_TRY(rg::configure_kernels(d));
+  {  // seeds: config seed (fixed, every episode identical) or fresh entropy (seed: null)
+    std::vector<uint64_t> lo(N), hi(N, 0);
+    bool seeded = P.has_seed != 0;
+    if (per_env) {
+      std::random_device rd;
+      for (size_t i = 0; i < N; ++i) {
+        const rg_params& q = (*per_env)[i];
+        if (q.has_seed != P.has_seed)
+          return fail(set_err(b, RG_ERR_SETTING, "per-env configs must all set or all omit `seed`"));
+        lo[i] = q.has_seed ? q.seed_lo : (((uint64_t)rd() << 32) | rd());
+        hi[i] = q.has_seed ? q.seed_hi : 0;
+      }
+    } else if (seeded) {
+      std::fill(lo.begin(), lo.end(), P.seed_lo);
+      std::fill(hi.begin(), hi.end(), P.seed_hi);
+    } else {
+      std::random_device rd;  // rng::gen_seed (core/src/rng.rs:37-45): thread_rng
+      for (size_t i = 0; i < N; ++i) lo[i] = ((uint64_t)rd() << 32) | rd();
+    }
+    if (!seeded && P.has_seed_range) {
+      const uint64_t span = P.seed_range_hi - P.seed_range_lo;
+      if (P.seed_range_hi <= P.seed_range_lo) return fail(set_err(b, RG_ERR_SETTING, "empty seed_range"));
+      for (size_t i = 0; i < N; ++i) lo[i] = P.seed_range_lo + lo[i] % span;
+    }
+    RG_TRY(cudaMemcpyAsync(b->d_u64, lo.data(), N * 8, cudaMemcpyHostToDevice, b->stream));
+    RG_TRY(cudaMemcpyAsync(b->d_u64 + N, hi.data(), N * 8, cudaMemcpyHostToDevice, b->stream));
+    RG_TRY(rg::launch_seed(d, b->d_u64, b->d_u64 + N, seeded ? 1 : 0, b->stream));
+    RG_TRY(cudaStreamSynchronize(b->stream));
+  }
+  // GameStateImpl::new builds the game and takes the first PlayerState (state_impls.rs:20-37)
+  RG_TRY(rg::launch_reset(d, b->stream));
+  b->launches += 2;
+  rc = rg_sync(b);
+  if (rc != RG_OK) return fail(rc);
+#undef RG_TRY
+  *out = b;
+  return RG_OK;
+}
+
+int copy_obs(rg_batch* b, rg_host_obs* out) {
+  if (!out) return RG_OK;
+  const DevBatch& d = b->d;
+  const size_t N = (size_t)b->n;
+  if (out->screen)
+    RG_CUDA(b, cudaMemcpy2DAsync(out->screen, d.C, d.screen, d.CP, d.C, N, cudaMemcpyDeviceToHost, b->stream));
+  if (out->history) {
+    if (!b->d_hist_bytes) RG_CUDA(b, dev_alloc(b, &b->d_hist_bytes, N * d.C));
+    RG_CUDA(b, rg::launch_unpack_hist(d, b->d_hist_bytes, b->stream));
+    b->launches += 1;
+    RG_CUDA(b, cudaMemcpyAsync(out->history, b->d_hist_bytes, N * d.C, cudaMemcpyDeviceToHost, b->stream));
+  }
+  if (out->status) RG_CUDA(b, cudaMemcpyAsync(out->status, d.status, N * 40, cudaMemcpyDeviceToHost, b->stream));
+  if (out->reward) RG_CUDA(b, cudaMemcpyAsync(out->reward, d.reward, N * 4, cudaMemcpyDeviceToHost, b->stream));
+  if (out->done) RG_CUDA(b, cudaMemcpyAsync(out->done, d.done, N, cudaMemcpyDeviceToHost, b->stream));
+  if (out->message) RG_CUDA(b, cudaMemcpyAsync(out->message, d.message, N * 4, cudaMemcpyDeviceToHost, b->stream));
+  if (out->error) RG_CUDA(b, cudaMemcpyAsync(out->error, d.error, N, cudaMemcpyDeviceToHost, b->stream));
+  return RG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rg_version(void) { return "rogue-gym_b200 0.1 (sm_100a)"; }
+
+const char* rg_last_error(rg_batch* b) { return b ? b->err.c_str() : g_last_error.c_str(); }
+
+int rg_create_from_params(const rg_params* p, int64_t n_envs, int64_t max_steps, int device, rg_batch** out) {
+  if (!p) return set_err(nullptr, RG_ERR_ARG, "rg_create_from_params: params is null");
+  return create_impl(*p, nullptr, n_envs, max_steps, device, out);
+}
+
+int rg_create(const char* const* cfg_json, int64_t n_cfg, int64_t n_envs, int64_t max_steps, int device, rg_batch** out) {
+  if (!cfg_json || n_cfg < 1 || (n_cfg != 1 && n_cfg != n_envs))
+    return set_err(nullptr, RG_ERR_ARG, "rg_create: n_cfg must be 1 or n_envs");
+  char ebuf[512];
+  rg_params P;
+  int rc = rg_parse_config(cfg_json[0], &P, ebuf, sizeof(ebuf));
+  if (rc != RG_OK) return set_err(nullptr, rc, ebuf);
+  if (n_cfg == 1) return create_impl(P, nullptr, n_envs, max_steps, device, out);
+  std::vector<rg_params> all((size_t)n_cfg);
+  all[0] = P;
+  for (int64_t i = 1; i < n_cfg; ++i) {
+    rc = rg_parse_config(cfg_json[i], &all[(size_t)i], ebuf, sizeof(ebuf));
+    if (rc != RG_OK) return set_err(nullptr, rc, ebuf);
+    if (!same_except_seed(P, all[(size_t)i]))
+      return set_err(nullptr, RG_ERR_SETTING,
+                     "Error in rogue-gym: Invalid Setting: configs of one batch may differ in `seed` only");
+  }
+  return create_impl(P, &all, n_envs, max_steps, device, out);
+}
+
+void rg_destroy(rg_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  for (void* p : b->dev_allocs) cudaFree(p);
+  if (b->h_errflag) cudaFreeHost(b->h_errflag);
+  if (b->h_error) cudaFreeHost(b->h_error);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+int rg_seed(rg_batch* b, const uint64_t* seed_lo, const uint64_t* seed_hi) {
+  if (!b || !seed_lo) return set_err(b, RG_ERR_ARG, "rg_seed: null argument");
+  const size_t N = (size_t)b->n;
+  RG_CUDA(b, cudaSetDevice(b->device));
+  RG_CUDA(b, cudaMemcpyAsync(b->d_u64, seed_lo, N * 8, cudaMemcpyHostToDevice, b->stream));
+  if (seed_hi) RG_CUDA(b, cudaMemcpyAsync(b->d_u64 + N, seed_hi, N * 8, cudaMemcpyHostToDevice, b->stream));
+  RG_CUDA(b, rg::launch_seed(b->d, b->d_u64, seed_hi ? b->d_u64 + N : nullptr, 1, b->stream));
+  b->launches += 1;
+  RG_CUDA(b, cudaStreamSynchronize(b->stream));  // the host arrays may be pageable
+  return RG_OK;
+}
+
+int rg_reset(rg_batch* b) {
+  if (!b) return set_err(b, RG_ERR_ARG, "rg_reset: null batch");
+  RG_CUDA(b, cudaSetDevice(b->device));
+  RG_CUDA(b, rg::launch_reset(b->d, b->stream));
+  b->launches += 1;
+  return RG_OK;
+}
+
+int rg_step(rg_batch* b, const uint8_t* actions_dev, int auto_reset) {
+  if (!b || !actions_dev) return set_err(b, RG_ERR_ARG, "rg_step: null argument");
+  RG_CUDA(b, cudaSetDevice(b->device));
+  RG_CUDA(b, rg::launch_step(b->d, actions_dev, auto_reset, b->stream));
+  b->launches += 1;
+  return RG_OK;
+}
+
+int rg_sync(rg_batch* b) {
+  if (!b) return set_err(b, RG_ERR_ARG, "rg_sync: null batch");
+  RG_CUDA(b, cudaMemcpyAsync(b->h_errflag, b->d.errflag, sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
+  RG_CUDA(b, cudaStreamSynchronize(b->stream));
+  if (*b->h_errflag == 0) return RG_OK;
+  // like the conductor, surface the first failing env's error (thread_impls.rs:65-68)
+  RG_CUDA(b, cudaMemcpyAsync(b->h_error, b->d.error, (size_t)b->n, cudaMemcpyDeviceToHost, b->stream));
+  RG_CUDA(b, cudaMemsetAsync(b->d.errflag, 0, sizeof(uint32_t), b->stream));
+  RG_CUDA(b, cudaStreamSynchronize(b->stream));
+  for (int64_t i = 0; i < b->n; ++i)
+    if (b->h_error[i]) {
+      int code = b->h_error[i];
+      return set_err(b, code, std::string("Error in rogue-gym: ") + status_text(code) + " (env " + std::to_string(i) + ")");
+    }
+  return RG_OK;
+}
+
+int rg_step_host(rg_batch* b, const uint8_t* actions_host, int auto_reset, rg_host_obs* out) {
+  if (!b || !actions_host) return set_err(b, RG_ERR_ARG, "rg_step_host: null argument");
+  RG_CUDA(b, cudaSetDevice(b->device));
+  RG_CUDA(b, cudaMemcpyAsync(b->d_actions, actions_host, (size_t)b->n, cudaMemcpyHostToDevice, b->stream));
+  int rc = rg_step(b, b->d_actions, auto_reset);
+  if (rc != RG_OK) return rc;
+  rc = copy_obs(b, out);
+  if (rc != RG_OK) return rc;
+  return rg_sync(b);
+}
+
+int rg_fetch(rg_batch* b, rg_host_obs* out) {
+  if (!b) return set_err(b, RG_ERR_ARG, "rg_fetch: null batch");
+  RG_CUDA(b, cudaSetDevice(b->device));
+  int rc = copy_obs(b, out);
+  if (rc != RG_OK) return rc;
+  RG_CUDA(b, cudaStreamSynchronize(b->stream));
+  return RG_OK;
+}
+
+int rg_views_get(rg_batch* b, rg_views* out) {
+  if (!b || !out) return set_err(b, RG_ERR_ARG, "rg_views_get: null argument");
+  out->n_envs = b->n;
+  out->width = b->d.W;
+  out->height = b->d.H;
+  out->cell_stride = b->d.CP;
+  out->hist_stride = b->d.HB;
+  out->screen = b->d.screen;
+  out->history_bits = b->d.hist;
+  out->status = b->d.status;
+  out->reward = b->d.reward;
+  out->done = b->d.done;
+  out->message = b->d.message;
+  out->error = b->d.error;
+  return RG_OK;
+}
+
+void* rg_stream(rg_batch* b) { return b ? (void*)b->stream : nullptr; }
+int64_t rg_launch_count(rg_batch* b) { return b ? b->launches : 0; }
+
+int rg_encode_channels(const rg_batch* b, int mode, uint32_t status_flag, int with_hist) {
+  if (!b || (mode != 0 && mode != 1)) return -1;
+  int base = mode == 0 ? 1 : (int)b->P.symbols;
+  return base + __builtin_popcount(status_flag & 0x1FFu) + (with_hist ? 1 : 0);
+}
+
+int rg_encode(rg_batch* b, int mode, uint32_t status_flag, int with_hist, float* out_dev, int* channels) {
+  if (!b || !out_dev) return set_err(b, RG_ERR_ARG, "rg_encode: null argument");
+  int ch = rg_encode_channels(b, mode, status_flag, with_hist);
+  if (ch < 0) return set_err(b, RG_ERR_ARG, "rg_encode: mode must be 0 (gray) or 1 (symbol)");
+  if (channels) *channels = ch;
+  RG_CUDA(b, rg::launch_encode(b->d, mode, status_flag & 0x1FFu, with_hist, ch, out_dev, b->stream));
+  b->launches += 1;
+  return RG_OK;
+}
+
+int rg_state_hash(rg_batch* b, uint64_t* out_host) {
+  if (!b || !out_host) return set_err(b, RG_ERR_ARG, "rg_state_hash: null argument");
+  RG_CUDA(b, cudaSetDevice(b->device));
+  RG_CUDA(b, rg::launch_state_hash(b->d, b->d_u64, b->stream));
+  b->launches += 1;
+  RG_CUDA(b, cudaMemcpyAsync(out_host, b->d_u64, (size_t)b->n * 8, cudaMemcpyDeviceToHost, b->stream));
+  RG_CUDA(b, cudaStreamSynchronize(b->stream));
+  return RG_OK;
+}
+
+int rg_test_move_enemy(rg_batch* b, int64_t env, int fx, int fy, int tx, int ty, int* kind, int* nx, int* ny) {
+  if (!b || env < 0 || env >= b->n) return set_err(b, RG_ERR_ARG, "rg_test_move_enemy: bad env");
+  if (fx < 0 || fy < 0 || fx >= b->d.W || fy >= b->d.H || tx < 0 || ty < 0 || tx >= b->d.W || ty >= b->d.H)
+    return set_err(b, RG_ERR_ARG, "rg_test_move_enemy: coordinate out of range");
+  RG_CUDA(b, cudaSetDevice(b->device));
+  RG_CUDA(b, rg::launch_test_move_enemy(b->d, env, fx, fy, tx, ty, b->d_out3, b->stream));
+  b->launches += 1;
+  int h[3];
+  RG_CUDA(b, cudaMemcpyAsync(h, b->d_out3, sizeof(h), cudaMemcpyDeviceToHost, b->stream));
+  RG_CUDA(b, cudaStreamSynchronize(b->stream));
+  if (kind) *kind = h[0];
+  if (nx) *nx = h[1];
+  if (ny) *ny = h[2];
+  return RG_OK;
+}
+
+int rg_dump_env(rg_batch* b, int64_t env, rg_dump* out) {
+  if (!b || !out || env < 0 || env >= b->n) return set_err(b, RG_ERR_ARG, "rg_dump_env: bad argument");
+  const DevBatch& d = b->d;
+  RG_CUDA(b, cudaSetDevice(b->device));
+  RG_CUDA(b, cudaStreamSynchronize(b->stream));
+  EnvState st;
+  RG_CUDA(b, cudaMemcpy(&st, d.st + env, sizeof(st), cudaMemcpyDeviceToHost));
+  rg_dump_scalars& s = out->s;
+  memset(&s, 0, sizeof(s));
+  s.level = st.level;
+  s.px = st.px;
+  s.py = st.py;
+  s.hp = st.hp;
+  s.hp_max = st.hp_max;
+  s.exp = st.exp;
+  s.plevel = st.plevel;
+  s.food_left = st.food_left;
+  s.quiet = st.quiet;
+  s.gold = st.gold;
+  s.ui_dead = st.ui_dead;
+  s.steps = (int32_t)st.steps;
+  s.is_terminal = st.is_terminal;
+  s.message = st.message;
+  s.error = st.error;
+  s.n_cache = st.cache_n;
+  memcpy(s.status, st.status, sizeof(s.status));
+  memcpy(s.rng, st.rng, sizeof(s.rng));
+  const int nrooms = b->P.room_num_x * b->P.room_num_y;
+  struct M { int x, y, kind, hp, active, level, defense, exp; };
+  std::vector<M> mons;
+  const int la = (int)((uint32_t)st.level > b->P.amulet_level ? (uint32_t)st.level - b->P.amulet_level : 0u);
+  for (int i = 0; i < nrooms; ++i) {
+    const rg::MonD& m = st.mon[i];
+    if (!(m.flags & rg::MF_PRESENT)) continue;
+    const rg_enemy_kind& k = b->P.enemies[m.kind];
+    mons.push_back(M{m.x, m.y, m.kind, m.hp, (m.flags & rg::MF_ACTIVE) ? 1 : 0, k.level + la, k.defense - la, (int)m.exp});
+  }
+  std::sort(mons.begin(), mons.end(), [](const M& a, const M& c) { return a.x != c.x ? a.x < c.x : a.y < c.y; });
+  s.n_monsters = (int32_t)mons.size();
+  if (out->monsters) {
+    memset(out->monsters, 0, sizeof(int32_t) * RG_MAX_ROOMS * 8);
+    for (size_t i = 0; i < mons.size(); ++i) memcpy(out->monsters + i * 8, &mons[i], sizeof(M));
+  }
+  std::vector<std::pair<int, uint32_t>> items;
+  for (int i = 0; i < nrooms; ++i)
+    if (st.item_pos[i] != 0xFFFF) items.push_back({st.item_pos[i], st.item_amt[i]});
+  std::sort(items.begin(), items.end());
+  s.n_items = (int32_t)items.size();
+  if (out->items) {
+    memset(out->items, 0, sizeof(int32_t) * RG_MAX_ROOMS * 3);
+    for (size_t i = 0; i < items.size(); ++i) {
+      out->items[i * 3 + 0] = items[i].first % d.W;
+      out->items[i * 3 + 1] = items[i].first / d.W;
+      out->items[i * 3 + 2] = (int32_t)items[i].second;
+    }
+  }
+  if (out->surface) RG_CUDA(b, cudaMemcpy(out->surface, d.surface + env * d.CP, d.C, cudaMemcpyDeviceToHost));
+  if (out->attr) RG_CUDA(b, cudaMemcpy(out->attr, d.attr + env * d.CP, d.C, cudaMemcpyDeviceToHost));
+  if (out->cache_xy)
+    for (int i = 0; i < RG_DIST_CACHE; ++i) {
+      bool live = i < st.cache_n;
+      int slot = (st.cache_head + i) % RG_DIST_CACHE;
+      out->cache_xy[i * 2] = live ? st.cache_x[slot] : -1;
+      out->cache_xy[i * 2 + 1] = live ? st.cache_y[slot] : -1;
+      if (live && out->cache_maps)
+        RG_CUDA(b, cudaMemcpy(out->cache_maps + (size_t)i * d.C, d.dist + ((size_t)env * RG_DIST_CACHE + slot) * d.CP,
+                              (size_t)d.C * 2, cudaMemcpyDeviceToHost));
+    }
+  if (out->rooms) {
+    memset(out->rooms, 0, sizeof(int32_t) * RG_MAX_ROOMS * 8);
+    for (int i = 0; i < nrooms; ++i) {
+      const rg::RoomD& r = st.rooms[i];
+      int32_t* o = out->rooms + i * 8;
+      o[0] = r.kind;
+      o[1] = (r.flags & rg::RF_DARK) ? 1 : 0;
+      o[2] = (r.flags & rg::RF_VISITED) ? 1 : 0;
+      o[3] = (r.flags & rg::RF_GOLD) ? 1 : 0;
+      o[4] = r.x0;
+      o[5] = r.y0;
+      o[6] = r.x1;
+      o[7] = r.y1;
+    }
+  }
+  return RG_OK;
+}
+
+// PlayerState::{gray,symbol}_image[_with_hist] for detached PlayerState values (python/src/lib.rs:158-205):
+// the states are uploaded, encoded by the same kernel as rg_encode, and the images copied back.
+int rg_encode_states(rg_batch* b, int64_t n, const uint8_t* screens, const uint8_t* history, const uint32_t* status,
+                     int mode, uint32_t status_flag, int with_hist, float* out_host, int* channels) {
+  if (!b || n < 1 || !screens || !status || !out_host || (with_hist && !history))
+    return set_err(b, RG_ERR_ARG, "rg_encode_states: bad argument");
+  int ch = rg_encode_channels(b, mode, status_flag, with_hist);
+  if (ch < 0) return set_err(b, RG_ERR_ARG, "rg_encode_states: mode must be 0 (gray) or 1 (symbol)");
+  if (channels) *channels = ch;
+  RG_CUDA(b, cudaSetDevice(b->device));
+  DevBatch t = b->d;
+  t.n = n;
+  const size_t N = (size_t)n;
+  uint8_t *scr = nullptr, *hist = nullptr, *err = nullptr;
+  uint32_t* st = nullptr;
+  float* out = nullptr;
+  std::vector<uint8_t> packed(N * t.HB, 0);
+  if (history)
+    for (size_t e = 0; e < N; ++e)
+      for (int i = 0; i < t.C; ++i)
+        if (history[e * t.C + i]) packed[e * t.HB + (i >> 3)] |= (uint8_t)(1u << (i & 7));
+  int rc = RG_OK;
+  auto run = [&]() -> cudaError_t {
+    cudaError_t e;
+    if ((e = cudaMalloc(&scr, N * t.CP)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&hist, N * t.HB)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&err, N)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&st, N * 40)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&out, N * (size_t)ch * t.C * sizeof(float))) != cudaSuccess) return e;
+    if ((e = cudaMemcpy2DAsync(scr, t.CP, screens, t.C, t.C, N, cudaMemcpyHostToDevice, b->stream)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(hist, packed.data(), N * t.HB, cudaMemcpyHostToDevice, b->stream)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(st, status, N * 40, cudaMemcpyHostToDevice, b->stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(err, 0, N, b->stream)) != cudaSuccess) return e;
+    t.screen = scr;
+    t.hist = hist;
+    t.status = st;
+    t.error = err;
+    if ((e = rg::launch_encode(t, mode, status_flag & 0x1FFu, with_hist, ch, out, b->stream)) != cudaSuccess) return e;
+    b->launches += 1;
+    if ((e = cudaMemcpyAsync(out_host, out, N * (size_t)ch * t.C * sizeof(float), cudaMemcpyDeviceToHost, b->stream)) !=
+        cudaSuccess)
+      return e;
+    std::vector<uint8_t> herr(N);
+    if ((e = cudaMemcpyAsync(herr.data(), err, N, cudaMemcpyDeviceToHost, b->stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(b->stream)) != cudaSuccess) return e;
+    for (size_t i = 0; i < N; ++i)
+      if (herr[i]) {
+        rc = set_err(b, RG_ERR_SETTING, "Error in rogue-gym: Invalid tile in the screen of state " + std::to_string(i) +
+                                            ", while max is " + std::to_string(b->P.symbols - 1));
+        // this launch raised the shared flag; it is not a step error
+        cudaMemsetAsync(b->d.errflag, 0, sizeof(uint32_t), b->stream);
+        cudaStreamSynchronize(b->stream);
+        break;
+      }
+    return cudaSuccess;
+  };
+  cudaError_t ce = run();
+  cudaFree(scr);
+  cudaFree(hist);
+  cudaFree(err);
+  cudaFree(st);
+  cudaFree(out);
+  if (ce != cudaSuccess) return cuda_fail(b, ce, "rg_encode_states");
+  return rc;
+}
+
+}  // extern "C"

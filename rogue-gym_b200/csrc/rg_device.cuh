@@ -1,0 +1,1336 @@
+// rg_device.cuh — warp-per-env device code of the B200 Rogue-Gym simulator.
+//
+// Execution model. One warp owns one dungeon. The env's tile planes (surface, attr) and its
+// small state live in shared memory while the warp works on it. Code is written in two modes:
+//   * UNIFORM: all 32 lanes execute the same scalar logic on the same data (decisions, RNG
+//     draws with their rejection loops, entity bookkeeping). Every lane computes the same
+//     value, so there is no divergence and no broadcast traffic; stores to shared memory are
+//     same-address/same-value.
+//   * PARALLEL: lanes take different cells / rows / directions / entities (tile fills, room
+//     reveal, bit-parallel BFS with one bitboard row per lane, the 9-neighbour probe of a
+//     monster, screen compose with 128-bit accesses). __syncwarp() separates a PARALLEL write
+//     phase from whatever reads it next.
+// This is a new design, not a translation: the reference's FenwickSets become popcount/nth
+// selects over implicit sets, its BTreeMaps a 16-slot monster table ordered on the fly, its
+// queue BFS a level-synchronous bitboard sweep, and the deferred passage list a two-pass RNG
+// replay. What must stay identical is the observable result and the order of RNG draws; each
+// function cites the reference code whose results it reproduces (/root/reference, c78608b).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rg_types.h"
+
+namespace rg {
+
+#define RG_FULL 0xffffffffu
+#define RG_DEV __device__ __forceinline__
+
+// Direction order Up, Down, Left, Right, LeftUp, RightUp, LeftDown, RightDown, Stay (coord.rs:198-208)
+enum { D_UP = 0, D_DOWN, D_LEFT, D_RIGHT, D_LEFTUP, D_RIGHTUP, D_LEFTDOWN, D_RIGHTDOWN, D_STAY };
+RG_DEV int ddx(int d) { return (int)((0x18885u >> (2 * d)) & 3u) - 1; }
+RG_DEV int ddy(int d) { return (int)((0x1A058u >> (2 * d)) & 3u) - 1; }
+RG_DEV bool is_diag(int d) { return d >= D_LEFTUP && d <= D_RIGHTDOWN; }
+RG_DEV int reverse_dir(int d) { return (int)((0x845672301ull >> (4 * d)) & 15ull); }  // coord.rs:272-285
+RG_DEV bool can_walk(uint8_t s) { return !(s == S_WALLX || s == S_WALLY || s == S_NONE); }  // rogue/mod.rs:176-183
+RG_DEV uint8_t surface_tile(uint8_t s) { return (uint8_t)(0x205E2B257C2D2E23ull >> (8 * s)); }  // rogue/mod.rs:148-161
+
+// ------------------------------------------------------------------ RNG
+// xorshift128 (rand_xorshift 0.2) + rand 0.7 UniformInt::sample_single; reference wrapper: rng.rs:47-98
+struct Rng {
+  uint32_t x, y, z, w;
+  RG_DEV void load(const uint32_t* p) { x = p[0]; y = p[1]; z = p[2]; w = p[3]; }
+  RG_DEV void store(uint32_t* p) const { p[0] = x; p[1] = y; p[2] = z; p[3] = w; }
+  RG_DEV void seed(const uint32_t* s) {
+    x = s[0]; y = s[1]; z = s[2]; w = s[3];
+    if ((x | y | z | w) == 0) x = y = z = w = 0x0BAD5EEDu;
+  }
+  RG_DEV uint32_t next() {
+    uint32_t t = x ^ (x << 11);
+    x = y; y = z; z = w;
+    w = w ^ (w >> 19) ^ (t ^ (t >> 8));
+    return w;
+  }
+  RG_DEV uint64_t next64() {
+    uint64_t lo = next();
+    uint64_t hi = next();
+    return (hi << 32) | lo;
+  }
+  // 32-bit lane: u32 and i32 call sites (lo/hi are wrapping)
+  RG_DEV uint32_t range32(uint32_t lo, uint32_t hi) {
+    uint32_t range = hi - lo;
+    uint32_t zone = (range << __clz(range)) - 1u;
+    for (;;) {
+      uint32_t v = next();
+      uint32_t l = v * range;
+      if (l <= zone) return lo + __umulhi(v, range);
+    }
+  }
+  RG_DEV int range_i32(int lo, int hi) { return (int)range32((uint32_t)lo, (uint32_t)hi); }
+  // 64-bit lane: usize / i64 call sites
+  RG_DEV uint64_t range64(uint64_t lo, uint64_t hi) {
+    uint64_t range = hi - lo;
+    uint64_t zone = (range << __clzll(range)) - 1ull;
+    for (;;) {
+      uint64_t v = next64();
+      uint64_t l = v * range;
+      if (l <= zone) return lo + __umul64hi(v, range);
+    }
+  }
+  RG_DEV bool does_happen(uint32_t p_inv) { return range32(0, p_inv) == 0; }  // rng.rs:91-93
+  RG_DEV bool parcent(uint32_t p) { return range32(1, 101) <= p; }            // rng.rs:95-98
+};
+
+RG_DEV int nth_set_bit(uint32_t m, uint32_t n) {
+  for (uint32_t i = 0; i < n; ++i) m &= m - 1;
+  return __ffs(m) - 1;
+}
+
+// ------------------------------------------------------------------ per-warp context
+struct Ctx {
+  uint8_t* S;         // smem surface plane [CP]
+  uint8_t* A;         // smem attr plane [CP]
+  EnvState* st;       // smem
+  const rg_params* P; // global (read-only)
+  int W, H, C, CP, WW;
+  int lane;
+  int nx, ny, rsx, rsy, nrooms;
+  uint8_t* g_screen;  // this env's slices in HBM
+  uint8_t* g_hist;
+  uint32_t* g_walk;
+  uint16_t* g_dist;
+  Rng rd, ri, re;     // dungeon / item / enemy streams (registers)
+  // per-step reaction summary (state_impls.rs:57-75 collapses to these)
+  uint32_t redraw, status_upd, dead, msg, hist_done, a_dirty, s_dirty, panic;
+};
+
+RG_DEV void set_panic(Ctx& c) { c.panic = 1; }
+
+// Room grid geometry: rooms.rs:176,191-206
+RG_DEV void room_area(const Ctx& c, int i, int& ax0, int& ay0, int& ax1, int& ay1) {
+  int xi = i % c.nx, yi = i / c.nx;
+  int ry = c.rsy;
+  if (yi == 0) {
+    ry -= 1;
+    ay0 = 1;
+  } else {
+    ay0 = ry * yi;
+  }
+  ax0 = c.rsx * xi;
+  if (ay0 + ry == c.H) ry -= 1;
+  ax1 = ax0 + c.rsx;
+  ay1 = ay0 + ry;
+}
+// Floor::cd_to_room_id floor.rs:194-200 (areas are disjoint, so "first" = "the")
+RG_DEV int room_of(const Ctx& c, int x, int y) {
+  if (x < 0 || y < 0) return -1;
+  int xi = x / c.rsx, yi = y / c.rsy;
+  if (xi >= c.nx || yi >= c.ny) return -1;
+  int i = yi * c.nx + xi;
+  int ax0, ay0, ax1, ay1;
+  room_area(c, i, ax0, ay0, ax1, ay1);
+  return (x >= ax0 && x < ax1 && y >= ay0 && y < ay1) ? i : -1;
+}
+RG_DEV bool in_rect(const RoomD& r, int x, int y) { return x >= r.x0 && x < r.x1 && y >= r.y0 && y < r.y1; }
+RG_DEV bool inb(const Ctx& c, int x, int y) { return x >= 0 && y >= 0 && x < c.W && y < c.H; }
+RG_DEV uint32_t lev_add(const Ctx& c) {  // rogue/mod.rs:483-489
+  uint32_t lv = (uint32_t)c.st->level;
+  return c.P->amulet_level < lv ? lv - c.P->amulet_level : 0u;
+}
+
+// Floor::can_move_impl floor.rs:169-182
+RG_DEV bool can_move(const Ctx& c, int x, int y, int d, bool is_enemy) {
+  int nx = x + ddx(d), ny = y + ddy(d);
+  if (!inb(c, nx, ny)) return false;
+  int ni = ny * c.W + nx;
+  bool res = can_walk(c.S[ni]);
+  if (!is_enemy) res = res && !(c.A[ni] & (A_HIDDEN | A_LOCKED));
+  if (is_diag(d)) {
+    res = res && can_walk(c.S[y * c.W + nx]);
+    res = res && can_walk(c.S[ny * c.W + x]);
+  }
+  return res;
+}
+
+// ------------------------------------------------------------------ floor generation
+// maze::dig_maze / dig_impl maze.rs:38-89. The recursion is an explicit stack kept in this
+// env's (not yet composed) screen slice; membership = A_MARK.
+__device__ int dig_maze(Ctx& c, Rng& r, int x0, int y0, int x1, int y1) {
+  uint16_t* stack = reinterpret_cast<uint16_t*>(c.g_screen);
+  const int W = c.W;
+  int sp = 0, n = 1;
+  int cx = x0, cy = y0;
+  c.A[cy * W + cx] |= A_MARK;
+  const int max_sp = c.CP / 2;
+  for (;;) {
+    int pick = -1;
+    uint32_t k = 0;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      int tx = cx + 2 * ddx(d), ty = cy + 2 * ddy(d);
+      if (tx >= x0 && tx < x1 && ty >= y0 && ty < y1 && !(c.A[ty * W + tx] & A_MARK)) {
+        if (r.does_happen(k + 1)) pick = d;  // reservoir pick: every candidate draws (maze.rs:64-75)
+        ++k;
+      }
+    }
+    if (pick < 0) {
+      if (sp == 0) break;
+      uint16_t v = stack[--sp];
+      cx = v & 0xff;
+      cy = v >> 8;
+      continue;
+    }
+    for (int s = 1; s <= 2; ++s) {
+      int mi = (cy + s * ddy(pick)) * W + cx + s * ddx(pick);
+      if (!(c.A[mi] & A_MARK)) {
+        c.A[mi] |= A_MARK;
+        ++n;
+      }
+    }
+    if (sp >= max_sp) {
+      set_panic(c);
+      break;
+    }
+    stack[sp++] = (uint16_t)(cx | (cy << 8));
+    cx += 2 * ddx(pick);
+    cy += 2 * ddy(pick);
+  }
+  return n;
+}
+
+// rooms::gen_rooms + make_room rooms.rs:165-269 (geometry and RNG only; tiles are laid later)
+__device__ void gen_rooms(Ctx& c, Rng& r, uint32_t level) {
+  const rg_params& P = *c.P;
+  const int nrooms = c.nrooms;
+  uint32_t empty_num = r.range32(0, P.max_empty_rooms + 1);
+  if (empty_num >= (uint32_t)nrooms) empty_num = (uint32_t)nrooms - 1;
+  uint32_t rest = (nrooms >= 32) ? RG_FULL : ((1u << nrooms) - 1u), empty_mask = 0;
+  for (uint32_t i = 0; i < empty_num; ++i) {  // RandomSelecter rng.rs:129-143
+    uint32_t cnt = __popc(rest);
+    if (!cnt) break;
+    uint32_t n = (uint32_t)r.range64(0, cnt);
+    int b = nth_set_bit(rest, n);
+    rest &= ~(1u << b);
+    empty_mask |= 1u << b;
+  }
+  for (int i = 0; i < nrooms; ++i) {
+    int ax0, ay0, ax1, ay1;
+    room_area(c, i, ax0, ay0, ax1, ay1);
+    int sx = ax1 - ax0, sy = ay1 - ay0;
+    RoomD rm;
+    rm.ncells = 0;
+    if ((empty_mask >> i) & 1u) {
+      int x = r.range_i32(1, sx - 1) + ax0;
+      int y = r.range_i32(1, sy - 1) + ay0;
+      rm.kind = K_EMPTY;
+      rm.flags = RF_DARK;
+      rm.x0 = rm.x1 = (uint8_t)x;
+      rm.y0 = rm.y1 = (uint8_t)y;
+    } else {
+      bool dark = r.range32(0, P.dark_level) < level;
+      rm.flags = dark ? RF_DARK : 0;
+      if (dark && r.does_happen(P.maze_rate_inv)) {
+        rm.kind = K_MAZE;
+        rm.x0 = (uint8_t)ax0;
+        rm.y0 = (uint8_t)ay0;
+        rm.x1 = (uint8_t)(ax1 - 1);
+        rm.y1 = (uint8_t)(ay1 - 1);
+        rm.ncells = (uint16_t)dig_maze(c, r, ax0, ay0, ax1 - 1, ay1 - 1);
+      } else {
+        rm.kind = K_NORMAL;
+        int w = r.range_i32(P.min_room_x, sx);
+        int h = r.range_i32(P.min_room_y, sy);
+        int lx = r.range_i32(0, sx - w) + ax0;
+        int ly = r.range_i32(0, sy - h) + ay0;
+        rm.x0 = (uint8_t)lx;
+        rm.y0 = (uint8_t)ly;
+        rm.x1 = (uint8_t)(lx + w);
+        rm.y1 = (uint8_t)(ly + h);
+      }
+    }
+    c.st->rooms[i] = rm;
+  }
+}
+
+// Room::draw + gen_attr for room tiles: floor.rs:61-71,420-451, rooms.rs:58-82
+__device__ void lay_rooms(Ctx& c, Rng& r, uint32_t level) {
+  const rg_params& P = *c.P;
+  const int W = c.W;
+  for (int i = 0; i < c.nrooms; ++i) {
+    RoomD rm = c.st->rooms[i];
+    if (rm.kind == K_NORMAL) {  // PARALLEL: no RNG is consumed by wall / floor tiles
+      int w = rm.x1 - rm.x0, n = w * (rm.y1 - rm.y0);
+      uint8_t fl = (rm.flags & RF_DARK) ? A_DARK : 0;
+      for (int k = c.lane; k < n; k += 32) {
+        int x = rm.x0 + k % w, y = rm.y0 + k / w;
+        bool he = (y == rm.y0 || y == rm.y1 - 1), ve = (x == rm.x0 || x == rm.x1 - 1);
+        c.S[y * W + x] = he ? S_WALLX : (ve ? S_WALLY : S_FLOOR);
+        c.A[y * W + x] = (he || ve) ? 0 : fl;
+      }
+      __syncwarp();
+    } else if (rm.kind == K_MAZE) {  // UNIFORM: each passage cell rolls gen_attr in index order
+      for (int y = rm.y0; y < rm.y1; ++y)
+        for (int x = rm.x0; x < rm.x1; ++x) {
+          int idx = y * W + x;
+          if (!(c.A[idx] & A_MARK)) continue;
+          uint8_t attr = 0;
+          if (r.range32(0, P.dark_level) < level && r.does_happen(P.hidden_passage_rate_inv)) attr = A_HIDDEN;
+          c.S[idx] = S_PASSAGE;
+          c.A[idx] = A_MARK | attr;
+        }
+    }
+  }
+}
+
+// floor.rs:85-102: one registered passage cell; `ra` is the attribute stream of the replay
+RG_DEV void apply_passage_cell(Ctx& c, Rng& ra, int x, int y, uint8_t surface, uint32_t level) {
+  const rg_params& P = *c.P;
+  int idx = y * c.W + x;
+  if (!inb(c, x, y)) {
+    set_panic(c);
+    return;
+  }
+  uint8_t keep = c.A[idx] & (A_DOOR | A_MARK);
+  uint8_t attr = 0;
+  if (surface == S_DOOR) {
+    keep |= A_DOOR;
+    if (ra.range32(0, P.dark_level) < level && ra.does_happen(P.locked_door_rate_inv)) attr = A_LOCKED;
+  } else {
+    if (ra.range32(0, P.dark_level) < level && ra.does_happen(P.hidden_passage_rate_inv)) attr = A_HIDDEN;
+  }
+  c.A[idx] = keep | attr;
+  if (!attr) c.S[idx] = surface;
+}
+
+// passages::select_start_or_end + edges passages.rs:143-219
+__device__ void select_start_or_end(Ctx& c, Rng& r, int room, int d, int& ox, int& oy) {
+  RoomD rm = c.st->rooms[room];
+  if (rm.kind == K_NORMAL) {  // edges(range, d, inclusive) then SliceRandom::choose (usize lane)
+    if (d == D_DOWN || d == D_UP) {
+      int len = rm.x1 - rm.x0 - 2;
+      int i = (int)r.range64(0, (uint64_t)len);
+      ox = rm.x0 + 1 + i;
+      oy = (d == D_DOWN) ? rm.y1 - 1 : rm.y0;
+    } else {
+      int len = rm.y1 - rm.y0 - 2;
+      int i = (int)r.range64(0, (uint64_t)len);
+      oy = rm.y0 + 1 + i;
+      ox = (d == D_RIGHT) ? rm.x1 - 1 : rm.x0;
+    }
+    return;
+  }
+  if (rm.kind == K_EMPTY) {
+    ox = rm.x0;
+    oy = rm.y0;
+    return;
+  }
+  // maze: shrink from the far side until an edge line holds a passage cell (passages.rs:149-176)
+  int x0 = rm.x0, y0 = rm.y0, x1 = rm.x1, y1 = rm.y1;
+  const int W = c.W;
+  while (x0 < x1 && y0 < y1) {
+    bool horiz = (d == D_DOWN || d == D_UP);
+    int fix = (d == D_DOWN) ? y1 - 1 : (d == D_UP) ? y0 : (d == D_RIGHT) ? x1 - 1 : x0;
+    int lo = horiz ? x0 : y0, hi = horiz ? x1 : y1;
+    int cnt = 0;
+    for (int t = lo; t < hi; ++t) {
+      int x = horiz ? t : fix, y = horiz ? fix : t;
+      // Maze::has_cd tests membership in the ORIGINAL range (maze.rs:25-31)
+      if (in_rect(rm, x, y) && (c.A[y * W + x] & A_MARK)) ++cnt;
+    }
+    if (cnt) {
+      int n = (int)r.range64(0, (uint64_t)cnt);
+      for (int t = lo; t < hi; ++t) {
+        int x = horiz ? t : fix, y = horiz ? fix : t;
+        if (in_rect(rm, x, y) && (c.A[y * W + x] & A_MARK)) {
+          if (n == 0) {
+            ox = x;
+            oy = y;
+            return;
+          }
+          --n;
+        }
+      }
+    }
+    if (d == D_DOWN) --y1;
+    else if (d == D_LEFT) --x0;
+    else if (d == D_RIGHT) --x1;
+    else --y0;
+    if (x0 < 0 || y0 < 0) break;
+  }
+  set_panic(c);  // "cannot find maze floor"
+  ox = rm.x0;
+  oy = rm.y0;
+}
+
+// passages::connect_2rooms passages.rs:84-133
+template <bool APPLY>
+__device__ void connect_2rooms(Ctx& c, Rng& rd, Rng& ra, int r1, int r2, int d, uint32_t level) {
+  if (d == D_UP || d == D_LEFT) {
+    int t = r1; r1 = r2; r2 = t;
+    d = reverse_dir(d);
+  }
+  int sx, sy, ex, ey;
+  select_start_or_end(c, rd, r1, d, sx, sy);
+  select_start_or_end(c, rd, r2, reverse_dir(d), ex, ey);
+  if (APPLY) {
+    apply_passage_cell(c, ra, sx, sy, c.st->rooms[r1].kind == K_NORMAL ? S_DOOR : S_PASSAGE, level);
+    apply_passage_cell(c, ra, ex, ey, c.st->rooms[r2].kind == K_NORMAL ? S_DOOR : S_PASSAGE, level);
+  }
+  int tsx, tsy, tex, tey, tdir;
+  if (d == D_DOWN) {
+    if (!(sy + 1 < ey)) { set_panic(c); return; }
+    int y = rd.range_i32(sy + 1, ey);
+    tdir = (sx < ex) ? D_RIGHT : D_LEFT;
+    tsx = sx; tsy = y; tex = ex; tey = y;
+  } else {
+    if (!(sx + 1 < ex)) { set_panic(c); return; }
+    int x = rd.range_i32(sx + 1, ex);
+    tdir = (sy < ey) ? D_DOWN : D_UP;
+    tsx = x; tsy = sy; tex = x; tey = ey;
+  }
+  if (APPLY) {
+    int guard = c.W + c.H + 4;
+    int x = sx + ddx(d), y = sy + ddy(d);  // .skip(1)
+    for (; (x != tsx || y != tsy) && guard > 0; x += ddx(d), y += ddy(d), --guard)
+      apply_passage_cell(c, ra, x, y, S_PASSAGE, level);
+    for (x = tsx, y = tsy; (x != tex || y != tey) && guard > 0; x += ddx(tdir), y += ddy(tdir), --guard)
+      apply_passage_cell(c, ra, x, y, S_PASSAGE, level);
+    for (x = tex, y = tey; (x != ex || y != ey) && guard > 0; x += ddx(d), y += ddy(d), --guard)
+      apply_passage_cell(c, ra, x, y, S_PASSAGE, level);
+    if (guard <= 0) set_panic(c);
+  }
+}
+
+RG_DEV int adj_dir(const Ctx& c, int a, int i) {  // Node::candidates passages.rs:252-262
+  int ax = a % c.nx, ay = a / c.nx, ix = i % c.nx, iy = i / c.nx;
+  if (ix == ax && iy == ay - 1) return D_UP;
+  if (ix == ax && iy == ay + 1) return D_DOWN;
+  if (iy == ay && ix == ax - 1) return D_LEFT;
+  if (iy == ay && ix == ax + 1) return D_RIGHT;
+  return -1;
+}
+
+// passages::dig_passges passages.rs:16-67. The reference collects every registered cell and
+// rolls their attributes afterwards (floor.rs:73-102); here the dig runs twice from the same
+// RNG snapshot: a dry run that only advances the stream, then a replay that lays tiles while a
+// second stream (starting where the dry run ended) rolls the attributes. Same draws, same
+// order, no cell list.
+template <bool APPLY>
+__device__ void dig_passages(Ctx& c, Rng& rd, Rng& ra, uint32_t level) {
+  const int n = c.nrooms;
+  uint64_t conn = 0;  // bit room*4+dir : connected to the neighbour in that direction
+  uint32_t selected;
+  int cur = (int)rd.range64(0, (uint64_t)n);
+  selected = 1u << cur;
+  int guard = 4096;
+  while (__popc(selected) < n && --guard > 0) {
+    int pick = -1, pdir = 0;
+    uint32_t k = 0;
+    for (int i = 0; i < n; ++i) {  // select_candidate passages.rs:69-82
+      if ((selected >> i) & 1u) continue;
+      int d = adj_dir(c, cur, i);
+      if (d < 0) continue;
+      if (rd.does_happen(k + 1)) { pick = i; pdir = d; }
+      ++k;
+    }
+    if (pick >= 0) {
+      selected |= 1u << pick;
+      conn |= 1ull << (cur * 4 + pdir);
+      conn |= 1ull << (pick * 4 + reverse_dir(pdir));
+      connect_2rooms<APPLY>(c, rd, ra, cur, pick, pdir, level);
+    } else {
+      uint32_t cnt = __popc(selected);
+      cur = nth_set_bit(selected, (uint32_t)rd.range64(0, cnt));
+    }
+    if (c.panic) return;
+  }
+  if (guard <= 0) { set_panic(c); return; }
+  uint32_t try_num = rd.range32(0, c.P->max_extra_edges);
+  for (uint32_t t = 0; t < try_num; ++t) {
+    int room1 = (int)rd.range64(0, (uint64_t)n);
+    int pick = -1, pdir = 0;
+    uint32_t k = 0;
+    for (int i = 0; i < n; ++i) {
+      int d = adj_dir(c, room1, i);
+      if (d < 0) continue;
+      if ((conn >> (room1 * 4 + d)) & 1ull) continue;
+      if (rd.does_happen(k + 1)) { pick = i; pdir = d; }
+      ++k;
+    }
+    if (pick >= 0) {
+      conn |= 1ull << (room1 * 4 + pdir);
+      conn |= 1ull << (pick * 4 + reverse_dir(pdir));
+      connect_2rooms<APPLY>(c, rd, ra, room1, pick, pdir, level);
+    }
+    if (c.panic) return;
+  }
+}
+
+// Room::select_cell rooms.rs:132-144 over the implicit set "free cells of this room":
+// interior floor cells (normal) or marked cells (maze), minus at most one occupied cell
+// (`excl`, a cell index or -1). During generation a room's set never loses more than one
+// member before it is sampled (see DESIGN.md "implicit cell sets").
+__device__ int select_in_room(Ctx& c, Rng& r, int room, int excl) {
+  RoomD rm = c.st->rooms[room];
+  const int W = c.W;
+  if (rm.kind == K_EMPTY) return -1;
+  if (rm.kind == K_NORMAL) {
+    int iw = rm.x1 - rm.x0 - 2, ih = rm.y1 - rm.y0 - 2;
+    int cnt = iw * ih - (excl >= 0 ? 1 : 0);
+    if (cnt <= 0) return -1;
+    int n = (int)r.range64(0, (uint64_t)cnt);  // FenwickSet::select (usize lane) fenwick.rs:90-96
+    if (excl >= 0) {
+      int eo = (excl % W - rm.x0 - 1) + (excl / W - rm.y0 - 1) * iw;
+      if (n >= eo) ++n;
+    }
+    return (rm.y0 + 1 + n / iw) * W + rm.x0 + 1 + n % iw;
+  }
+  int cnt = (int)rm.ncells - (excl >= 0 ? 1 : 0);
+  if (cnt <= 0) return -1;
+  int n = (int)r.range64(0, (uint64_t)cnt);
+  for (int y = rm.y0; y < rm.y1; ++y)
+    for (int x = rm.x0; x < rm.x1; ++x) {
+      int idx = y * W + x;
+      if (!(c.A[idx] & A_MARK) || idx == excl) continue;
+      if (n == 0) return idx;
+      --n;
+    }
+  set_panic(c);
+  return -1;
+}
+
+// Floor::select_cell floor.rs:333-346. excl_kind: 0 = occupied by this room's gold (object set),
+// 1 = occupied by this room's monster (character set)
+__device__ int select_in_floor(Ctx& c, Rng& r, int excl_kind) {
+  uint32_t cand = 0;
+  for (int i = 0; i < c.nrooms; ++i)
+    if (c.st->rooms[i].kind != K_EMPTY) cand |= 1u << i;
+  while (cand) {
+    uint32_t cnt = __popc(cand);
+    int room = nth_set_bit(cand, (uint32_t)r.range64(0, cnt));
+    int excl = -1;
+    if (excl_kind == 0) {
+      if (c.st->item_pos[room] != 0xFFFF) excl = c.st->item_pos[room];
+    } else {
+      MonD m = c.st->mon[room];
+      if (m.flags & MF_PRESENT) excl = m.y * c.W + m.x;
+    }
+    int pos = select_in_room(c, r, room, excl);
+    if (pos >= 0) return pos;
+    cand &= ~(1u << room);
+  }
+  return -1;
+}
+
+// EnemyHandler::gen_enemy / select / exp_add enemies.rs:265-320
+__device__ bool gen_enemy(Ctx& c, Rng& re, uint32_t rmin, uint32_t rmax, bool has_gold, MonD& out) {
+  const rg_params& P = *c.P;
+  if (!re.parcent(has_gold ? P.appear_rate_gold : P.appear_rate_nogold)) return false;
+  uint32_t len = P.n_enemies;
+  uint32_t idx = re.range32(rmin, rmax);
+  if (idx > len) {
+    uint32_t rr = len < 5 ? len : 5;
+    idx = (uint32_t)re.range64(len - rr, len);
+  }
+  if (idx >= len) return false;
+  const rg_enemy_kind& k = P.enemies[idx];
+  int la = (int)lev_add(c);
+  int lvl = k.level + la;
+  int hp = 0;
+  for (int i = 0; i < 8; ++i) hp += (int)re.range64(1, (uint64_t)(lvl + 1));
+  int base = (lvl == 1) ? hp / 8 : hp / 6;
+  uint32_t add = (10 <= lvl) ? (uint32_t)base * 20u : (uint32_t)base * 4u;
+  out.kind = (uint8_t)idx;
+  out.flags = MF_PRESENT;
+  out.hp = hp;
+  out.exp = k.exp + (uint32_t)(la * 10) + add;
+  return true;
+}
+
+// ------------------------------------------------------------------ visibility ("FOV")
+// Floor::enters_room floor.rs:231-247 (+ activate_area from player_in :273-279)
+__device__ void enters_room(Ctx& c, int x, int y) {
+  int id = room_of(c, x, y);
+  if (id < 0) { set_panic(c); return; }
+  RoomD rm = c.st->rooms[id];
+  if (!(rm.flags & RF_VISITED)) {
+    c.st->rooms[id].flags = rm.flags | RF_VISITED;
+    if (rm.kind == K_NORMAL && !(rm.flags & RF_DARK)) {
+      int w = rm.x1 - rm.x0, n = w * (rm.y1 - rm.y0);
+      for (int k = c.lane; k < n; k += 32) c.A[(rm.y0 + k / w) * c.W + rm.x0 + k % w] |= (A_DRAWN | A_VISIBLE);
+      __syncwarp();
+    }
+  }
+  // EnemyHandler::activate_area enemies.rs:342-355: placed MEAN monsters inside the assigned area
+  for (int m = 0; m < c.nrooms; ++m) {
+    MonD mo = c.st->mon[m];
+    if ((mo.flags & MF_PRESENT) && !(mo.flags & MF_ACTIVE) && (c.P->enemies[mo.kind].attr & EA_MEAN) &&
+        room_of(c, mo.x, mo.y) == id)
+      c.st->mon[m].flags = mo.flags | MF_ACTIVE;
+  }
+}
+// Floor::leaves_room floor.rs:250-261
+__device__ void leaves_room(Ctx& c, int x, int y) {
+  int id = room_of(c, x, y);
+  if (id < 0) { set_panic(c); return; }
+  RoomD rm = c.st->rooms[id];
+  if (!((rm.flags & RF_VISITED) && (rm.flags & RF_DARK))) return;
+  int x0 = rm.x0, y0 = rm.y0, x1 = rm.x1, y1 = rm.y1;
+  if (rm.kind == K_EMPTY) room_area(c, id, x0, y0, x1, y1);
+  int w = x1 - x0 - 2, h = y1 - y0 - 2;
+  if (w <= 0 || h <= 0) return;
+  for (int k = c.lane; k < w * h; k += 32) c.A[(y0 + 1 + k / w) * c.W + x0 + 1 + k % w] &= (uint8_t)~A_VISIBLE;
+  __syncwarp();
+}
+// Floor::player_in floor.rs:264-295 ; Cell::approached field.rs:20-26
+__device__ void player_in(Ctx& c, int x, int y, bool init) {
+  const int W = c.W;
+  if (init || (c.A[y * W + x] & A_DOOR)) enters_room(c, x, y);
+  c.A[y * W + x] |= A_VISITED;
+#pragma unroll
+  for (int d = 0; d < 9; ++d) {
+    int nx = x + ddx(d), ny = y + ddy(d);
+    if (!inb(c, nx, ny)) continue;
+    int idx = ny * W + nx;
+    if (is_diag(d) && c.S[idx] == S_PASSAGE) continue;
+    uint8_t a = c.A[idx];
+    if (a & A_HIDDEN) continue;
+    c.A[idx] = a | A_DRAWN | A_VISIBLE;
+  }
+  c.a_dirty = 1;
+}
+// Floor::player_out floor.rs:298-312 ; Cell::left field.rs:30-34
+__device__ void player_out(Ctx& c, int x, int y) {
+  const int W = c.W;
+  if (c.A[y * W + x] & A_DOOR) leaves_room(c, x, y);
+#pragma unroll
+  for (int d = 0; d < 9; ++d) {
+    int nx = x + ddx(d), ny = y + ddy(d);
+    if (!inb(c, nx, ny)) continue;
+    int idx = ny * W + nx;
+    if (c.S[idx] == S_FLOOR && (c.A[idx] & A_DARK)) c.A[idx] &= (uint8_t)~A_VISIBLE;
+  }
+  c.a_dirty = 1;
+}
+
+// Build the monster-walkable bitboard rows from the surface plane (one ballot per 32 cells).
+__device__ void build_walk(Ctx& c) {
+  __syncwarp();
+  for (int row = 0; row < c.H; ++row)
+    for (int w = 0; w < c.WW; ++w) {
+      int x = w * 32 + c.lane;
+      bool b = x < c.W && can_walk(c.S[row * c.W + x]);
+      uint32_t m = __ballot_sync(RG_FULL, b);
+      if (c.lane == 0) c.g_walk[row * c.WW + w] = m;
+    }
+  __syncwarp();
+}
+
+// rogue::Dungeon::new_level_ rogue/mod.rs:434-481 + Floor::gen_floor floor.rs:50-104
+// + setup_items :132-153 + setup_stair :156-167 + place_enemies :106-130,
+// then actions::new_level's player placement (actions.rs:134-137).
+__device__ __noinline__ void new_level(Ctx* cp, bool is_initial) {
+  Ctx& c = *cp;
+  const rg_params& P = *c.P;
+  EnvState* st = c.st;
+  const int W = c.W;
+  if (!is_initial) {
+    // The descending step shows the visited map of the floor being left:
+    // emit it now, before the planes are overwritten.
+    __syncwarp();
+    for (int ch = c.lane; ch < c.CP / 16; ch += 32) {
+      uint4 a = *reinterpret_cast<const uint4*>(c.A + ch * 16);
+      uint32_t v[4] = {a.x, a.y, a.z, a.w};
+      uint32_t bits = 0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) bits |= ((v[k >> 2] >> (8 * (k & 3))) & 1u) << k;
+      reinterpret_cast<uint16_t*>(c.g_hist)[ch] = (uint16_t)bits;
+    }
+    c.hist_done = 1;
+  }
+  st->level += 1;
+  const uint32_t level = (uint32_t)st->level;
+  // fresh field
+  __syncwarp();
+  for (int ch = c.lane; ch < c.CP / 16; ch += 32) {
+    *reinterpret_cast<uint4*>(c.S + ch * 16) = make_uint4(0x07070707u, 0x07070707u, 0x07070707u, 0x07070707u);
+    *reinterpret_cast<uint4*>(c.A + ch * 16) = make_uint4(0, 0, 0, 0);
+  }
+  __syncwarp();
+  Rng rd = c.rd;
+  gen_rooms(c, rd, level);
+  lay_rooms(c, rd, level);
+  {  // two-pass passage dig (see dig_passages)
+    Rng dry = rd, none = rd;
+    dig_passages<false>(c, dry, none, level);
+    Rng ra = dry;
+    dig_passages<true>(c, rd, ra, level);
+    rd = ra;
+  }
+  // Floor::setup_items: cell from the dungeon stream, amount from the item stream (gold.rs:18-24)
+  Rng ri = c.ri;
+  for (int i = 0; i < c.nrooms; ++i) {
+    st->item_pos[i] = 0xFFFF;
+    st->item_amt[i] = 0;
+  }
+  for (int i = 0; i < c.nrooms; ++i) {
+    int pos = select_in_room(c, rd, i, -1);
+    if (pos < 0) continue;
+    if (!ri.does_happen(P.gold_rate_inv)) continue;
+    uint32_t num = ri.range32(0, P.gold_base + P.gold_per_level * level) + P.gold_minimum;
+    st->item_pos[i] = (uint16_t)pos;
+    st->item_amt[i] = num;
+    st->rooms[i].flags |= RF_GOLD;
+  }
+  c.ri = ri;
+  {  // Floor::setup_stair
+    int pos = select_in_floor(c, rd, 0);
+    if (pos < 0) set_panic(c);
+    else c.S[pos] = S_STAIR;
+  }
+  for (int i = 0; i < MAX_ROOMS; ++i) st->mon[i].flags = 0;  // remove_enemies (a fresh handler is empty too)
+  if (P.n_enemies != 0) {  // Floor::place_enemies
+    Rng re = c.re;
+    uint32_t mn = level >= 4 ? level - 4 : 0, mx = level + 6;
+    for (int i = 0; i < c.nrooms; ++i) {
+      int pos = select_in_room(c, rd, i, -1);
+      if (pos < 0) continue;
+      MonD m;
+      if (gen_enemy(c, re, mn, mx, (st->rooms[i].flags & RF_GOLD) != 0, m)) {
+        m.x = (uint8_t)(pos % W);
+        m.y = (uint8_t)(pos / W);
+        st->mon[i] = m;
+      }
+    }
+    c.re = re;
+  }
+  if (!P.hide_dungeon) {  // rogue/mod.rs:465-475
+    __syncwarp();
+    for (int k = W + c.lane; k < (c.H - 1) * W; k += 32) c.A[k] |= A_VISIBLE;
+    __syncwarp();
+  }
+  if (is_initial) {  // Player::init_items -> weapon.rs:159 draws on the item stream (core/src/lib.rs:206-207)
+    Rng r2 = c.ri;
+    for (uint32_t i = 0; i < P.n_init_draws; ++i) r2.range32(P.init_draw_lo[i], P.init_draw_hi[i]);
+    c.ri = r2;
+  }
+  int ppos = select_in_floor(c, rd, 1);
+  c.rd = rd;
+  if (ppos < 0) { set_panic(c); ppos = W + 1; }
+  st->px = (int16_t)(ppos % W);
+  st->py = (int16_t)(ppos / W);
+  __syncwarp();
+  for (int k = c.lane; k < c.CP; k += 32) c.A[k] &= (uint8_t)~A_MARK;
+  __syncwarp();
+  build_walk(c);
+  player_in(c, st->px, st->py, true);
+  c.a_dirty = 1;
+  c.s_dirty = 1;
+}
+
+// ------------------------------------------------------------------ BFS distance map
+// Floor::make_dist_map floor.rs:395-416 (8-dir, monster rules, diagonal needs both orthogonal
+// neighbours walkable) as a level-synchronous bitboard sweep: lane r owns row r (and r+32).
+template <int WORDS>
+RG_DEV void shl1(const uint32_t (&a)[WORDS], uint32_t (&o)[WORDS]) {
+#pragma unroll
+  for (int w = WORDS - 1; w > 0; --w) o[w] = (a[w] << 1) | (a[w - 1] >> 31);
+  o[0] = a[0] << 1;
+}
+template <int WORDS>
+RG_DEV void shr1(const uint32_t (&a)[WORDS], uint32_t (&o)[WORDS]) {
+#pragma unroll
+  for (int w = 0; w < WORDS - 1; ++w) o[w] = (a[w] >> 1) | (a[w + 1] << 31);
+  o[WORDS - 1] = a[WORDS - 1] >> 1;
+}
+template <int WORDS, int RPL>
+RG_DEV void rows_up(const uint32_t (&X)[RPL][WORDS], uint32_t (&O)[RPL][WORDS], int lane) {  // O[row] = X[row-1]
+#pragma unroll
+  for (int j = 0; j < RPL; ++j)
+#pragma unroll
+    for (int w = 0; w < WORDS; ++w) {
+      uint32_t same = __shfl_up_sync(RG_FULL, X[j][w], 1);
+      uint32_t wrap = (j > 0) ? __shfl_sync(RG_FULL, X[j > 0 ? j - 1 : 0][w], 31) : 0u;
+      O[j][w] = lane > 0 ? same : wrap;
+    }
+}
+template <int WORDS, int RPL>
+RG_DEV void rows_down(const uint32_t (&X)[RPL][WORDS], uint32_t (&O)[RPL][WORDS], int lane) {  // O[row] = X[row+1]
+#pragma unroll
+  for (int j = 0; j < RPL; ++j)
+#pragma unroll
+    for (int w = 0; w < WORDS; ++w) {
+      uint32_t same = __shfl_down_sync(RG_FULL, X[j][w], 1);
+      uint32_t wrap = (j + 1 < RPL) ? __shfl_sync(RG_FULL, X[j + 1 < RPL ? j + 1 : j][w], 0) : 0u;
+      O[j][w] = lane < 31 ? same : wrap;
+    }
+}
+
+template <int WORDS, int RPL>
+__device__ __noinline__ void bfs_impl(const uint32_t* walk, uint16_t* out, int W, int H,
+                                      int CP, int fx, int fy, int lane) {
+  uint32_t Wc[RPL][WORDS], Wu[RPL][WORDS], Wd[RPL][WORDS], Vis[RPL][WORDS], F[RPL][WORDS];
+#pragma unroll
+  for (int j = 0; j < RPL; ++j) {
+    int row = lane + 32 * j;
+#pragma unroll
+    for (int w = 0; w < WORDS; ++w) {
+      Wc[j][w] = row < H ? walk[row * WORDS + w] : 0u;
+      F[j][w] = (row == fy && (fx >> 5) == w) ? (1u << (fx & 31)) : 0u;
+      Vis[j][w] = F[j][w];
+    }
+  }
+  rows_up<WORDS, RPL>(Wc, Wu, lane);
+  rows_down<WORDS, RPL>(Wc, Wd, lane);
+  for (int i = lane; i < CP / 8; i += 32)
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(RG_FULL, RG_FULL, RG_FULL, RG_FULL);
+  __syncwarp();
+  if (lane == (fy & 31)) out[fy * W + fx] = 0;
+  for (int level = 1; level < 0xFFFF; ++level) {
+    uint32_t Fu[RPL][WORDS], Fd[RPL][WORDS];
+    rows_up<WORDS, RPL>(F, Fu, lane);
+    rows_down<WORDS, RPL>(F, Fd, lane);
+    uint32_t anynew = 0;
+#pragma unroll
+    for (int j = 0; j < RPL; ++j) {
+      uint32_t a[WORDS], b[WORDS], t0[WORDS], t1[WORDS], n[WORDS];
+      shl1<WORDS>(F[j], t0);
+      shr1<WORDS>(F[j], t1);
+#pragma unroll
+      for (int w = 0; w < WORDS; ++w) {
+        n[w] = t0[w] | t1[w] | Fu[j][w] | Fd[j][w];
+        a[w] = Fu[j][w] & Wc[j][w];  // sources one row up whose vertical step is legal
+        b[w] = Fd[j][w] & Wc[j][w];
+      }
+      shl1<WORDS>(a, t0);
+      shr1<WORDS>(a, t1);
+#pragma unroll
+      for (int w = 0; w < WORDS; ++w) n[w] |= (t0[w] | t1[w]) & Wu[j][w];
+      shl1<WORDS>(b, t0);
+      shr1<WORDS>(b, t1);
+#pragma unroll
+      for (int w = 0; w < WORDS; ++w) {
+        n[w] |= (t0[w] | t1[w]) & Wd[j][w];
+        n[w] &= Wc[j][w] & ~Vis[j][w];
+        Vis[j][w] |= n[w];
+        F[j][w] = n[w];
+        anynew |= n[w];
+        uint32_t bits = n[w];
+        int base = (lane + 32 * j) * W + w * 32;
+        while (bits) {
+          int bpos = __ffs(bits) - 1;
+          bits &= bits - 1;
+          out[base + bpos] = (uint16_t)level;
+        }
+      }
+    }
+    if (!__any_sync(RG_FULL, anynew != 0)) break;
+  }
+  __syncwarp();
+}
+
+__device__ void bfs(Ctx& c, int fx, int fy, uint16_t* out) {
+  const int rpl = (c.H + 31) / 32;
+#define RG_BFS_CASE(WD, RP) \
+  if (c.WW == WD && rpl == RP) { bfs_impl<WD, RP>(c.g_walk, out, c.W, c.H, c.CP, fx, fy, c.lane); return; }
+  RG_BFS_CASE(3, 1) RG_BFS_CASE(1, 1) RG_BFS_CASE(2, 1) RG_BFS_CASE(4, 1) RG_BFS_CASE(5, 1)
+  RG_BFS_CASE(1, 2) RG_BFS_CASE(2, 2) RG_BFS_CASE(3, 2) RG_BFS_CASE(4, 2) RG_BFS_CASE(5, 2)
+#undef RG_BFS_CASE
+  set_panic(c);
+}
+
+// DistCache::make_dist_map rogue/mod.rs:504-517: FIFO of 9 keyed by the target coordinate,
+// never flushed (stale maps from earlier floors are used on purpose).
+__device__ const uint16_t* cached_dist_map(Ctx& c, int tx, int ty) {
+  EnvState* st = c.st;
+  int n = st->cache_n, head = st->cache_head;
+  for (int k = 0; k < n; ++k) {
+    int slot = (head + k) % NCACHE;
+    if (st->cache_x[slot] == tx && st->cache_y[slot] == ty) return c.g_dist + (size_t)slot * c.CP;
+  }
+  int slot;
+  if (n < NCACHE) {
+    slot = (head + n) % NCACHE;
+    st->cache_n = (uint8_t)(n + 1);
+  } else {
+    slot = head;
+    st->cache_head = (uint8_t)((head + 1) % NCACHE);
+  }
+  st->cache_x[slot] = (uint8_t)tx;
+  st->cache_y[slot] = (uint8_t)ty;
+  uint16_t* out = c.g_dist + (size_t)slot * c.CP;
+  bfs(c, tx, ty, out);
+  return out;
+}
+
+// ------------------------------------------------------------------ monsters
+// `moved` = monsters already re-inserted this turn; skip(q) = a moved-active or placed monster
+// stands on q (enemies.rs:383-384).
+RG_DEV bool cell_blocked(const Ctx& c, int x, int y, uint32_t moved) {
+  bool hit = false;
+  for (int m = 0; m < c.nrooms; ++m) {
+    MonD mo = c.st->mon[m];
+    bool counts = (mo.flags & MF_PRESENT) && (!(mo.flags & MF_ACTIVE) || ((moved >> m) & 1u));
+    hit = hit || (counts && mo.x == x && mo.y == y);
+  }
+  return hit;
+}
+
+enum { MV_CANT = 0, MV_CAN = 1, MV_REACH = 2 };
+// rogue::Dungeon::move_enemy rogue/mod.rs:339-375. PARALLEL over the 9 directions: lane d
+// probes neighbour d, the in-order semantics are rebuilt from ballots.
+__device__ int move_enemy(Ctx& c, int mx, int my, int tx, int ty, uint32_t moved, bool noskip, int& ox, int& oy) {
+  const uint16_t* dm = cached_dist_map(c, tx, ty);
+  if (c.panic) return MV_CANT;
+  const int d = c.lane;
+  const bool valid = d < 9;
+  const int nx = mx + ddx(valid ? d : 8), ny = my + ddy(valid ? d : 8);
+  const bool skip = valid && !noskip && cell_blocked(c, nx, ny, moved);
+  const bool live = valid && !skip;
+  const bool oob = live && !inb(c, nx, ny);
+  uint32_t nd = 0xFFFFu;
+  if (live && !oob) nd = dm[ny * c.W + nx];
+  const bool reach = live && !oob && nd == 0 && can_move(c, mx, my, d, true);
+  const bool cand = live && !oob && nd != 0xFFFFu && nd > 0;
+  const uint32_t oobM = __ballot_sync(RG_FULL, oob);
+  const uint32_t reachM = __ballot_sync(RG_FULL, reach);
+  const int first_oob = oobM ? __ffs(oobM) - 1 : 99;
+  const int first_reach = reachM ? __ffs(reachM) - 1 : 99;
+  if (first_oob < first_reach) {  // `*dist_map.get_p(next)` out of range: the reference panics (:361)
+    set_panic(c);
+    return MV_CANT;
+  }
+  if (reachM) return MV_REACH;
+  uint32_t key = cand ? ((nd << 4) | (uint32_t)d) : RG_FULL;  // stable sort_by_key + [0]
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(RG_FULL, key, o));
+  if (key == RG_FULL) return MV_CANT;
+  int bd = (int)(key & 15u);
+  ox = mx + ddx(bd);
+  oy = my + ddy(bd);
+  return MV_CAN;
+}
+// rogue::Dungeon::move_enemy_randomly rogue/mod.rs:376-397
+__device__ int move_enemy_randomly(Ctx& c, int mx, int my, uint32_t moved, int& ox, int& oy) {
+  int d = (int)c.rd.range64(0, 8);
+  int nx = mx + ddx(d), ny = my + ddy(d);
+  if (cell_blocked(c, nx, ny, moved) || !can_move(c, mx, my, d, true)) return MV_CANT;
+  if (nx == c.st->px && ny == c.st->py) return MV_REACH;
+  ox = nx;
+  oy = ny;
+  return MV_CAN;
+}
+
+RG_DEV uint32_t clamp_parcent(int v) { return (uint32_t)min(100, max(0, v)); }  // Parcent::truncate rng.rs:152-154
+
+// fight::roll fight.rs:52-72 on the enemy stream; returns -1 on a miss
+__device__ int roll_dice(Rng& re, const int32_t* times, const int32_t* maxs, int n, uint32_t rate, int dam_plus) {
+  bool did_hit = false;
+  int sum = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!re.parcent(rate)) continue;
+    did_hit = true;
+    int acc = 0;
+    for (int t = 0; t < times[i]; ++t) acc += (int)re.range64(1, (uint64_t)(maxs[i] + 1));  // Dice::random, i64 lane
+    sum += acc + dam_plus;
+  }
+  return did_hit ? sum : -1;
+}
+
+// actions::move_active_enemies + EnemyHandler::move_actives actions.rs:82-119, enemies.rs:366-424
+// returns true when the player died (Some(Grave))
+__device__ bool move_active_enemies(Ctx& c) {
+  EnvState* st = c.st;
+  const rg_params& P = *c.P;
+  uint32_t pending = 0;
+  for (int m = 0; m < c.nrooms; ++m) {
+    uint8_t f = st->mon[m].flags;
+    if ((f & MF_PRESENT) && (f & MF_ACTIVE)) pending |= 1u << m;
+  }
+  if (!pending) return false;
+  uint32_t moved = 0, attackers = 0;
+  uint8_t attack_order[MAX_ROOMS];
+  int n_att = 0;
+  while (pending) {
+    // next monster in BTreeMap order of its ORIGINAL position: [level, x, y] => x-major
+    int best = -1;
+    uint32_t bkey = RG_FULL;
+    for (int m = 0; m < c.nrooms; ++m)
+      if ((pending >> m) & 1u) {
+        uint32_t key = ((uint32_t)st->mon[m].x << 8) | st->mon[m].y;
+        if (key < bkey) { bkey = key; best = m; }
+      }
+    const int m = best;
+    pending &= ~(1u << m);
+    MonD mo = st->mon[m];
+    const uint32_t attr = P.enemies[mo.kind].attr;
+    bool randomly;
+    if (c.re.does_happen(2) && (attr & EA_RANDOM)) randomly = true;
+    else randomly = (!c.re.does_happen(5)) && (attr & EA_CONFUSED);
+    int nx = mo.x, ny = mo.y, kind;
+    if (randomly) kind = move_enemy_randomly(c, mo.x, mo.y, moved, nx, ny);
+    else kind = move_enemy(c, mo.x, mo.y, st->px, st->py, moved, false, nx, ny);
+    if (c.panic) return false;
+    if (kind == MV_REACH) {
+      attackers |= 1u << m;
+      attack_order[n_att++] = (uint8_t)m;
+    }
+    if (kind != MV_CAN) {
+      // re-insert at its own key: BTreeMap::insert replaces a monster that already moved there
+      for (int o = 0; o < c.nrooms; ++o)
+        if (((moved >> o) & 1u) && (st->mon[o].flags & MF_PRESENT) && st->mon[o].x == mo.x && st->mon[o].y == mo.y)
+          st->mon[o].flags = 0;
+    } else {
+      st->mon[m].x = (uint8_t)nx;
+      st->mon[m].y = (uint8_t)ny;
+    }
+    moved |= 1u << m;
+  }
+  if (!n_att) return false;
+  st->quiet = 0;  // player.buttle()
+  bool did_hit = false;
+  for (int i = 0; i < n_att; ++i) {
+    const MonD mo = st->mon[attack_order[i]];
+    const rg_enemy_kind& k = P.enemies[mo.kind];
+    int elevel = k.level + (int)lev_add(c);
+    uint32_t rate = clamp_parcent((elevel + P.armor_def + 0 + 1) * 5);  // fight.rs:80-87, hit_prob_plus(10) = 0
+    int dmg = roll_dice(c.re, k.dice_times, k.dice_max, (int)k.n_dice, rate, 0);  // damage_plus(10)+damage_plus(16) = 0
+    if (dmg >= 0) {
+      c.msg |= MSG_HIT_FROM;
+      did_hit = true;
+      st->hp = max(st->hp - dmg, 0);  // Player::get_damage player.rs:177-184
+      if (st->hp == 0) {
+        c.dead = 1;
+        return true;
+      }
+    } else {
+      c.msg |= MSG_MISS_FROM;
+    }
+  }
+  if (did_hit) c.status_upd = 1;
+  return false;
+}
+
+// Player::heal player.rs:221-240
+__device__ bool heal(Ctx& c) {
+  EnvState* st = c.st;
+  st->quiet += 1;
+  int q = (int)st->quiet, lv = st->plevel, amount;
+  if (lv < 8) amount = max(min(q + (lv << 1) - 20, 1), 0);
+  else if (q >= 3) amount = (int)c.re.range64(1, (uint64_t)(lv - 6));
+  else amount = 0;
+  if (amount > 0) {
+    st->hp = min(st->hp + amount, st->hp_max);
+    st->quiet = 0;
+    return true;
+  }
+  return false;
+}
+// actions::after_turn actions.rs:67-80 + Player::turn_passed player.rs:163-176
+__device__ bool after_turn(Ctx& c) {
+  EnvState* st = c.st;
+  st->food_left -= 1;  // wraps like the release build
+  if (st->food_left != 0) {
+    uint32_t hunger = c.P->hunger_time / 10;
+    bool hungry = st->food_left == hunger || st->food_left == hunger * 2;
+    bool healed = heal(c);
+    if (hungry || healed) c.status_upd = 1;
+  }
+  return move_active_enemies(c);
+}
+
+// Player::level_up + Leveling::check_level player.rs:185-197,346-352
+__device__ bool level_up(Ctx& c, uint32_t gained) {
+  EnvState* st = c.st;
+  const rg_params& P = *c.P;
+  st->exp += gained;
+  uint32_t cur = (uint32_t)(st->plevel - 1), diff = 0;
+  if (cur < P.n_exps) {
+    bool found = false;
+    for (uint32_t i = cur; i < P.n_exps; ++i)
+      if (st->exp < P.exps[i]) { diff = i - cur; found = true; break; }
+    if (!found) { set_panic(c); return false; }
+  }
+  if (diff > 0) {
+    st->plevel += (int)diff;
+    int add = 0;
+    for (uint32_t i = 0; i < diff; ++i) add += (int)c.re.range64(1, 11);
+    st->hp_max += add;
+    st->hp += add;
+    return true;
+  }
+  return false;
+}
+
+// actions::move_player actions.rs:168-195 (incl. player_attack :140-166, get_item :206-231)
+// returns `done`; *first_nonempty-style bookkeeping is left to the caller via flags
+struct MoveOut {
+  bool done;
+  uint32_t redraw, status_upd, msg;
+};
+__device__ MoveOut move_player(Ctx& c, int d) {
+  EnvState* st = c.st;
+  const rg_params& P = *c.P;
+  MoveOut o{true, 0, 0, 0};
+  const int px = st->px, py = st->py;
+  // rogue::Dungeon::can_move_player
+  if (!can_move(c, px, py, d, false)) return o;  // Notify(CantMove): not a message flag
+  const int nx = px + ddx(d), ny = py + ddy(d);
+  // EnemyHandler::get_cloned (enemies.rs:336-341): positions are unique between turns
+  int target = -1;
+  for (int m = 0; m < c.nrooms; ++m) {
+    MonD mo = st->mon[m];
+    if (target < 0 && (mo.flags & MF_PRESENT) && mo.x == nx && mo.y == ny) target = m;
+  }
+  if (target >= 0) {  // player_attack
+    st->quiet = 0;
+    MonD mo = st->mon[target];
+    st->mon[target].flags = mo.flags | MF_ACTIVE;  // activate(): runs before the to-hit
+    const rg_enemy_kind& k = P.enemies[mo.kind];
+    int edef = k.defense - (int)lev_add(c);
+    uint32_t rate = clamp_parcent((st->plevel + edef + 0 + 0 + P.weapon_hit_plus + 1) * 5);  // fight.rs:74-78
+    int32_t t = P.weapon_times, mx = P.weapon_max;
+    int dmg = roll_dice(c.re, &t, &mx, 1, rate, P.weapon_dam_plus);
+    if (dmg >= 0) {
+      o.msg |= MSG_HIT_TO;
+      if (mo.hp <= dmg) {  // Enemy::get_damage enemies.rs:205-213
+        st->mon[target].flags = 0;
+        if (level_up(c, mo.exp)) o.status_upd = 1;
+        o.msg |= MSG_KILLED;
+        o.redraw = 1;
+      } else {
+        st->mon[target].hp = dmg - mo.hp;
+      }
+    } else {
+      o.msg |= MSG_MISS_TO;
+    }
+    return o;
+  }
+  player_out(c, px, py);
+  player_in(c, nx, ny, false);
+  st->px = (int16_t)nx;
+  st->py = (int16_t)ny;
+  o.done = false;
+  o.redraw = 1;
+  const int pos = ny * c.W + nx;
+  for (int i = 0; i < c.nrooms; ++i)
+    if (st->item_pos[i] == pos && P.pack_accepts_gold) {
+      st->gold += st->item_amt[i];
+      st->item_pos[i] = 0xFFFF;
+      o.status_upd = 1;  // Notify(GotItem) is not a message flag
+      o.done = true;
+    }
+  return o;
+}
+
+// Floor::search floor.rs:349-370
+__device__ void search(Ctx& c) {
+  const int W = c.W;
+  const int px = c.st->px, py = c.st->py;
+  for (int d = 0; d < 8; ++d) {
+    int nx = px + ddx(d), ny = py + ddy(d);
+    if (!inb(c, nx, ny)) continue;
+    int idx = ny * W + nx;
+    bool opened = false;
+    if ((c.A[idx] & A_HIDDEN) && c.rd.does_happen(c.P->passage_unlock_rate_inv)) {
+      c.A[idx] = (c.A[idx] & (uint8_t)~(A_LOCKED | A_HIDDEN)) | A_VISIBLE;
+      c.S[idx] = S_PASSAGE;
+      opened = true;
+    }
+    if ((c.A[idx] & A_LOCKED) && c.rd.does_happen(c.P->door_unlock_rate_inv)) {
+      c.A[idx] = (c.A[idx] & (uint8_t)~(A_LOCKED | A_HIDDEN)) | A_VISIBLE;
+      c.S[idx] = S_DOOR;
+      c.msg |= MSG_SECRET_DOOR;
+      opened = true;
+    }
+    if (opened) {
+      c.g_walk[ny * c.WW + (nx >> 5)] |= 1u << (nx & 31);
+      c.s_dirty = 1;
+    }
+  }
+  c.a_dirty = 1;
+}
+
+// RunTime::player_status core/src/lib.rs:345-356 -> Status::to_vec player.rs:417-430
+__device__ void refresh_status(Ctx& c) {
+  EnvState* st = c.st;
+  uint32_t hunger = c.P->hunger_time / 10;
+  st->status[0] = (uint32_t)st->level;
+  st->status[1] = st->gold;
+  st->status[2] = (uint32_t)st->hp;
+  st->status[3] = (uint32_t)st->hp_max;
+  st->status[4] = 16;  // strength is hard-wired (player.rs:286)
+  st->status[5] = 16;
+  st->status[6] = 0;   // defense is never filled (player.rs:107-118)
+  st->status[7] = (uint32_t)st->plevel;
+  st->status[8] = st->exp;
+  st->status[9] = st->food_left <= hunger ? 2u : (st->food_left <= hunger * 2 ? 1u : 0u);
+}
+
+// actions::process_action actions.rs:16-65. act: 0 Move, 1 MoveUntil, 2 Search, 3 DownStair
+__device__ void process_action(Ctx& c, int act, int d) {
+  EnvState* st = c.st;
+  bool ui = false;
+  if (act == 3) {
+    if (c.S[st->py * c.W + st->px] == S_STAIR) {
+      new_level(&c, false);
+      c.redraw = 1;
+      c.status_upd = 1;
+    } else {
+      c.msg |= MSG_NO_DOWNSTAIR;
+    }
+    if (!c.panic) ui = after_turn(c);
+  } else if (act == 0) {
+    MoveOut o = move_player(c, d);
+    c.redraw |= o.redraw; c.status_upd |= o.status_upd; c.msg |= o.msg;
+    if (!c.panic) ui = after_turn(c);
+  } else if (act == 1) {
+    for (int guard = 0; guard < 512 && !c.panic; ++guard) {
+      MoveOut o = move_player(c, d);
+      int idx = st->py * c.W + st->px;
+      // Dungeon::tile: the VISIBLE tile (rogue/mod.rs:321-328); keep running only on '.' / '#'
+      bool on_open = (c.A[idx] & A_VISIBLE) && (c.S[idx] == S_FLOOR || c.S[idx] == S_PASSAGE);
+      // the reactions of every sub-move matter only through these idempotent flags
+      c.redraw |= o.redraw; c.status_upd |= o.status_upd; c.msg |= o.msg;
+      if (o.done || !on_open) break;
+      ui = after_turn(c);
+    }
+  } else if (act == 2) {
+    search(c);
+    c.redraw = 1;
+    if (!c.panic) ui = after_turn(c);
+  }
+  if (ui) st->ui_dead = 1;
+}
+
+// ------------------------------------------------------------------ observation compose
+// RunTime::draw_screen core/src/lib.rs:264-285 + Dungeon::draw / draw_ranges / draw_enemy
+// rogue/mod.rs:278-300,398-404 + Floor::history_map floor.rs:372-379.
+__device__ void compose(Ctx& c) {
+  const int W = c.W, H = c.H;
+  EnvState* st = c.st;
+  __syncwarp();
+  for (int ch = c.lane; ch < c.CP / 16; ch += 32) {  // PARALLEL, 128-bit in / 128-bit out
+    uint4 s4 = *reinterpret_cast<const uint4*>(c.S + ch * 16);
+    uint4 a4 = *reinterpret_cast<const uint4*>(c.A + ch * 16);
+    uint32_t sv[4] = {s4.x, s4.y, s4.z, s4.w}, av[4] = {a4.x, a4.y, a4.z, a4.w}, ov[4];
+    uint32_t hbits = 0;
+    const int base = ch * 16;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t o = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t s = (sv[q] >> (8 * k)) & 0xFFu, a = (av[q] >> (8 * k)) & 0xFFu;
+        int idx = base + q * 4 + k;
+        bool drawn = (a & A_VISIBLE) && idx >= W && idx < (H - 1) * W;  // rows 0 and H-1 are never written
+        uint32_t t = drawn ? (uint32_t)surface_tile((uint8_t)(s & 7u)) : 0x20u;
+        o |= t << (8 * k);
+        hbits |= (a & 1u) << (q * 4 + k);
+      }
+      ov[q] = o;
+    }
+    *reinterpret_cast<uint4*>(c.g_screen + base) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+    if (!c.hist_done) reinterpret_cast<uint16_t*>(c.g_hist)[ch] = (uint16_t)hbits;
+  }
+  __syncwarp();
+  // overlays in increasing priority: monsters, items, player (core/src/lib.rs:272-283)
+  const int px = st->px, py = st->py;
+  if (c.lane < c.nrooms) {
+    MonD mo = st->mon[c.lane];
+    if (mo.flags & MF_PRESENT) {
+      int idx = mo.y * W + mo.x;
+      bool vis = (c.A[idx] & (A_VISIBLE | A_DRAWN)) && mo.y >= 1 && mo.y < H - 1;
+      int dx = px - mo.x, dy = py - mo.y;
+      bool show = dx * dx + dy * dy <= 2;  // Coord::is_adjacent
+      if (!show) {                         // Floor::in_same_room floor.rs:381-393
+        int id = room_of(c, px, py);
+        if (id >= 0 && room_of(c, mo.x, mo.y) == id) {
+          RoomD rm = st->rooms[id];
+          show = (rm.kind == K_EMPTY) || (in_rect(rm, px, py) == in_rect(rm, mo.x, mo.y));
+        }
+      }
+      if (vis && show) c.g_screen[idx] = (uint8_t)c.P->enemies[mo.kind].tile;
+    }
+  }
+  __syncwarp();
+  if (c.lane < c.nrooms) {
+    uint16_t ip = st->item_pos[c.lane];
+    if (ip != 0xFFFF && (c.A[ip] & (A_VISIBLE | A_DRAWN)) && ip >= W && ip < (H - 1) * W) c.g_screen[ip] = '*';
+  }
+  __syncwarp();
+  if (c.lane == 0) {
+    int idx = py * W + px;
+    if ((c.A[idx] & (A_VISIBLE | A_DRAWN)) && py >= 1 && py < H - 1) c.g_screen[idx] = '@';
+  }
+  __syncwarp();
+}
+
+// GameConfig::build + GameStateImpl::reset + PlayerState::reset
+// core/src/lib.rs:193-228, python/src/state_impls.rs:38-44, python/src/lib.rs:52-58
+__device__ void reset_env(Ctx& c) {
+  EnvState* st = c.st;
+  const rg_params& P = *c.P;
+  c.rd.seed(st->seed);
+  c.ri.seed(st->seed);
+  c.re.seed(st->seed);
+  if (!st->seeded) {  // seed: null => a fresh seed every reset (core/src/lib.rs:157-165)
+    uint64_t z = ((uint64_t)st->seed[1] << 32 | st->seed[0]) + 0x9E3779B97F4A7C15ull * (uint64_t)(st->episode + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    uint64_t lo = P.has_seed_range ? P.seed_range_lo : 0, span = P.has_seed_range ? (P.seed_range_hi - P.seed_range_lo) : 0;
+    if (span) z = lo + z % span;
+    st->seed[0] = (uint32_t)z;
+    st->seed[1] = (uint32_t)(z >> 32);
+    st->seed[2] = st->seed[3] = 0;
+  }
+  st->episode += 1;
+  st->level = 0;
+  st->cache_n = 0;
+  st->cache_head = 0;
+  st->hp = st->hp_max = P.init_hp;
+  st->exp = 0;
+  st->plevel = 1;
+  st->food_left = P.hunger_time;
+  st->quiet = 0;
+  st->gold = P.init_gold;
+  st->ui_dead = 0;
+  st->error = 0;
+  c.panic = 0;
+  new_level(&c, true);
+  refresh_status(c);
+  c.hist_done = 0;
+  st->message = 0;
+  st->is_terminal = 0;
+  st->steps = 0;
+}
+
+// KeyMap::ai input.rs:74-99 ; act 4 = NoOp, -1 = not in the map
+RG_DEV int map_key(uint8_t key, int& d) {
+  d = D_STAY;
+  switch (key) {
+    case 'l': d = D_RIGHT; return 0;
+    case 'k': d = D_UP; return 0;
+    case 'j': d = D_DOWN; return 0;
+    case 'h': d = D_LEFT; return 0;
+    case 'u': d = D_RIGHTUP; return 0;
+    case 'y': d = D_LEFTUP; return 0;
+    case 'n': d = D_RIGHTDOWN; return 0;
+    case 'b': d = D_LEFTDOWN; return 0;
+    case 'L': d = D_RIGHT; return 1;
+    case 'K': d = D_UP; return 1;
+    case 'J': d = D_DOWN; return 1;
+    case 'H': d = D_LEFT; return 1;
+    case 'U': d = D_RIGHTUP; return 1;
+    case 'Y': d = D_LEFTUP; return 1;
+    case 'N': d = D_RIGHTDOWN; return 1;
+    case 'B': d = D_LEFTDOWN; return 1;
+    case 's': return 2;
+    case '>': return 3;
+    case '.': return 4;
+    default: return -1;
+  }
+}
+
+}  // namespace rg

@@ -1,0 +1,385 @@
+// rg_kernels.cu — __global__ entry points (warp per env) and their launchers.
+#include <cuda_runtime.h>
+
+#include "rg_device.cuh"
+#include "rg_launch.h"
+
+namespace rg {
+
+constexpr int WARPS_PER_BLOCK = 4;
+
+// Stage one env's small state into shared memory and fill the context.
+RG_DEV void fill_ctx(const DevBatch& b, Ctx& c, unsigned char* base, int64_t env) {
+  c.S = base;
+  c.A = base + b.CP;
+  c.st = reinterpret_cast<EnvState*>(base + 2 * (size_t)b.CP);
+  c.P = b.P;
+  c.W = b.W; c.H = b.H; c.C = b.C; c.CP = b.CP; c.WW = b.WW;
+  c.lane = threadIdx.x & 31;
+  c.nx = b.P->room_num_x; c.ny = b.P->room_num_y;
+  c.rsx = b.W / c.nx; c.rsy = b.H / c.ny;
+  c.nrooms = c.nx * c.ny;
+  c.g_screen = b.screen + env * b.CP;
+  c.g_hist = b.hist + env * b.HB;
+  c.g_walk = b.walk + env * (int64_t)(b.H * b.WW);
+  c.g_dist = b.dist + env * (int64_t)NCACHE * b.CP;
+  c.redraw = c.status_upd = c.dead = c.msg = c.hist_done = c.a_dirty = c.s_dirty = c.panic = 0;
+  // small state: 128-bit coalesced
+  const uint4* src = reinterpret_cast<const uint4*>(b.st + env);
+  uint4* dst = reinterpret_cast<uint4*>(c.st);
+  for (int i = c.lane; i < (int)(sizeof(EnvState) / 16); i += 32) dst[i] = src[i];
+  __syncwarp();
+  c.rd.load(c.st->rng);
+  c.ri.load(c.st->rng + 4);
+  c.re.load(c.st->rng + 8);
+}
+// Returns false for warps past the end of the batch.
+RG_DEV bool open_env(const DevBatch& b, Ctx& c, unsigned char* smem, int64_t& env) {
+  const int warp = threadIdx.x >> 5;
+  env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
+  if (env >= b.n) return false;
+  fill_ctx(b, c, smem + (size_t)warp * (2 * (size_t)b.CP + sizeof(EnvState)), env);
+  return true;
+}
+RG_DEV void load_grid(const DevBatch& b, Ctx& c, int64_t env) {
+  const uint4* gs = reinterpret_cast<const uint4*>(b.surface + env * b.CP);
+  const uint4* ga = reinterpret_cast<const uint4*>(b.attr + env * b.CP);
+  for (int i = c.lane; i < b.CP / 16; i += 32) {
+    reinterpret_cast<uint4*>(c.S)[i] = gs[i];
+    reinterpret_cast<uint4*>(c.A)[i] = ga[i];
+  }
+  __syncwarp();
+}
+RG_DEV void close_env(const DevBatch& b, Ctx& c, int64_t env) {
+  __syncwarp();
+  if (c.lane == 0) {
+    c.rd.store(c.st->rng);
+    c.ri.store(c.st->rng + 4);
+    c.re.store(c.st->rng + 8);
+  }
+  __syncwarp();
+  if (c.s_dirty) {
+    uint4* gs = reinterpret_cast<uint4*>(b.surface + env * b.CP);
+    for (int i = c.lane; i < b.CP / 16; i += 32) gs[i] = reinterpret_cast<const uint4*>(c.S)[i];
+  }
+  if (c.a_dirty) {
+    uint4* ga = reinterpret_cast<uint4*>(b.attr + env * b.CP);
+    for (int i = c.lane; i < b.CP / 16; i += 32) ga[i] = reinterpret_cast<const uint4*>(c.A)[i];
+  }
+  uint4* dst = reinterpret_cast<uint4*>(b.st + env);
+  const uint4* src = reinterpret_cast<const uint4*>(c.st);
+  for (int i = c.lane; i < (int)(sizeof(EnvState) / 16); i += 32) dst[i] = src[i];
+}
+RG_DEV void emit_obs(const DevBatch& b, Ctx& c, int64_t env, int32_t reward, uint8_t err) {
+  if (c.lane < 10) b.status[env * 10 + c.lane] = c.st->status[c.lane];
+  if (c.lane == 10) b.reward[env] = reward;
+  if (c.lane == 11) b.done[env] = c.st->is_terminal;
+  if (c.lane == 12) b.message[env] = c.st->message;
+  if (c.lane == 13) {
+    b.error[env] = err;
+    if (err) atomicOr(b.errflag, 1u << err);
+  }
+}
+
+// ThreadWorker::run Instruction::Reset for every env (python/src/thread_impls.rs:117-124)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_reset(DevBatch b) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Ctx c;
+  int64_t env;
+  if (!open_env(b, c, smem, env)) return;
+  reset_env(c);
+  uint8_t err = 0;
+  if (c.panic) {
+    c.st->error = RG_ERR_PANIC;
+    err = RG_ERR_PANIC;
+  }
+  compose(c);
+  emit_obs(b, c, env, 0, err);
+  close_env(b, c, env);
+}
+
+// GameStateImpl::react (python/src/state_impls.rs:51-79), and with auto_reset the conductor's
+// "reset terminal envs and return the fresh state flagged terminal" (thread_impls.rs:69-79).
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_step(DevBatch b, const uint8_t* __restrict__ actions,
+                                                              int auto_reset) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Ctx c;
+  int64_t env;
+  if (!open_env(b, c, smem, env)) return;
+  EnvState* st = c.st;
+  const uint8_t key = actions[env];
+  if (st->error == RG_ERR_PANIC || st->error == RG_ERR_SETTING) {  // the reference's worker is gone
+    emit_obs(b, c, env, 0, st->error);
+    return;
+  }
+  if ((int64_t)st->steps > b.max_steps) {  // state_impls.rs:52-54
+    emit_obs(b, c, env, 0, 0);
+    return;
+  }
+  int d;
+  const int act = map_key(key, d);
+  if (act < 0) {  // ErrorKind::InvalidInput: nothing changes (core/src/lib.rs:322-327)
+    emit_obs(b, c, env, 0, RG_ERR_INVALID_INPUT);
+    return;
+  }
+  if (st->ui_dead) {  // UiState::Mordal(Grave) + Act => IgnoredInput (core/src/lib.rs:314)
+    emit_obs(b, c, env, 0, RG_ERR_IGNORED_INPUT);
+    return;
+  }
+  const uint32_t gold_before = st->status[1];
+  if (act != 4) {
+    load_grid(b, c, env);
+    process_action(c, act, d);
+  }
+  uint8_t err = 0;
+  if (c.panic) {
+    st->error = RG_ERR_PANIC;
+    err = RG_ERR_PANIC;
+  } else {
+    st->message = c.msg;
+    if (c.status_upd) refresh_status(c);
+    st->steps += 1;
+    st->is_terminal = (c.dead || (int64_t)st->steps >= b.max_steps) ? 1 : 0;
+    if (st->is_terminal && auto_reset) {
+      reset_env(c);
+      if (c.panic) {
+        st->error = RG_ERR_PANIC;
+        err = RG_ERR_PANIC;
+      }
+      st->is_terminal = 1;
+      c.redraw = 1;
+    }
+    if (c.redraw) compose(c);
+  }
+  const int32_t diff = (int32_t)st->status[1] - (int32_t)gold_before;
+  emit_obs(b, c, env, diff > 0 ? diff : 0, err);
+  close_env(b, c, env);
+}
+
+// Dungeon::move_enemy with an always-false skip, for the known-answer test (rogue/mod.rs:566-578)
+__global__ void k_test_move_enemy(DevBatch b, int64_t env_id, int fx, int fy, int tx, int ty, int* out3) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Ctx c;
+  const int64_t env = env_id;
+  if ((threadIdx.x >> 5) != 0) return;
+  fill_ctx(b, c, smem, env);
+  load_grid(b, c, env);
+  int ox = -1, oy = -1;
+  int kind = move_enemy(c, fx, fy, tx, ty, 0, true, ox, oy);
+  if (c.lane == 0) {
+    out3[0] = c.panic ? -1 : kind;
+    out3[1] = ox;
+    out3[2] = oy;
+  }
+  close_env(b, c, env);
+}
+
+// ---------------------------------------------------------------- observation encoders
+// PlayerState::{gray,symbol}_image[_with_hist] python/src/lib.rs:72-111,158-205 and
+// symbol::construct_symbol_map core/src/symbol.rs:51-71. One block per (env, plane group);
+// every thread produces float4s, so the store stream is fully coalesced. HBM-write bound.
+RG_DEV int tile_sym(uint32_t t) {  // Symbol::from_tile symbol.rs:17-40
+  switch (t) {
+    case ' ': return 0;
+    case '@': return 1;
+    case '#': return 2;
+    case '.': return 3;
+    case '-':
+    case '|': return 4;
+    case '%': return 5;
+    case '+': return 6;
+    case '^': return 7;
+    case '!': return 8;
+    case '?': return 9;
+    case ']': return 10;
+    case ')': return 11;
+    case '/': return 12;
+    case '*': return 13;
+    case ':': return 14;
+    case '=': return 15;
+    case ',': return 16;
+    default: return (t >= 'A' && t <= 'Z') ? (int)t - 'A' + 17 : -1;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_encode(DevBatch b, int mode, uint32_t flag, int with_hist, int channels,
+                                               float* __restrict__ out) {
+  const int64_t env = blockIdx.x;
+  const int C = b.C;  // C is a multiple of 4 whenever W is; the tail is handled per element
+  const uint8_t* scr = b.screen + env * b.CP;
+  const int symbols = (int)b.P->symbols;
+  const int base = mode == 0 ? 1 : symbols;
+  float* o = out + env * (int64_t)channels * C;
+  __shared__ uint8_t sym[160 * 48];
+  __shared__ int bad;
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    int s = tile_sym(scr[i]);
+    if (s < 0 || (mode == 1 && s >= symbols - 1)) {  // InvalidTileError symbol.rs:60-64
+      bad = 1;
+      s = 0;
+    }
+    sym[i] = (uint8_t)s;
+  }
+  __syncthreads();
+  if (C & 3) {  // odd sizes: plain per-element path
+    const int order_s[9] = {0, 2, 3, 4, 5, 6, 7, 8, 9};
+    const uint32_t* stv = b.status + env * 10;
+    for (int64_t i = threadIdx.x; i < (int64_t)channels * C; i += blockDim.x) {
+      int ch = (int)(i / C), cell = (int)(i - (int64_t)ch * C);
+      float v;
+      if (ch < base) {
+        v = mode == 0 ? (float)sym[cell] / (float)symbols : ((ch < symbols - 1 && sym[cell] == ch) ? 1.f : 0.f);
+      } else {
+        int k = ch - base, bit = 0, seen = 0;
+        for (bit = 0; bit < 9; ++bit)
+          if (flag & (1u << bit)) {
+            if (seen == k) break;
+            ++seen;
+          }
+        if (bit < 9) v = (float)(int32_t)stv[order_s[bit]];
+        else v = ((b.hist + env * b.HB)[cell >> 3] >> (cell & 7)) & 1u ? 1.f : 0.f;
+      }
+      o[i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && bad) {
+      b.error[env] = RG_ERR_SETTING;
+      atomicOr(b.errflag, 1u << RG_ERR_SETTING);
+    }
+    return;
+  }
+  const int C4 = C / 4;
+  if (mode == 0) {
+    const float inv = (float)symbols;
+    for (int i = threadIdx.x; i < C4; i += blockDim.x) {
+      float4 v = make_float4((float)sym[4 * i] / inv, (float)sym[4 * i + 1] / inv, (float)sym[4 * i + 2] / inv,
+                             (float)sym[4 * i + 3] / inv);
+      reinterpret_cast<float4*>(o)[i] = v;
+    }
+  } else {
+    // channels 0 .. symbols-2 are one-hot; channel symbols-1 stays zero
+    const int total = symbols * C4;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      int ch = i / C4, q = i - ch * C4;
+      float4 v = make_float4(sym[4 * q] == ch ? 1.f : 0.f, sym[4 * q + 1] == ch ? 1.f : 0.f,
+                             sym[4 * q + 2] == ch ? 1.f : 0.f, sym[4 * q + 3] == ch ? 1.f : 0.f);
+      if (ch == symbols - 1) v = make_float4(0.f, 0.f, 0.f, 0.f);
+      reinterpret_cast<float4*>(o)[i] = v;
+    }
+  }
+  // StatusFlagInner::copy_status python/src/flags.rs:87-115
+  int off = base;
+  const uint32_t* st = b.status + env * 10;
+  const int order[9] = {0, 2, 3, 4, 5, 6, 7, 8, 9};
+  for (int bit = 0; bit < 9; ++bit)
+    if (flag & (1u << bit)) {
+      const float v = (float)(int32_t)st[order[bit]];
+      float4* p = reinterpret_cast<float4*>(o + (int64_t)off * C);
+      for (int i = threadIdx.x; i < C4; i += blockDim.x) p[i] = make_float4(v, v, v, v);
+      ++off;
+    }
+  if (with_hist) {  // copy_hist python/src/lib.rs:105-111
+    const uint8_t* hb = b.hist + env * b.HB;
+    float4* p = reinterpret_cast<float4*>(o + (int64_t)off * C);
+    for (int i = threadIdx.x; i < C4; i += blockDim.x) {
+      uint32_t byte = hb[(4 * i) >> 3];
+      int sh = (4 * i) & 7;
+      p[i] = make_float4((byte >> sh) & 1u ? 1.f : 0.f, (byte >> (sh + 1)) & 1u ? 1.f : 0.f,
+                         (byte >> (sh + 2)) & 1u ? 1.f : 0.f, (byte >> (sh + 3)) & 1u ? 1.f : 0.f);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && bad) {
+    b.error[env] = RG_ERR_SETTING;
+    atomicOr(b.errflag, 1u << RG_ERR_SETTING);
+  }
+}
+
+// per-env state hash for large-N parity checks (matches oracle orc_state_hash)
+__global__ void k_state_hash(DevBatch b, uint64_t* out) {
+  const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= b.n) return;
+  uint64_t h = 0xcbf29ce484222325ull;
+  auto mix = [&](uint8_t v) { h ^= v; h *= 0x100000001b3ull; };
+  const uint8_t* scr = b.screen + env * b.CP;
+  for (int i = 0; i < b.C; ++i) mix(scr[i]);
+  const EnvState* st = b.st + env;
+  for (int i = 0; i < 10; ++i)
+    for (int k = 0; k < 4; ++k) mix((uint8_t)(st->status[i] >> (8 * k)));
+  for (int i = 0; i < 12; ++i)
+    for (int k = 0; k < 4; ++k) mix((uint8_t)(st->rng[i] >> (8 * k)));
+  int32_t s[6] = {st->px, st->py, st->hp, st->level, (int32_t)st->steps, (int32_t)st->is_terminal};
+  for (int i = 0; i < 6; ++i)
+    for (int k = 0; k < 4; ++k) mix((uint8_t)((uint32_t)s[i] >> (8 * k)));
+  out[env] = h;
+}
+
+// Instruction::Seed for every env (python/src/thread_impls.rs:125-128): stored, used by the next reset
+__global__ void k_seed(DevBatch b, const uint64_t* __restrict__ lo, const uint64_t* __restrict__ hi, int seeded) {
+  const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= b.n) return;
+  EnvState* st = b.st + env;
+  const uint64_t l = lo[env], h = hi ? hi[env] : 0ull;
+  st->seed[0] = (uint32_t)l;
+  st->seed[1] = (uint32_t)(l >> 32);
+  st->seed[2] = (uint32_t)h;
+  st->seed[3] = (uint32_t)(h >> 32);
+  st->seeded = (uint8_t)seeded;
+}
+
+// PlayerState.history as 0/1 bytes [N][C] for host consumers (python/src/lib.rs:33)
+__global__ void k_unpack_hist(DevBatch b, uint8_t* __restrict__ out) {
+  const int64_t env = blockIdx.x;
+  const uint8_t* hb = b.hist + env * b.HB;
+  uint8_t* o = out + env * (int64_t)b.C;
+  for (int i = threadIdx.x; i < b.C; i += blockDim.x) o[i] = (hb[i >> 3] >> (i & 7)) & 1u;
+}
+
+// ---------------------------------------------------------------- launchers
+static size_t block_smem(const DevBatch& b) { return (size_t)WARPS_PER_BLOCK * (2 * (size_t)b.CP + sizeof(EnvState)); }
+
+cudaError_t configure_kernels(const DevBatch& b) {
+  size_t sm = block_smem(b);
+  cudaError_t e = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_test_move_enemy, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)(2 * (size_t)b.CP + sizeof(EnvState)));
+}
+cudaError_t launch_reset(const DevBatch& b, cudaStream_t s) {
+  int blocks = (int)((b.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+  k_reset<<<blocks, WARPS_PER_BLOCK * 32, block_smem(b), s>>>(b);
+  return cudaGetLastError();
+}
+cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_reset, cudaStream_t s) {
+  int blocks = (int)((b.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+  k_step<<<blocks, WARPS_PER_BLOCK * 32, block_smem(b), s>>>(b, actions, auto_reset);
+  return cudaGetLastError();
+}
+cudaError_t launch_test_move_enemy(const DevBatch& b, int64_t env, int fx, int fy, int tx, int ty, int* out3,
+                                   cudaStream_t s) {
+  k_test_move_enemy<<<1, 32, 2 * (size_t)b.CP + sizeof(EnvState), s>>>(b, env, fx, fy, tx, ty, out3);
+  return cudaGetLastError();
+}
+cudaError_t launch_encode(const DevBatch& b, int mode, uint32_t flag, int with_hist, int channels, float* out,
+                          cudaStream_t s) {
+  k_encode<<<(unsigned)b.n, 256, 0, s>>>(b, mode, flag, with_hist, channels, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_seed(const DevBatch& b, const uint64_t* lo, const uint64_t* hi, int seeded, cudaStream_t s) {
+  k_seed<<<(unsigned)((b.n + 127) / 128), 128, 0, s>>>(b, lo, hi, seeded);
+  return cudaGetLastError();
+}
+cudaError_t launch_unpack_hist(const DevBatch& b, uint8_t* out, cudaStream_t s) {
+  k_unpack_hist<<<(unsigned)b.n, 128, 0, s>>>(b, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_state_hash(const DevBatch& b, uint64_t* out, cudaStream_t s) {
+  k_state_hash<<<(unsigned)((b.n + 127) / 128), 128, 0, s>>>(b, out);
+  return cudaGetLastError();
+}
+
+}  // namespace rg

@@ -1,0 +1,99 @@
+// rg_types.h — device-resident layout of one batch (shared by the kernels and the host glue).
+//
+// HBM layout (SoA over envs; every per-env slice is 16-byte aligned so a warp moves it with
+// 128-bit loads/stores):
+//   surface   u8  [N][CP]      Surface code per cell            (reference Cell.surface, field.rs:12-15)
+//   attr      u8  [N][CP]      CellAttr bits 0..5 + bit 6 "in Floor.doors" (field.rs:107-124, floor.rs:19)
+//   screen    u8  [N][CP]      composed ASCII screen            (PlayerState.map, python/src/lib.rs:32)
+//   hist      u8  [N][HB]      visited bitmap shown to the agent(PlayerState.history, :33)
+//   walk      u32 [N][H][WW]   monster-walkable bitboard rows   (derived from surface; feeds the BFS)
+//   dist      u16 [N][9][CP]   DistCache maps                   (rogue/mod.rs:492-518)
+//   st        EnvState [N]     everything scalar / small        (RunTime + GameStateImpl + PlayerState.status)
+// CP = W*H rounded up to 16, HB = CP/8 rounded up to 16, WW = ceil(W/32).
+#pragma once
+#include <stdint.h>
+
+#include "../../include/rogue_b200.h"
+
+namespace rg {
+
+constexpr int MAX_ROOMS = RG_MAX_ROOMS;
+constexpr int NCACHE = RG_DIST_CACHE;
+
+// Surface codes follow the reference's declaration order (rogue/mod.rs:137-146).
+enum : uint8_t { S_PASSAGE = 0, S_FLOOR = 1, S_WALLX = 2, S_WALLY = 3, S_STAIR = 4, S_DOOR = 5, S_TRAP = 6, S_NONE = 7 };
+// CellAttr (field.rs:107-124) + two private bits.
+enum : uint8_t {
+  A_VISITED = 1, A_HIDDEN = 2, A_VISIBLE = 4, A_DRAWN = 8, A_LOCKED = 16, A_DARK = 32,
+  A_DOOR = 64,   // cell is in Floor.doors
+  A_MARK = 128   // generation scratch: maze passage member (cleared before the floor is used)
+};
+enum : uint8_t { K_NORMAL = 0, K_MAZE = 1, K_EMPTY = 2 };
+enum : uint8_t { RF_DARK = 1, RF_VISITED = 2, RF_GOLD = 4 };
+enum : uint8_t { MF_PRESENT = 1, MF_ACTIVE = 2 };
+// EnemyAttr bits that the path reads (enemies.rs:125-137)
+enum : uint32_t { EA_MEAN = 1u, EA_RANDOM = 0x200u, EA_CONFUSED = 0x400u };
+// MessageFlagInner (python/src/flags.rs:9-17)
+enum : uint32_t {
+  MSG_HIT_FROM = 1, MSG_HIT_TO = 2, MSG_MISS_TO = 4, MSG_MISS_FROM = 8, MSG_KILLED = 16, MSG_SECRET_DOOR = 32,
+  MSG_NO_DOWNSTAIR = 64
+};
+
+struct RoomD {       // rooms.rs:23-41 minus the generation-only cell sets
+  uint8_t kind;      // K_*
+  uint8_t flags;     // RF_*
+  uint8_t x0, y0;    // room / maze range (half-open), or up_left for K_EMPTY
+  uint8_t x1, y1;
+  uint16_t ncells;   // maze: number of passage cells
+};
+struct MonD {        // enemies.rs:159-171; level/defense/dice come from the kind table
+  uint8_t x, y, kind, flags;
+  int32_t hp;
+  uint32_t exp;
+};
+
+struct alignas(16) EnvState {
+  uint32_t rng[12];        // dungeon, item, enemy xorshift128 states
+  uint32_t seed[4];        // seed used by the next reset (thread_impls.rs:125-128)
+  uint32_t status[10];     // DISPLAYED status (stale semantics, state_impls.rs:63-65)
+  int32_t level;
+  int32_t hp, hp_max;
+  uint32_t exp;
+  int32_t plevel;
+  uint32_t food_left, quiet, gold;
+  uint32_t steps, message;
+  uint32_t episode;        // resets so far (drives fresh seeds when the config has none)
+  int16_t px, py;
+  uint8_t is_terminal, ui_dead, error, seeded;
+  uint8_t cache_n, cache_head, pad0, pad1;
+  uint8_t cache_x[NCACHE + 1], cache_y[NCACHE + 1];
+  uint32_t pad2;
+  RoomD rooms[MAX_ROOMS];
+  uint16_t item_pos[MAX_ROOMS];  // y*W+x or 0xFFFF ; slot = room id
+  uint32_t item_amt[MAX_ROOMS];
+  MonD mon[MAX_ROOMS];           // slot = room id the monster was spawned in
+};
+static_assert(sizeof(EnvState) % 16 == 0, "EnvState must be a multiple of 16 bytes");
+
+struct DevBatch {
+  int64_t n;
+  int32_t W, H, C, CP, HB, WW;
+  int64_t max_steps;
+  const rg_params* P;  // device copy
+  uint8_t* surface;
+  uint8_t* attr;
+  uint8_t* screen;
+  uint8_t* hist;
+  uint32_t* walk;
+  uint16_t* dist;
+  EnvState* st;
+  // observation block
+  uint32_t* status;
+  int32_t* reward;
+  uint8_t* done;
+  uint32_t* message;
+  uint8_t* error;
+  uint32_t* errflag;  // OR of all errors raised since the last rg_sync
+};
+
+}  // namespace rg

@@ -1,0 +1,61 @@
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "rogue-gym_b200", "python"))
+sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def fixtures():
+    with open(os.path.join(ROOT, "tests", "golden", "reference_fixtures.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    import oracle_py
+    oracle_py.build()
+    return oracle_py
+
+
+@pytest.fixture(scope="session")
+def cabi():
+    """The product's C-ABI library; built in-tree if the .so is missing (nvcc cross-compiles on CPU)."""
+    from rogue_gym_python import _cabi
+    if not os.path.exists(_cabi.LIB_PATH):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "rogue-gym_b200"), "-s", "-j4"])
+    _cabi.lib()
+    return _cabi
+
+
+@pytest.fixture(scope="session")
+def gpu(cabi):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from rogue_gym_python import _rogue_gym
+    return _rogue_gym
+
+
+MINI = {"width": 32, "height": 16, "seed": 4,
+        "dungeon": {"style": "rogue", "room_num_x": 2, "room_num_y": 2, "min_room_size": {"x": 4, "y": 4}}}
+MINI_NOMON = dict(MINI, enemies={"enemies": []})
+DEFAULT = {}
+CONFIGS = {"default": DEFAULT, "mini": MINI, "mini_nomon": MINI_NOMON,
+           "default_clear": {"hide_dungeon": False, "enemies": {"enemies": []}},
+           "wide": {"width": 160, "height": 48},
+           "odd": {"width": 50, "height": 19, "dungeon": {"style": "rogue", "room_num_x": 2, "room_num_y": 2}},
+           "deep": {"dungeon": {"style": "rogue", "dark_level": 2, "maze_rate_inv": 2, "hidden_passage_rate_inv": 4,
+                                "locked_door_rate_inv": 2, "amulet_level": 1}},
+           "grid4": {"width": 128, "height": 40, "dungeon": {"style": "rogue", "room_num_x": 4, "room_num_y": 4,
+                                                           "max_empty_rooms": 6}}}

@@ -1,0 +1,64 @@
+"""Writes tests/golden/reference_fixtures.json from the reference's own test data.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+    python tests/golden/make_golden.py
+It imports the reference's python/tests/data.py (pure data, no extension module needed) and
+records, next to each vector, the reference test that uses it and the expectation that test
+asserts. The Rust extension itself cannot be built here (no rustc/cargo), so these live
+fixtures are the reference's only executable-independent known answers.
+"""
+import json
+import os
+import sys
+
+REF = "/root/reference/python/tests"
+sys.path.insert(0, REF)
+import data  # noqa: E402
+
+out = {
+    "source": "kngwyu/rogue-gym @ c78608b python/tests/data.py",
+    "seed1_dungeon_clear": {
+        "cite": "python/tests/data.py:83-108, used by python/tests/test_ff_env.py:14-16",
+        "config": {"seed": 1, "hide_dungeon": False, "enemies": {"enemies": []}},
+        "screen": data.SEED1_DUNGEON_CLEAR,
+    },
+    "first_floor": {
+        "cite": "python/tests/test_ff_env.py:5-22",
+        "config": {"seed": 1, "hide_dungeon": False, "enemies": {"enemies": []}},
+        "keys": data.CMD_STR2,
+        "stair_reward": 100.0,
+        "expect_reward": 102,
+        "expect_done": True,
+        "image_status_flag": 1,
+        "expect_image_shape": [18, 24, 80],
+    },
+    "stair_reward": {
+        "cite": "python/tests/test_st_env.py:11-37",
+        "config": {"width": 32, "height": 16, "seed": 5, "hide_dungeon": False,
+                   "dungeon": {"style": "rogue", "room_num_x": 2, "room_num_y": 2},
+                   "enemies": {"enemies": []}},
+        "keys": [data.CMD_STR3, data.CMD_STR4],
+        "stair_reward": 100.0,
+        "expect_rewards": [104.0, 100.0],
+        "image_status_flag": 1 | 2 | 128,
+        "expect_image_shape": [21, 16, 32],
+        "expect_img_17_0_0": 3.0,
+        "expect_img_18_0_0": 12.0,
+        "expect_full_status_vec": [3, 12, 12, 16, 16, 0, 1, 0, 0],
+    },
+    "move_enemy": {
+        "cite": "core/src/dungeon/rogue/mod.rs:566-578 (test_move_enemy)",
+        "config": {"width": 32, "height": 16, "seed": 5,
+                   "dungeon": {"style": "rogue", "room_num_x": 2, "room_num_y": 2}},
+        "from": [9, 9], "to": [28, 4], "expect": [10, 9],
+    },
+    "stale": {
+        "note": "SEED1_DUNGEON/2/3 + CMD_STR/CMD_STR5 are stale in the reference (21 rows vs 24; SURVEY §8c-3); "
+                "kept only as inputs",
+        "cmd_str": data.CMD_STR, "cmd_str5": data.CMD_STR5,
+    },
+}
+dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_fixtures.json")
+with open(dst, "w") as f:
+    json.dump(out, f, indent=1)
+print("wrote", dst)

@@ -1,0 +1,101 @@
+"""Shared helpers of the GPU parity tests: canonical state dumps of both sides and diffs."""
+import ctypes as C
+
+import numpy as np
+
+SCALAR_FIELDS = ("level", "px", "py", "hp", "hp_max", "exp", "plevel", "food_left", "quiet", "gold", "ui_dead", "steps",
+                 "is_terminal", "message", "error", "n_monsters", "n_items", "n_cache", "status", "rng")
+KEYS19 = np.frombuffer(b".hjklnbuy>sHJKLNBUY", np.uint8)
+
+
+def gpu_dump(batch, env, with_maps=True):
+    """rg_dump_env of one env of a rogue_gym_python._rogue_gym._Batch."""
+    from rogue_gym_python import _cabi
+    Cc = batch.C
+    surface = np.zeros(Cc, np.uint8)
+    attr = np.zeros(Cc, np.uint8)
+    mons = np.zeros((_cabi.MAX_ROOMS, 8), np.int32)
+    items = np.zeros((_cabi.MAX_ROOMS, 3), np.int32)
+    cxy = np.zeros((_cabi.DIST_CACHE, 2), np.int32)
+    maps = np.zeros((_cabi.DIST_CACHE, Cc), np.uint16) if with_maps else None
+    rooms = np.zeros((_cabi.MAX_ROOMS, 8), np.int32)
+    d = _cabi.Dump()
+    d.surface, d.attr, d.monsters, d.items = surface.ctypes.data, attr.ctypes.data, mons.ctypes.data, items.ctypes.data
+    d.cache_xy, d.rooms = cxy.ctypes.data, rooms.ctypes.data
+    d.cache_maps = maps.ctypes.data if with_maps else None
+    _cabi.check(batch.L.rg_dump_env(batch.h, env, C.byref(d)), batch.h)
+    s = d.s.as_dict()
+    nrooms = batch.params.room_num_x * batch.params.room_num_y
+    return dict(scalars=s, surface=surface, attr=attr & 0x7F, monsters=mons[: s["n_monsters"]], items=items[: s["n_items"]],
+                cache_xy=cxy[: s["n_cache"]], cache_maps=(maps[: s["n_cache"]] if with_maps else None), rooms=rooms[:nrooms])
+
+
+def oracle_dump(env, with_maps=True):
+    s = env.scalars().as_dict()
+    surface, attr = env.grid()
+    mons, items = env.entities()
+    cxy, maps = env.dist_cache(with_maps)
+    return dict(scalars=s, surface=surface.ravel(), attr=attr.ravel(), monsters=mons, items=items, cache_xy=cxy,
+                cache_maps=maps, rooms=env.rooms())
+
+
+def diff_dumps(g, o, W):
+    """Returns a list of human-readable differences (empty = identical)."""
+    out = []
+    if o["scalars"]["error"] in (3, 4) or g["scalars"]["error"] in (3, 4):
+        # a panicked env stops mid-step on both sides; only the error itself is defined
+        if o["scalars"]["error"] != g["scalars"]["error"]:
+            out.append("error: gpu %d oracle %d" % (g["scalars"]["error"], o["scalars"]["error"]))
+        return out
+    for k in SCALAR_FIELDS:
+        if g["scalars"][k] != o["scalars"][k]:
+            out.append("scalar %s: gpu %s oracle %s" % (k, g["scalars"][k], o["scalars"][k]))
+    for k in ("surface", "attr"):
+        bad = np.nonzero(g[k] != o[k])[0]
+        if len(bad):
+            out.append("%s differs at %d cells, first (x,y,gpu,oracle): %s" % (
+                k, len(bad), [(int(i % W), int(i // W), int(g[k][i]), int(o[k][i])) for i in bad[:6]]))
+    for k in ("monsters", "items", "cache_xy", "rooms"):
+        if g[k].shape != o[k].shape or not np.array_equal(g[k], o[k]):
+            out.append("%s: gpu %s oracle %s" % (k, g[k].tolist(), o[k].tolist()))
+    if g["cache_maps"] is not None and o["cache_maps"] is not None and g["cache_maps"].shape == o["cache_maps"].shape:
+        for i in range(len(g["cache_maps"])):
+            bad = np.nonzero(g["cache_maps"][i] != o["cache_maps"][i])[0]
+            if len(bad):
+                out.append("dist map %d differs at %d cells, first (x,y,gpu,oracle): %s" % (
+                    i, len(bad), [(int(j % W), int(j // W), int(g["cache_maps"][i][j]), int(o["cache_maps"][i][j]))
+                                  for j in bad[:6]]))
+    return out
+
+
+def render(screen_row, W):
+    raw = bytes(screen_row)
+    return "\n".join(raw[i:i + W].decode("latin-1") for i in range(0, len(raw), W))
+
+
+def diff_obs(batch, ob, step, W, live=None):
+    """Compares the host mirrors of a _Batch with OracleBatch.obs(); returns a list of differences."""
+    out = []
+    n = batch.n
+    if live is None:
+        live = np.ones(n, bool)
+    pairs = (("screen", batch.screen, ob["screen"]), ("history", batch.history, ob["history"]),
+             ("status", batch.status, ob["status"]), ("message", batch.message, ob["message"]),
+             ("done", batch.done, ob["done"]))
+    for name, g, o in pairs:
+        neq = (g != o)
+        if neq.ndim > 1:
+            neq = neq.any(axis=1)
+        neq &= live
+        if neq.any():
+            i = int(np.nonzero(neq)[0][0])
+            msg = "step %d: %s differs for %d envs, first env %d" % (step, name, int(neq.sum()), i)
+            if name in ("screen",):
+                msg += "\n--- gpu\n%s\n--- oracle\n%s" % (render(g[i], W), render(o[i], W))
+            elif name == "history":
+                bad = np.nonzero(g[i] != o[i])[0]
+                msg += " cells %s" % [(int(j % W), int(j // W), int(g[i][j]), int(o[i][j])) for j in bad[:8]]
+            else:
+                msg += ": gpu %s oracle %s" % (g[i].tolist(), o[i].tolist())
+            out.append(msg)
+    return out

@@ -1,0 +1,106 @@
+"""The CPU oracle against every live known answer the reference holds for the path
+(SURVEY.md §8c-3). No GPU needed."""
+import numpy as np
+
+
+def _reward_run(oracle, cfg, key_strs, stair_reward):
+    """RogueEnv.step(str) + StairRewardEnv / FirstFloorEnv (python/rogue_gym/envs/wrappers.py:12-44)."""
+    env = oracle.OracleEnv(cfg)
+    rewards, level = [], 1
+    for keys in key_strs:
+        gold_before = int(env.obs()["status"][1])
+        env.react_str(keys)
+        st = env.obs()["status"]
+        r = int(st[1]) - gold_before
+        if int(st[0]) > level:
+            level = int(st[0])
+            r += stair_reward
+        rewards.append(r)
+    return env, rewards
+
+
+def test_seed1_floor_cell_for_cell(oracle, fixtures):
+    fx = fixtures["seed1_dungeon_clear"]
+    env = oracle.OracleEnv(fx["config"])
+    assert env.dungeon() == fx["screen"]
+
+
+def test_first_floor_env(oracle, fixtures):
+    fx = fixtures["first_floor"]
+    env, rewards = _reward_run(oracle, fx["config"], [fx["keys"]], fx["stair_reward"])
+    assert rewards == [fx["expect_reward"]]
+    assert int(env.obs()["status"][0]) == 2  # FirstFloorEnv: done when level 2 is reached
+    img = env.encode(1, fx["image_status_flag"], False)
+    assert list(img.shape) == fx["expect_image_shape"]
+
+
+def test_stair_reward_env(oracle, fixtures):
+    fx = fixtures["stair_reward"]
+    env, rewards = _reward_run(oracle, fx["config"], fx["keys"], fx["stair_reward"])
+    assert rewards == fx["expect_rewards"]
+    img = env.encode(1, fx["image_status_flag"], True)
+    assert list(img.shape) == fx["expect_image_shape"]
+    assert img[17][0][0] == fx["expect_img_17_0_0"]
+    assert img[18][0][0] == fx["expect_img_18_0_0"]
+    st = env.obs()["status"]
+    assert [int(st[i]) for i in (0, 2, 3, 4, 5, 6, 7, 8, 9)] == fx["expect_full_status_vec"]
+
+
+def test_move_enemy_tie_break(oracle, fixtures):
+    fx = fixtures["move_enemy"]
+    env = oracle.OracleEnv(fx["config"])
+    kind, nxt = env.test_move_enemy(tuple(fx["from"]), tuple(fx["to"]))
+    assert kind == 1 and list(nxt) == fx["expect"]
+
+
+def test_noaction_and_max_steps(oracle):
+    """python/tests/test_rogue_env.py:28-44: '.' changes nothing; done at max_steps."""
+    env = oracle.OracleEnv({"seed": 1}, max_steps=5)
+    before = env.obs()
+    for i in range(5):
+        assert not env.obs()["is_terminal"]
+        env.react(".")
+    after = env.obs()
+    assert after["is_terminal"]
+    assert np.array_equal(before["screen"], after["screen"])
+
+
+def test_same_seed_same_game_and_keys_diverge(oracle):
+    """python/src/thread_impls.rs:137-174."""
+    envs = [oracle.OracleEnv({"seed": 3}) for _ in range(4)]
+    assert len({e.state_hash() for e in envs}) == 1
+    for e, k in zip(envs, "hjkl"):
+        e.react(k)
+    assert len({e.state_hash() for e in envs}) > 1
+
+
+def test_auto_reset_returns_fresh_state_flagged_terminal(oracle):
+    env = oracle.OracleEnv({"seed": 2}, max_steps=3)
+    first = env.obs()["screen"].copy()
+    for _ in range(2):
+        env.step_auto("h")
+        assert not env.obs()["is_terminal"]
+    env.step_auto("h")
+    o = env.obs()
+    assert o["is_terminal"] and np.array_equal(o["screen"], first) and env.scalars().steps == 0
+
+
+def test_errors(oracle):
+    import pytest
+    env = oracle.OracleEnv({"seed": 2})
+    with pytest.raises(oracle.OracleError) as ei:
+        env.react("x")
+    assert ei.value.code == 1
+    assert env.scalars().steps == 0
+
+
+def test_batch_rollout_is_deterministic(oracle):
+    ids = np.arange(64)
+    digests = []
+    for _ in range(2):
+        b = oracle.OracleBatch({}, 64, seeds=list(range(1, 65)), threads=4)
+        b.reset()
+        for t in range(150):
+            b.step(oracle.synthetic_actions(t, ids))
+        digests.append(b.hashes())
+    assert np.array_equal(digests[0], digests[1])
