@@ -37,6 +37,7 @@ struct rg_batch {
   std::vector<void*> dev_allocs;
   std::string err;
   int64_t launches = 0;
+  int step_parity = 0;
 };
 
 namespace {
@@ -126,10 +127,40 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
   d.HB = ((d.CP / 8) + 15) / 16 * 16;
   d.WW = (d.W + 31) / 32;
   d.max_steps = max_steps;
+  d.nx = P.room_num_x;
+  d.ny = P.room_num_y;
+  d.rsx = d.W / d.nx;
+  d.rsy = d.H / d.ny;
   const size_t N = (size_t)n_envs;
+  {
+    cudaDeviceProp prop;
+    RG_TRY(cudaGetDeviceProperties(&prop, device));
+    d.gen_blocks = prop.multiProcessorCount * 4;  // persistent grid-stride grid of the generation kernel
+  }
   RG_TRY(dev_alloc(b, &b->dP, 1));
   RG_TRY(cudaMemcpy(b->dP, &P, sizeof(P), cudaMemcpyHostToDevice));
   d.P = b->dP;
+  {  // Floor::cd_to_room_id (floor.rs:194-200) as a table: the sector grid of rooms.rs:176,191-206
+    uint8_t lut[208];
+    memset(lut, 0xFF, sizeof(lut));
+    for (int x = 0; x < d.W; ++x)
+      if (x / d.rsx < d.nx) lut[x] = (uint8_t)(x / d.rsx);
+    for (int yi = 0; yi < d.ny; ++yi) {
+      int ry = d.rsy, ay0;
+      if (yi == 0) {
+        ry -= 1;
+        ay0 = 1;
+      } else {
+        ay0 = ry * yi;
+      }
+      if (ay0 + ry == d.H) ry -= 1;
+      for (int y = ay0; y < ay0 + ry && y < d.H; ++y) lut[160 + y] = (uint8_t)yi;
+    }
+    uint8_t* dl = nullptr;
+    RG_TRY(dev_alloc(b, &dl, sizeof(lut)));
+    RG_TRY(cudaMemcpy(dl, lut, sizeof(lut), cudaMemcpyHostToDevice));
+    d.room_lut = dl;
+  }
   RG_TRY(dev_alloc(b, &d.surface, N * d.CP));
   RG_TRY(dev_alloc(b, &d.attr, N * d.CP));
   RG_TRY(dev_alloc(b, &d.screen, N * d.CP));
@@ -143,6 +174,9 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
   RG_TRY(dev_alloc(b, &d.message, N));
   RG_TRY(dev_alloc(b, &d.error, N));
   RG_TRY(dev_alloc(b, &d.errflag, 1));
+  RG_TRY(dev_alloc(b, &d.defer_list, N));
+  RG_TRY(dev_alloc(b, &d.defer_count, 4));
+  RG_TRY(cudaMemsetAsync(d.defer_count, 0, 16, b->stream));
   RG_TRY(dev_alloc(b, &b->d_actions, N));
   RG_TRY(dev_alloc(b, &b->d_u64, 2 * N));
   RG_TRY(dev_alloc(b, &b->d_out3, 4));
@@ -280,8 +314,9 @@ int rg_reset(rg_batch* b) {
 int rg_step(rg_batch* b, const uint8_t* actions_dev, int auto_reset) {
   if (!b || !actions_dev) return set_err(b, RG_ERR_ARG, "rg_step: null argument");
   RG_CUDA(b, cudaSetDevice(b->device));
-  RG_CUDA(b, rg::launch_step(b->d, actions_dev, auto_reset, b->stream));
-  b->launches += 1;
+  RG_CUDA(b, rg::launch_step(b->d, actions_dev, auto_reset, (int)(b->step_parity & 1), b->stream));
+  b->step_parity ^= 1;
+  b->launches += 2;
   return RG_OK;
 }
 

@@ -91,6 +91,8 @@ struct Ctx {
   uint8_t* S;         // smem surface plane [CP]
   uint8_t* A;         // smem attr plane [CP]
   EnvState* st;       // smem
+  const uint8_t* col_room;  // global [160] sector column of x (0xFF = none)
+  const uint8_t* row_room;  // global [48]  sector row of y (0xFF = none: rows 0, H-1 and beyond the grid)
   const rg_params* P; // global (read-only)
   int W, H, C, CP, WW;
   int lane;
@@ -121,15 +123,12 @@ RG_DEV void room_area(const Ctx& c, int i, int& ax0, int& ay0, int& ax1, int& ay
   ax1 = ax0 + c.rsx;
   ay1 = ay0 + ry;
 }
-// Floor::cd_to_room_id floor.rs:194-200 (areas are disjoint, so "first" = "the")
+// Floor::cd_to_room_id floor.rs:194-200 (areas are disjoint, so "first" = "the"). The sector of a
+// column / row is a pure function of the config; it is tabulated once per batch by the host (rg_api.cu).
 RG_DEV int room_of(const Ctx& c, int x, int y) {
-  if (x < 0 || y < 0) return -1;
-  int xi = x / c.rsx, yi = y / c.rsy;
-  if (xi >= c.nx || yi >= c.ny) return -1;
-  int i = yi * c.nx + xi;
-  int ax0, ay0, ax1, ay1;
-  room_area(c, i, ax0, ay0, ax1, ay1);
-  return (x >= ax0 && x < ax1 && y >= ay0 && y < ay1) ? i : -1;
+  if (x < 0 || y < 0 || x >= c.W || y >= c.H) return -1;
+  const uint32_t cx = __ldg(c.col_room + x), ry = __ldg(c.row_room + y);
+  return (cx == 0xFFu || ry == 0xFFu) ? -1 : (int)(ry * c.nx + cx);
 }
 RG_DEV bool in_rect(const RoomD& r, int x, int y) { return x >= r.x0 && x < r.x1 && y >= r.y0 && y < r.y1; }
 RG_DEV bool inb(const Ctx& c, int x, int y) { return x >= 0 && y >= 0 && x < c.W && y < c.H; }
@@ -866,8 +865,9 @@ __device__ const uint16_t* cached_dist_map(Ctx& c, int tx, int ty) {
 // ------------------------------------------------------------------ monsters
 // `moved` = monsters already re-inserted this turn; skip(q) = a moved-active or placed monster
 // stands on q (enemies.rs:383-384).
-RG_DEV bool cell_blocked(const Ctx& c, int x, int y, uint32_t moved) {
+__device__ __noinline__ bool cell_blocked(const Ctx& c, int x, int y, uint32_t moved) {
   bool hit = false;
+#pragma unroll 1
   for (int m = 0; m < c.nrooms; ++m) {
     MonD mo = c.st->mon[m];
     bool counts = (mo.flags & MF_PRESENT) && (!(mo.flags & MF_ACTIVE) || ((moved >> m) & 1u));
@@ -1167,13 +1167,16 @@ __device__ void refresh_status(Ctx& c) {
   st->status[9] = st->food_left <= hunger ? 2u : (st->food_left <= hunger * 2 ? 1u : 0u);
 }
 
-// actions::process_action actions.rs:16-65. act: 0 Move, 1 MoveUntil, 2 Search, 3 DownStair
+// actions::process_action actions.rs:16-65. act: 0 Move, 1 MoveUntil, 2 Search, 3 DownStair.
+// HOT: the caller has already routed "DownStair on a stair" to the generation kernel, so the
+// floor generator is not compiled into the hot kernel at all.
+template <bool HOT>
 __device__ void process_action(Ctx& c, int act, int d) {
   EnvState* st = c.st;
   bool ui = false;
   if (act == 3) {
-    if (c.S[st->py * c.W + st->px] == S_STAIR) {
-      new_level(&c, false);
+    if (!HOT && c.S[st->py * c.W + st->px] == S_STAIR) {
+      if constexpr (!HOT) new_level(&c, false);
       c.redraw = 1;
       c.status_upd = 1;
     } else {

@@ -7,17 +7,20 @@
 namespace rg {
 
 constexpr int WARPS_PER_BLOCK = 4;
+RG_DEV size_t warp_smem(const DevBatch& b) { return 2 * (size_t)b.CP + sizeof(EnvState); }
 
 // Stage one env's small state into shared memory and fill the context.
 RG_DEV void fill_ctx(const DevBatch& b, Ctx& c, unsigned char* base, int64_t env) {
   c.S = base;
   c.A = base + b.CP;
   c.st = reinterpret_cast<EnvState*>(base + 2 * (size_t)b.CP);
+  c.col_room = b.room_lut;
+  c.row_room = b.room_lut + 160;
   c.P = b.P;
   c.W = b.W; c.H = b.H; c.C = b.C; c.CP = b.CP; c.WW = b.WW;
   c.lane = threadIdx.x & 31;
-  c.nx = b.P->room_num_x; c.ny = b.P->room_num_y;
-  c.rsx = b.W / c.nx; c.rsy = b.H / c.ny;
+  c.nx = b.nx; c.ny = b.ny;
+  c.rsx = b.rsx; c.rsy = b.rsy;
   c.nrooms = c.nx * c.ny;
   c.g_screen = b.screen + env * b.CP;
   c.g_hist = b.hist + env * b.HB;
@@ -32,14 +35,6 @@ RG_DEV void fill_ctx(const DevBatch& b, Ctx& c, unsigned char* base, int64_t env
   c.rd.load(c.st->rng);
   c.ri.load(c.st->rng + 4);
   c.re.load(c.st->rng + 8);
-}
-// Returns false for warps past the end of the batch.
-RG_DEV bool open_env(const DevBatch& b, Ctx& c, unsigned char* smem, int64_t& env) {
-  const int warp = threadIdx.x >> 5;
-  env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
-  if (env >= b.n) return false;
-  fill_ctx(b, c, smem + (size_t)warp * (2 * (size_t)b.CP + sizeof(EnvState)), env);
-  return true;
 }
 RG_DEV void load_grid(const DevBatch& b, Ctx& c, int64_t env) {
   const uint4* gs = reinterpret_cast<const uint4*>(b.surface + env * b.CP);
@@ -81,12 +76,23 @@ RG_DEV void emit_obs(const DevBatch& b, Ctx& c, int64_t env, int32_t reward, uin
   }
 }
 
+// Work the hot step kernel hands to the generation kernel (one entry per env, any order).
+enum : uint32_t { DEFER_STEP = 0u, DEFER_RESET = 0x80000000u };
+RG_DEV void defer(const DevBatch& b, Ctx& c, int64_t env, uint32_t code, int parity) {
+  if (c.lane == 0) {
+    uint32_t slot = atomicAdd(b.defer_count + parity, 1u);
+    b.defer_list[slot] = (uint32_t)env | code;
+  }
+}
+
 // ThreadWorker::run Instruction::Reset for every env (python/src/thread_impls.rs:117-124)
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_reset(DevBatch b) {
   extern __shared__ __align__(16) unsigned char smem[];
   Ctx c;
-  int64_t env;
-  if (!open_env(b, c, smem, env)) return;
+  const int warp = threadIdx.x >> 5;
+  const int64_t env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
+  if (env >= b.n) return;
+  fill_ctx(b, c, smem + (size_t)warp * warp_smem(b), env);
   reset_env(c);
   uint8_t err = 0;
   if (c.panic) {
@@ -98,15 +104,35 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_reset(DevBatch b) {
   close_env(b, c, env);
 }
 
-// GameStateImpl::react (python/src/state_impls.rs:51-79), and with auto_reset the conductor's
-// "reset terminal envs and return the fresh state flagged terminal" (thread_impls.rs:69-79).
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_step(DevBatch b, const uint8_t* __restrict__ actions,
-                                                              int auto_reset) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  Ctx c;
-  int64_t env;
-  if (!open_env(b, c, smem, env)) return;
+// One env-step: GameStateImpl::react (python/src/state_impls.rs:51-79) and, with auto_reset, the
+// conductor's "reset terminal envs and return the fresh state flagged terminal"
+// (thread_impls.rs:69-79).
+//
+// HOT = true is the kernel every env runs every step. It contains no floor generation: an env
+// that descends a stair, or that ends its episode under auto_reset, is appended to a work list
+// and finished by the same code compiled with HOT = false in k_step_gen (a second, usually tiny
+// launch). This keeps the hot kernel's instruction footprint and register count small, and
+// moves the long-tail warps (a floor build costs ~1000 dependent RNG draws) out of the way of
+// the 99 % of warps that only resolve a turn.
+template <bool HOT>
+RG_DEV void step_env(const DevBatch& b, Ctx& c, int64_t env, const uint8_t* __restrict__ actions, int auto_reset,
+                     int parity, bool reset_only) {
   EnvState* st = c.st;
+  if (!HOT && reset_only) {  // second half of a terminal step: the hot kernel left gold_before in reward[]
+    const uint32_t gold_before = (uint32_t)b.reward[env];
+    reset_env(c);
+    uint8_t err = 0;
+    if (c.panic) {
+      st->error = RG_ERR_PANIC;
+      err = RG_ERR_PANIC;
+    }
+    st->is_terminal = 1;
+    compose(c);
+    const int32_t diff = (int32_t)st->status[1] - (int32_t)gold_before;
+    emit_obs(b, c, env, diff > 0 ? diff : 0, err);
+    close_env(b, c, env);
+    return;
+  }
   const uint8_t key = actions[env];
   if (st->error == RG_ERR_PANIC || st->error == RG_ERR_SETTING) {  // the reference's worker is gone
     emit_obs(b, c, env, 0, st->error);
@@ -126,10 +152,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_step(DevBatch b, const
     emit_obs(b, c, env, 0, RG_ERR_IGNORED_INPUT);
     return;
   }
+  if (HOT && act == 3 && b.surface[env * b.CP + st->py * b.W + st->px] == S_STAIR) {
+    defer(b, c, env, DEFER_STEP, parity);  // nothing has been touched: the whole step runs in k_step_gen
+    return;
+  }
   const uint32_t gold_before = st->status[1];
   if (act != 4) {
     load_grid(b, c, env);
-    process_action(c, act, d);
+    process_action<HOT>(c, act, d);
   }
   uint8_t err = 0;
   if (c.panic) {
@@ -141,19 +171,55 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_step(DevBatch b, const
     st->steps += 1;
     st->is_terminal = (c.dead || (int64_t)st->steps >= b.max_steps) ? 1 : 0;
     if (st->is_terminal && auto_reset) {
-      reset_env(c);
-      if (c.panic) {
-        st->error = RG_ERR_PANIC;
-        err = RG_ERR_PANIC;
+      if (HOT) {  // write the finished turn back; the fresh game is built by k_step_gen
+        if (c.lane == 0) b.reward[env] = (int32_t)gold_before;
+        close_env(b, c, env);
+        defer(b, c, env, DEFER_RESET, parity);
+        return;
+      } else {
+        if constexpr (!HOT) reset_env(c);
+        if (c.panic) {
+          st->error = RG_ERR_PANIC;
+          err = RG_ERR_PANIC;
+        }
+        st->is_terminal = 1;
+        c.redraw = 1;
       }
-      st->is_terminal = 1;
-      c.redraw = 1;
     }
     if (c.redraw) compose(c);
   }
   const int32_t diff = (int32_t)st->status[1] - (int32_t)gold_before;
   emit_obs(b, c, env, diff > 0 ? diff : 0, err);
   close_env(b, c, env);
+}
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_step(DevBatch b, const uint8_t* __restrict__ actions,
+                                                                 int auto_reset, int parity) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  if (blockIdx.x == 0 && threadIdx.x == 0) b.defer_count[parity ^ 1] = 0;  // next step's counter
+  Ctx c;
+  const int warp = threadIdx.x >> 5;
+  const int64_t env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
+  if (env >= b.n) return;
+  fill_ctx(b, c, smem + (size_t)warp * warp_smem(b), env);
+  step_env<true>(b, c, env, actions, auto_reset, parity, false);
+}
+
+// Finishes the envs the hot kernel deferred: full-step path with floor generation, or the reset
+// half of a terminal step. Grid-stride over the work list; exits at once when the list is empty.
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_step_gen(DevBatch b, const uint8_t* __restrict__ actions,
+                                                                  int auto_reset, int parity) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const uint32_t count = b.defer_count[parity];
+  const int warp = threadIdx.x >> 5;
+  for (uint32_t i = blockIdx.x * WARPS_PER_BLOCK + warp; i < count; i += gridDim.x * WARPS_PER_BLOCK) {
+    const uint32_t item = b.defer_list[i];
+    const int64_t env = (int64_t)(item & 0x7FFFFFFFu);
+    Ctx c;
+    fill_ctx(b, c, smem + (size_t)warp * warp_smem(b), env);
+    step_env<false>(b, c, env, actions, auto_reset, parity, (item & DEFER_RESET) != 0);
+    __syncwarp();
+  }
 }
 
 // Dungeon::move_enemy with an always-false skip, for the known-answer test (rogue/mod.rs:566-578)
@@ -338,7 +404,8 @@ __global__ void k_unpack_hist(DevBatch b, uint8_t* __restrict__ out) {
 }
 
 // ---------------------------------------------------------------- launchers
-static size_t block_smem(const DevBatch& b) { return (size_t)WARPS_PER_BLOCK * (2 * (size_t)b.CP + sizeof(EnvState)); }
+static size_t one_warp_smem(const DevBatch& b) { return 2 * (size_t)b.CP + sizeof(EnvState); }
+static size_t block_smem(const DevBatch& b) { return (size_t)WARPS_PER_BLOCK * one_warp_smem(b); }
 
 cudaError_t configure_kernels(const DevBatch& b) {
   size_t sm = block_smem(b);
@@ -346,22 +413,27 @@ cudaError_t configure_kernels(const DevBatch& b) {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_test_move_enemy, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)(2 * (size_t)b.CP + sizeof(EnvState)));
+  e = cudaFuncSetAttribute(k_step_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_test_move_enemy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one_warp_smem(b));
 }
 cudaError_t launch_reset(const DevBatch& b, cudaStream_t s) {
   int blocks = (int)((b.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
   k_reset<<<blocks, WARPS_PER_BLOCK * 32, block_smem(b), s>>>(b);
   return cudaGetLastError();
 }
-cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_reset, cudaStream_t s) {
+cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_reset, int parity, cudaStream_t s) {
   int blocks = (int)((b.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-  k_step<<<blocks, WARPS_PER_BLOCK * 32, block_smem(b), s>>>(b, actions, auto_reset);
+  k_step<<<blocks, WARPS_PER_BLOCK * 32, block_smem(b), s>>>(b, actions, auto_reset, parity);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  int gen_blocks = blocks < b.gen_blocks ? blocks : b.gen_blocks;
+  k_step_gen<<<gen_blocks, WARPS_PER_BLOCK * 32, block_smem(b), s>>>(b, actions, auto_reset, parity);
   return cudaGetLastError();
 }
 cudaError_t launch_test_move_enemy(const DevBatch& b, int64_t env, int fx, int fy, int tx, int ty, int* out3,
                                    cudaStream_t s) {
-  k_test_move_enemy<<<1, 32, 2 * (size_t)b.CP + sizeof(EnvState), s>>>(b, env, fx, fy, tx, ty, out3);
+  k_test_move_enemy<<<1, 32, one_warp_smem(b), s>>>(b, env, fx, fy, tx, ty, out3);
   return cudaGetLastError();
 }
 cudaError_t launch_encode(const DevBatch& b, int mode, uint32_t flag, int with_hist, int channels, float* out,

@@ -78,8 +78,11 @@ static_assert(sizeof(EnvState) % 16 == 0, "EnvState must be a multiple of 16 byt
 struct DevBatch {
   int64_t n;
   int32_t W, H, C, CP, HB, WW;
+  int32_t nx, ny, rsx, rsy;  // room grid and sector size (rooms.rs:176)
+  int32_t gen_blocks;        // grid of the generation kernel
   int64_t max_steps;
   const rg_params* P;  // device copy
+  const uint8_t* room_lut;  // [160] sector column of x, then [48] sector row of y (0xFF = no sector)
   uint8_t* surface;
   uint8_t* attr;
   uint8_t* screen;
@@ -94,6 +97,8 @@ struct DevBatch {
   uint32_t* message;
   uint8_t* error;
   uint32_t* errflag;  // OR of all errors raised since the last rg_sync
+  uint32_t* defer_list;   // [N] env id | DEFER_* : work handed from k_step to k_step_gen
+  uint32_t* defer_count;  // [2] ping-pong by step parity
 };
 
 }  // namespace rg
