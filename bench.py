@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--config-json", default=None, help="experiments only: replaces config-default (the line is then not the headline workload)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -170,7 +171,7 @@ def main():
 
     K, Wm, n = args.steps, args.warmup, args.envs_per_gpu
     lo, hi = shard_range(n * world, rank, world)
-    shard = Shard(json.dumps(CONFIG), lo, hi, max_steps=MAX_STEPS, device=local_rank)
+    shard = Shard(args.config_json or json.dumps(CONFIG), lo, hi, max_steps=MAX_STEPS, device=local_rank)
     stream = torch.cuda.ExternalStream(shard.stream(), device=torch.device("cuda", local_rank))
 
     # synthetic inputs, resident in HBM before the timed region: actions for every step
@@ -265,7 +266,7 @@ def main():
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_total": total_envs, "envs_per_gpu": n, "sharding": "contiguous env-id blocks, no collective",
+            "config": {"workload": WORKLOAD if not args.config_json else "EXPERIMENT " + args.config_json, "envs_total": total_envs, "envs_per_gpu": n, "sharding": "contiguous env-id blocks, no collective",
                        "cache": "inputs larger than L2: each step touches ~%.0f MB of env state per GPU (L2 is 126 MB)" % (n * 9000 / 1e6),
                        "live_envs": int(live_all), "panicked_envs": int(total_envs - live_all),
                        "panic_note": "envs in a state where the reference panics (monster at x=0 probing x=-1, rogue/mod.rs:361) are sticky-dead like the reference's worker and are not counted",

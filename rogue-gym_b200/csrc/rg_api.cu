@@ -135,7 +135,8 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
   {
     cudaDeviceProp prop;
     RG_TRY(cudaGetDeviceProperties(&prop, device));
-    d.gen_blocks = prop.multiProcessorCount * 4;  // persistent grid-stride grid of the generation kernel
+    d.gen_warps = prop.multiProcessorCount * 16;  // grid-stride warps of the full-path kernel
+    d.mon_warps = prop.multiProcessorCount * 32;  // grid-stride warps of the monster kernel
   }
   RG_TRY(dev_alloc(b, &b->dP, 1));
   RG_TRY(cudaMemcpy(b->dP, &P, sizeof(P), cudaMemcpyHostToDevice));
@@ -167,6 +168,7 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
   RG_TRY(dev_alloc(b, &d.hist, N * d.HB));
   RG_TRY(dev_alloc(b, &d.walk, N * (size_t)d.H * d.WW));
   RG_TRY(dev_alloc(b, &d.dist, N * (size_t)rg::NCACHE * d.CP));
+  RG_TRY(dev_alloc(b, &d.bfs, N * (size_t)rg::NCACHE * 2 * d.H * d.WW));
   RG_TRY(dev_alloc(b, &d.st, N));
   RG_TRY(dev_alloc(b, &d.status, N * 10));
   RG_TRY(dev_alloc(b, &d.reward, N));
@@ -177,6 +179,9 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
   RG_TRY(dev_alloc(b, &d.defer_list, N));
   RG_TRY(dev_alloc(b, &d.defer_count, 4));
   RG_TRY(cudaMemsetAsync(d.defer_count, 0, 16, b->stream));
+  RG_TRY(dev_alloc(b, &d.mon_list, N));
+  RG_TRY(dev_alloc(b, &d.mon_count, 4));
+  RG_TRY(cudaMemsetAsync(d.mon_count, 0, 16, b->stream));
   RG_TRY(dev_alloc(b, &b->d_actions, N));
   RG_TRY(dev_alloc(b, &b->d_u64, 2 * N));
   RG_TRY(dev_alloc(b, &b->d_out3, 4));
@@ -316,7 +321,7 @@ int rg_step(rg_batch* b, const uint8_t* actions_dev, int auto_reset) {
   RG_CUDA(b, cudaSetDevice(b->device));
   RG_CUDA(b, rg::launch_step(b->d, actions_dev, auto_reset, (int)(b->step_parity & 1), b->stream));
   b->step_parity ^= 1;
-  b->launches += 2;
+  b->launches += 4;
   return RG_OK;
 }
 
@@ -423,6 +428,10 @@ int rg_dump_env(rg_batch* b, int64_t env, rg_dump* out) {
   if (!b || !out || env < 0 || env >= b->n) return set_err(b, RG_ERR_ARG, "rg_dump_env: bad argument");
   const DevBatch& d = b->d;
   RG_CUDA(b, cudaSetDevice(b->device));
+  if (out->cache_maps) {  // DistCache maps are evaluated lazily on the device: finish this env's maps first
+    RG_CUDA(b, rg::launch_complete_maps(d, env, env + 1, b->stream));
+    b->launches += 1;
+  }
   RG_CUDA(b, cudaStreamSynchronize(b->stream));
   EnvState st;
   RG_CUDA(b, cudaMemcpy(&st, d.st + env, sizeof(st), cudaMemcpyDeviceToHost));

@@ -101,6 +101,7 @@ struct Ctx {
   uint8_t* g_hist;
   uint32_t* g_walk;
   uint16_t* g_dist;
+  uint32_t* g_bfs;    // per cache slot: frontier rows then visited rows of a suspended BFS
   Rng rd, ri, re;     // dungeon / item / enemy streams (registers)
   // per-step reaction summary (state_impls.rs:57-75 collapses to these)
   uint32_t redraw, status_upd, dead, msg, hist_done, a_dirty, s_dirty, panic;
@@ -625,6 +626,8 @@ __device__ void build_walk(Ctx& c) {
   __syncwarp();
 }
 
+__device__ void complete_all_maps(Ctx& c);  // lazy DistCache, defined with the BFS below
+
 // rogue::Dungeon::new_level_ rogue/mod.rs:434-481 + Floor::gen_floor floor.rs:50-104
 // + setup_items :132-153 + setup_stair :156-167 + place_enemies :106-130,
 // then actions::new_level's player placement (actions.rs:134-137).
@@ -634,6 +637,7 @@ __device__ __noinline__ void new_level(Ctx* cp, bool is_initial) {
   EnvState* st = c.st;
   const int W = c.W;
   if (!is_initial) {
+    complete_all_maps(c);  // suspended DistCache maps belong to the floor that is about to be replaced
     // The descending step shows the visited map of the floor being left:
     // emit it now, before the planes are overwritten.
     __syncwarp();
@@ -765,27 +769,72 @@ RG_DEV void rows_down(const uint32_t (&X)[RPL][WORDS], uint32_t (&O)[RPL][WORDS]
     }
 }
 
+// Lazy evaluation. The reference computes the whole map when a DistCache entry is created
+// (rogue/mod.rs:504-517) but only ever reads the nine cells around a monster (:356-368). Here a
+// map is extended level by level only until every walkable cell of the 3x3 block that is about
+// to be read has its final distance (a BFS label never changes once written), then suspended:
+// the frontier / visited bitboards and the number of finished levels are kept per cache slot and
+// a later reader resumes from there. Every value that is read is therefore identical to the
+// reference's; `complete_all_maps` finishes all suspended maps before the walkability they were
+// started on changes (search unlocking a cell, descending to a new floor).
+constexpr uint16_t BFS_COMPLETE = 0xFFFFu;
+
 template <int WORDS, int RPL>
-__device__ __noinline__ void bfs_impl(const uint32_t* walk, uint16_t* out, int W, int H,
-                                      int CP, int fx, int fy, int lane) {
-  uint32_t Wc[RPL][WORDS], Wu[RPL][WORDS], Wd[RPL][WORDS], Vis[RPL][WORDS], F[RPL][WORDS];
+__device__ __noinline__ uint32_t bfs_impl(const uint32_t* __restrict__ walk, uint16_t* __restrict__ out,
+                                          uint32_t* __restrict__ Fg, uint32_t* __restrict__ Vg, int W, int H, int CP,
+                                          int fx, int fy, uint32_t done_levels, int nx0, int ny0, int lane) {
+  uint32_t Wc[RPL][WORDS], Wu[RPL][WORDS], Wd[RPL][WORDS], Vis[RPL][WORDS], F[RPL][WORDS], Need[RPL][WORDS];
+  const bool fresh = done_levels == 0;
+  const bool need_all = nx0 < -1;  // complete the map
 #pragma unroll
   for (int j = 0; j < RPL; ++j) {
-    int row = lane + 32 * j;
+    const int row = lane + 32 * j;
 #pragma unroll
     for (int w = 0; w < WORDS; ++w) {
       Wc[j][w] = row < H ? walk[row * WORDS + w] : 0u;
-      F[j][w] = (row == fy && (fx >> 5) == w) ? (1u << (fx & 31)) : 0u;
-      Vis[j][w] = F[j][w];
+      if (fresh) {
+        F[j][w] = (row == fy && (fx >> 5) == w) ? (1u << (fx & 31)) : 0u;
+        Vis[j][w] = F[j][w];
+      } else {
+        F[j][w] = row < H ? Fg[row * WORDS + w] : 0u;
+        Vis[j][w] = row < H ? Vg[row * WORDS + w] : 0u;
+      }
+      // the cells about to be read: columns nx0-1..nx0+1 of rows ny0-1..ny0+1, walkable ones only
+      uint32_t nd = 0;
+      if (need_all) {
+        nd = Wc[j][w];
+      } else if (row >= ny0 - 1 && row <= ny0 + 1) {
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int x = nx0 + dx;
+          if (x >= 0 && x < W && (x >> 5) == w) nd |= 1u << (x & 31);
+        }
+        nd &= Wc[j][w];
+      }
+      Need[j][w] = nd;
     }
   }
   rows_up<WORDS, RPL>(Wc, Wu, lane);
   rows_down<WORDS, RPL>(Wc, Wd, lane);
-  for (int i = lane; i < CP / 8; i += 32)
-    reinterpret_cast<uint4*>(out)[i] = make_uint4(RG_FULL, RG_FULL, RG_FULL, RG_FULL);
-  __syncwarp();
-  if (lane == (fy & 31)) out[fy * W + fx] = 0;
-  for (int level = 1; level < 0xFFFF; ++level) {
+  if (fresh) {
+    for (int i = lane; i < CP / 8; i += 32)
+      reinterpret_cast<uint4*>(out)[i] = make_uint4(RG_FULL, RG_FULL, RG_FULL, RG_FULL);
+    __syncwarp();
+    if (lane == (fy & 31)) out[fy * W + fx] = 0;
+  }
+  uint32_t level = done_levels;
+  bool complete = false;
+  for (;;) {
+    uint32_t unmet = 0;
+#pragma unroll
+    for (int j = 0; j < RPL; ++j)
+#pragma unroll
+      for (int w = 0; w < WORDS; ++w) unmet |= Need[j][w] & ~Vis[j][w];
+    if (!__any_sync(RG_FULL, unmet != 0)) {
+      complete = need_all;  // every walkable cell is labelled: nothing can ever be added
+      break;
+    }
+    ++level;
     uint32_t Fu[RPL][WORDS], Fd[RPL][WORDS];
     rows_up<WORDS, RPL>(F, Fu, lane);
     rows_down<WORDS, RPL>(F, Fd, lane);
@@ -815,51 +864,100 @@ __device__ __noinline__ void bfs_impl(const uint32_t* walk, uint16_t* out, int W
         F[j][w] = n[w];
         anynew |= n[w];
         uint32_t bits = n[w];
-        int base = (lane + 32 * j) * W + w * 32;
+        const int base = (lane + 32 * j) * W + w * 32;
         while (bits) {
-          int bpos = __ffs(bits) - 1;
+          const int bpos = __ffs(bits) - 1;
           bits &= bits - 1;
           out[base + bpos] = (uint16_t)level;
         }
       }
     }
-    if (!__any_sync(RG_FULL, anynew != 0)) break;
+    if (!__any_sync(RG_FULL, anynew != 0) || level >= 0xFFFEu) {
+      complete = true;
+      break;
+    }
   }
+  if (!complete) {
+#pragma unroll
+    for (int j = 0; j < RPL; ++j) {
+      const int row = lane + 32 * j;
+      if (row < H) {
+#pragma unroll
+        for (int w = 0; w < WORDS; ++w) {
+          Fg[row * WORDS + w] = F[j][w];
+          Vg[row * WORDS + w] = Vis[j][w];
+        }
+      }
+    }
+  }
+  __syncwarp();
+  return complete ? (uint32_t)BFS_COMPLETE : level;
+}
+
+// Extends the map in `slot` until the 3x3 block around (nx0, ny0) is final (nx0 = -2: until complete).
+__device__ void bfs_extend(Ctx& c, int slot, int nx0, int ny0) {
+  EnvState* st = c.st;
+  const uint32_t lvl = st->cache_lvl[slot];
+  if (lvl == BFS_COMPLETE) return;
+  uint16_t* out = c.g_dist + (size_t)slot * c.CP;
+  uint32_t* Fg = c.g_bfs + (size_t)slot * 2 * c.H * c.WW;
+  uint32_t* Vg = Fg + c.H * c.WW;
+  const int fx = st->cache_x[slot], fy = st->cache_y[slot];
+  const int rpl = (c.H + 31) / 32;
+  uint32_t r = BFS_COMPLETE;
+  bool ok = false;
+#define RG_BFS_CASE(WD, RP)                                                                                   \
+  if (c.WW == WD && rpl == RP) {                                                                              \
+    r = bfs_impl<WD, RP>(c.g_walk, out, Fg, Vg, c.W, c.H, c.CP, fx, fy, lvl, nx0, ny0, c.lane);                 \
+    ok = true;                                                                                                \
+  }
+  RG_BFS_CASE(3, 1) else RG_BFS_CASE(1, 1) else RG_BFS_CASE(2, 1) else RG_BFS_CASE(4, 1) else RG_BFS_CASE(5, 1)
+  else RG_BFS_CASE(1, 2) else RG_BFS_CASE(2, 2) else RG_BFS_CASE(3, 2) else RG_BFS_CASE(4, 2) else RG_BFS_CASE(5, 2)
+#undef RG_BFS_CASE
+  if (!ok) {
+    set_panic(c);
+    return;
+  }
+  st->cache_lvl[slot] = (uint16_t)r;
   __syncwarp();
 }
 
-__device__ void bfs(Ctx& c, int fx, int fy, uint16_t* out) {
-  const int rpl = (c.H + 31) / 32;
-#define RG_BFS_CASE(WD, RP) \
-  if (c.WW == WD && rpl == RP) { bfs_impl<WD, RP>(c.g_walk, out, c.W, c.H, c.CP, fx, fy, c.lane); return; }
-  RG_BFS_CASE(3, 1) RG_BFS_CASE(1, 1) RG_BFS_CASE(2, 1) RG_BFS_CASE(4, 1) RG_BFS_CASE(5, 1)
-  RG_BFS_CASE(1, 2) RG_BFS_CASE(2, 2) RG_BFS_CASE(3, 2) RG_BFS_CASE(4, 2) RG_BFS_CASE(5, 2)
-#undef RG_BFS_CASE
-  set_panic(c);
+// Finish every suspended map of this env (called before the walkability they were started on changes).
+__device__ void complete_all_maps(Ctx& c) {
+  EnvState* st = c.st;
+  const int n = st->cache_n, head = st->cache_head;
+  for (int k = 0; k < n; ++k) {
+    const int slot = (head + k) % NCACHE;
+    if (st->cache_lvl[slot] != BFS_COMPLETE) bfs_extend(c, slot, -2, -2);
+  }
 }
 
 // DistCache::make_dist_map rogue/mod.rs:504-517: FIFO of 9 keyed by the target coordinate,
 // never flushed (stale maps from earlier floors are used on purpose).
-__device__ const uint16_t* cached_dist_map(Ctx& c, int tx, int ty) {
+// Returns the slot; the map is final at least on the 3x3 block around (nx0, ny0).
+__device__ int cached_dist_map(Ctx& c, int tx, int ty, int nx0, int ny0) {
   EnvState* st = c.st;
   int n = st->cache_n, head = st->cache_head;
+  int slot = -1;
   for (int k = 0; k < n; ++k) {
-    int slot = (head + k) % NCACHE;
-    if (st->cache_x[slot] == tx && st->cache_y[slot] == ty) return c.g_dist + (size_t)slot * c.CP;
+    int s = (head + k) % NCACHE;
+    if (slot < 0 && st->cache_x[s] == tx && st->cache_y[s] == ty) slot = s;
   }
-  int slot;
-  if (n < NCACHE) {
-    slot = (head + n) % NCACHE;
-    st->cache_n = (uint8_t)(n + 1);
-  } else {
-    slot = head;
-    st->cache_head = (uint8_t)((head + 1) % NCACHE);
+  if (slot < 0) {
+    if (n < NCACHE) {
+      slot = (head + n) % NCACHE;
+      st->cache_n = (uint8_t)(n + 1);
+    } else {
+      slot = head;
+      st->cache_head = (uint8_t)((head + 1) % NCACHE);
+    }
+    st->cache_x[slot] = (uint8_t)tx;
+    st->cache_y[slot] = (uint8_t)ty;
+    st->cache_lvl[slot] = 0;
+    __syncwarp();
   }
-  st->cache_x[slot] = (uint8_t)tx;
-  st->cache_y[slot] = (uint8_t)ty;
-  uint16_t* out = c.g_dist + (size_t)slot * c.CP;
-  bfs(c, tx, ty, out);
-  return out;
+  bfs_extend(c, slot, nx0, ny0);
+  return slot;
 }
 
 // ------------------------------------------------------------------ monsters
@@ -880,8 +978,9 @@ enum { MV_CANT = 0, MV_CAN = 1, MV_REACH = 2 };
 // rogue::Dungeon::move_enemy rogue/mod.rs:339-375. PARALLEL over the 9 directions: lane d
 // probes neighbour d, the in-order semantics are rebuilt from ballots.
 __device__ int move_enemy(Ctx& c, int mx, int my, int tx, int ty, uint32_t moved, bool noskip, int& ox, int& oy) {
-  const uint16_t* dm = cached_dist_map(c, tx, ty);
+  const int slot = cached_dist_map(c, tx, ty, mx, my);
   if (c.panic) return MV_CANT;
+  const uint16_t* dm = c.g_dist + (size_t)slot * c.CP;
   const int d = c.lane;
   const bool valid = d < 9;
   const int nx = mx + ddx(valid ? d : 8), ny = my + ddy(valid ? d : 8);
@@ -1026,7 +1125,10 @@ __device__ bool heal(Ctx& c) {
   }
   return false;
 }
-// actions::after_turn actions.rs:67-80 + Player::turn_passed player.rs:163-176
+// actions::after_turn actions.rs:67-80 + Player::turn_passed player.rs:163-176.
+// HOT: only the player's half runs here; the monster phase (move_active_enemies) is a separate
+// kernel over the envs that have an active monster.
+template <bool HOT>
 __device__ bool after_turn(Ctx& c) {
   EnvState* st = c.st;
   st->food_left -= 1;  // wraps like the release build
@@ -1036,7 +1138,8 @@ __device__ bool after_turn(Ctx& c) {
     bool healed = heal(c);
     if (hungry || healed) c.status_upd = 1;
   }
-  return move_active_enemies(c);
+  if constexpr (HOT) return false;
+  else return move_active_enemies(c);
 }
 
 // Player::level_up + Leveling::check_level player.rs:185-197,346-352
@@ -1127,11 +1230,16 @@ __device__ MoveOut move_player(Ctx& c, int d) {
 __device__ void search(Ctx& c) {
   const int W = c.W;
   const int px = c.st->px, py = c.st->py;
+  bool maps_done = false;
   for (int d = 0; d < 8; ++d) {
     int nx = px + ddx(d), ny = py + ddy(d);
     if (!inb(c, nx, ny)) continue;
     int idx = ny * W + nx;
     bool opened = false;
+    if ((c.A[idx] & (A_HIDDEN | A_LOCKED)) && !maps_done) {  // walkability may change below
+      complete_all_maps(c);
+      maps_done = true;
+    }
     if ((c.A[idx] & A_HIDDEN) && c.rd.does_happen(c.P->passage_unlock_rate_inv)) {
       c.A[idx] = (c.A[idx] & (uint8_t)~(A_LOCKED | A_HIDDEN)) | A_VISIBLE;
       c.S[idx] = S_PASSAGE;
@@ -1182,26 +1290,28 @@ __device__ void process_action(Ctx& c, int act, int d) {
     } else {
       c.msg |= MSG_NO_DOWNSTAIR;
     }
-    if (!c.panic) ui = after_turn(c);
+    if (!c.panic) ui = after_turn<HOT>(c);
   } else if (act == 0) {
     MoveOut o = move_player(c, d);
     c.redraw |= o.redraw; c.status_upd |= o.status_upd; c.msg |= o.msg;
-    if (!c.panic) ui = after_turn(c);
+    if (!c.panic) ui = after_turn<HOT>(c);
   } else if (act == 1) {
-    for (int guard = 0; guard < 512 && !c.panic; ++guard) {
-      MoveOut o = move_player(c, d);
-      int idx = st->py * c.W + st->px;
-      // Dungeon::tile: the VISIBLE tile (rogue/mod.rs:321-328); keep running only on '.' / '#'
-      bool on_open = (c.A[idx] & A_VISIBLE) && (c.S[idx] == S_FLOOR || c.S[idx] == S_PASSAGE);
-      // the reactions of every sub-move matter only through these idempotent flags
-      c.redraw |= o.redraw; c.status_upd |= o.status_upd; c.msg |= o.msg;
-      if (o.done || !on_open) break;
-      ui = after_turn(c);
+    if constexpr (!HOT) {  // MoveUntil interleaves moves and monster phases: always the full-path kernel
+      for (int guard = 0; guard < 512 && !c.panic; ++guard) {
+        MoveOut o = move_player(c, d);
+        int idx = st->py * c.W + st->px;
+        // Dungeon::tile: the VISIBLE tile (rogue/mod.rs:321-328); keep running only on '.' / '#'
+        bool on_open = (c.A[idx] & A_VISIBLE) && (c.S[idx] == S_FLOOR || c.S[idx] == S_PASSAGE);
+        // the reactions of every sub-move matter only through these idempotent flags
+        c.redraw |= o.redraw; c.status_upd |= o.status_upd; c.msg |= o.msg;
+        if (o.done || !on_open) break;
+        ui = after_turn<false>(c);
+      }
     }
   } else if (act == 2) {
     search(c);
     c.redraw = 1;
-    if (!c.panic) ui = after_turn(c);
+    if (!c.panic) ui = after_turn<HOT>(c);
   }
   if (ui) st->ui_dead = 1;
 }
@@ -1213,25 +1323,32 @@ __device__ void compose(Ctx& c) {
   const int W = c.W, H = c.H;
   EnvState* st = c.st;
   __syncwarp();
-  for (int ch = c.lane; ch < c.CP / 16; ch += 32) {  // PARALLEL, 128-bit in / 128-bit out
-    uint4 s4 = *reinterpret_cast<const uint4*>(c.S + ch * 16);
-    uint4 a4 = *reinterpret_cast<const uint4*>(c.A + ch * 16);
-    uint32_t sv[4] = {s4.x, s4.y, s4.z, s4.w}, av[4] = {a4.x, a4.y, a4.z, a4.w}, ov[4];
+  const int lo = W, hi = (H - 1) * W;  // rows 0 and H-1 are never written (python/src/lib.rs:44)
+  for (int ch = c.lane; ch < c.CP / 16; ch += 32) {  // PARALLEL, 128-bit in / 128-bit out, 4 cells per op
+    const uint4 s4 = *reinterpret_cast<const uint4*>(c.S + ch * 16);
+    const uint4 a4 = *reinterpret_cast<const uint4*>(c.A + ch * 16);
+    const uint32_t sv[4] = {s4.x, s4.y, s4.z, s4.w}, av[4] = {a4.x, a4.y, a4.z, a4.w};
+    uint32_t ov[4];
     uint32_t hbits = 0;
     const int base = ch * 16;
+    const bool inside = base >= lo && base + 16 <= hi;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      uint32_t o = 0;
+      // Surface::tile (rogue/mod.rs:148-161) for four cells with one byte permute: the selector
+      // nibbles are the surface codes, the 8-entry table is "#.-|%+^ "
+      const uint32_t sel = (sv[q] & 7u) | ((sv[q] >> 4) & 0x70u) | ((sv[q] >> 8) & 0x700u) | ((sv[q] >> 12) & 0x7000u);
+      const uint32_t tiles = __byte_perm(0x7C2D2E23u, 0x205E2B25u, sel);
+      uint32_t vm = (av[q] >> 2) & 0x01010101u;  // IS_VISIBLE per byte (Cell::tile field.rs:92-98)
+      if (!inside) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        uint32_t s = (sv[q] >> (8 * k)) & 0xFFu, a = (av[q] >> (8 * k)) & 0xFFu;
-        int idx = base + q * 4 + k;
-        bool drawn = (a & A_VISIBLE) && idx >= W && idx < (H - 1) * W;  // rows 0 and H-1 are never written
-        uint32_t t = drawn ? (uint32_t)surface_tile((uint8_t)(s & 7u)) : 0x20u;
-        o |= t << (8 * k);
-        hbits |= (a & 1u) << (q * 4 + k);
+        for (int k = 0; k < 4; ++k) {
+          const int idx = base + q * 4 + k;
+          if (idx < lo || idx >= hi) vm &= ~(1u << (8 * k));
+        }
       }
-      ov[q] = o;
+      const uint32_t mask = (vm << 8) - vm;      // 0xFF in every visible byte
+      ov[q] = (tiles & mask) | (0x20202020u & ~mask);
+      hbits |= (((av[q] & 0x01010101u) * 0x01020408u) >> 24) << (4 * q);  // IS_VISITED bits (Floor::history_map)
     }
     *reinterpret_cast<uint4*>(c.g_screen + base) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
     if (!c.hist_done) reinterpret_cast<uint16_t*>(c.g_hist)[ch] = (uint16_t)hbits;

@@ -6,7 +6,16 @@
 
 namespace rg {
 
-constexpr int WARPS_PER_BLOCK = 4;
+#ifndef RG_WPB
+#define RG_WPB 1
+#endif
+#ifndef RG_HOT_MIN_BLOCKS
+#define RG_HOT_MIN_BLOCKS 32
+#endif
+// One warp per block: a block's registers and shared memory are released the moment its env is
+// done, so a warp that runs a BFS does not pin three finished neighbours (measured: 4 warps/block
+// 0.668 ms per step, 1 warp/block 0.626 ms at 64 registers, 65 536 envs).
+constexpr int WARPS_PER_BLOCK = RG_WPB;
 RG_DEV size_t warp_smem(const DevBatch& b) { return 2 * (size_t)b.CP + sizeof(EnvState); }
 
 // Stage one env's small state into shared memory and fill the context.
@@ -26,6 +35,7 @@ RG_DEV void fill_ctx(const DevBatch& b, Ctx& c, unsigned char* base, int64_t env
   c.g_hist = b.hist + env * b.HB;
   c.g_walk = b.walk + env * (int64_t)(b.H * b.WW);
   c.g_dist = b.dist + env * (int64_t)NCACHE * b.CP;
+  c.g_bfs = b.bfs + env * (int64_t)NCACHE * 2 * b.H * b.WW;
   c.redraw = c.status_upd = c.dead = c.msg = c.hist_done = c.a_dirty = c.s_dirty = c.panic = 0;
   // small state: 128-bit coalesced
   const uint4* src = reinterpret_cast<const uint4*>(b.st + env);
@@ -104,21 +114,175 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_reset(DevBatch b) {
   close_env(b, c, env);
 }
 
-// One env-step: GameStateImpl::react (python/src/state_impls.rs:51-79) and, with auto_reset, the
-// conductor's "reset terminal envs and return the fresh state flagged terminal"
-// (thread_impls.rs:69-79).
+RG_DEV void store_state(const DevBatch& b, Ctx& c, int64_t env) {
+  __syncwarp();
+  if (c.lane == 0) {
+    c.rd.store(c.st->rng);
+    c.ri.store(c.st->rng + 4);
+    c.re.store(c.st->rng + 8);
+  }
+  __syncwarp();
+  uint4* dst = reinterpret_cast<uint4*>(b.st + env);
+  const uint4* src = reinterpret_cast<const uint4*>(c.st);
+  for (int i = c.lane; i < (int)(sizeof(EnvState) / 16); i += 32) dst[i] = src[i];
+}
+RG_DEV void load_surface(const DevBatch& b, Ctx& c, int64_t env) {
+  const uint4* gs = reinterpret_cast<const uint4*>(b.surface + env * b.CP);
+  for (int i = c.lane; i < b.CP / 16; i += 32) reinterpret_cast<uint4*>(c.S)[i] = gs[i];
+  __syncwarp();
+}
+RG_DEV bool has_active_monster(const Ctx& c) {
+  bool any = false;
+#pragma unroll 1
+  for (int m = 0; m < c.nrooms; ++m) {
+    const uint8_t f = c.st->mon[m].flags;
+    any = any || ((f & MF_PRESENT) && (f & MF_ACTIVE));
+  }
+  return any;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One env-step = GameStateImpl::react (python/src/state_impls.rs:51-79) and, with auto_reset,
+// the conductor's "reset terminal envs and return the fresh state flagged terminal"
+// (thread_impls.rs:69-79). It runs as a short pipeline of kernels, each small enough to stay
+// resident in the instruction caches (the single-kernel version spent most of its stall samples
+// on instruction fetch: 17-30 k SASS instructions executed divergently by independent warps):
 //
-// HOT = true is the kernel every env runs every step. It contains no floor generation: an env
-// that descends a stair, or that ends its episode under auto_reset, is appended to a work list
-// and finished by the same code compiled with HOT = false in k_step_gen (a second, usually tiny
-// launch). This keeps the hot kernel's instruction footprint and register count small, and
-// moves the long-tail warps (a floor build costs ~1000 dependent RNG draws) out of the way of
-// the 99 % of warps that only resolve a turn.
-template <bool HOT>
-RG_DEV void step_env(const DevBatch& b, Ctx& c, int64_t env, const uint8_t* __restrict__ actions, int auto_reset,
-                     int parity, bool reset_only) {
+//   k_step_player   every env: key -> action -> player move / attack / pickup / search, hunger, heal.
+//                   Descents and MoveUntil go to the full-path list; envs with an active monster
+//                   go to the monster list.
+//   k_step_monsters monster list only: coin flips, lazy-BFS chase, attacks.
+//   k_step_finish   every env: message / status / step count / terminal, compose, observation.
+//                   Terminal envs under auto_reset go to the full-path list.
+//   k_step_gen      full-path list only: the whole step compiled as one piece with the floor
+//                   generator (descents, MoveUntil), or the reset half of a terminal step.
+//
+// The hand-over between the phases is EnvState::f_flags / f_msg / f_gold_before.
+// ---------------------------------------------------------------------------------------------
+RG_DEV void skip_env(const DevBatch& b, Ctx& c, int64_t env) {
+  if (c.lane == 0) b.st[env].f_flags = SF_SKIP;
+}
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_HOT_MIN_BLOCKS)
+k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset, int parity) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // next step's counters
+    b.defer_count[parity ^ 1] = 0;
+    b.mon_count[parity ^ 1] = 0;
+  }
+  Ctx c;
+  const int warp = threadIdx.x >> 5;
+  const int64_t env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
+  if (env >= b.n) return;
+  fill_ctx(b, c, smem + (size_t)warp * warp_smem(b), env);
   EnvState* st = c.st;
-  if (!HOT && reset_only) {  // second half of a terminal step: the hot kernel left gold_before in reward[]
+  const uint8_t key = actions[env];
+  if (st->error == RG_ERR_PANIC || st->error == RG_ERR_SETTING) {  // the reference's worker is gone
+    emit_obs(b, c, env, 0, st->error);
+    skip_env(b, c, env);
+    return;
+  }
+  if ((int64_t)st->steps > b.max_steps) {  // state_impls.rs:52-54
+    emit_obs(b, c, env, 0, 0);
+    skip_env(b, c, env);
+    return;
+  }
+  int d;
+  const int act = map_key(key, d);
+  if (act < 0) {  // ErrorKind::InvalidInput: nothing changes (core/src/lib.rs:322-327)
+    emit_obs(b, c, env, 0, RG_ERR_INVALID_INPUT);
+    skip_env(b, c, env);
+    return;
+  }
+  if (st->ui_dead) {  // UiState::Mordal(Grave) + Act => IgnoredInput (core/src/lib.rs:314)
+    emit_obs(b, c, env, 0, RG_ERR_IGNORED_INPUT);
+    skip_env(b, c, env);
+    return;
+  }
+  if (act == 1 || (act == 3 && b.surface[env * b.CP + st->py * b.W + st->px] == S_STAIR)) {
+    defer(b, c, env, DEFER_STEP, parity);  // nothing has been touched: the whole step runs in k_step_gen
+    skip_env(b, c, env);
+    return;
+  }
+  st->f_gold_before = st->status[1];
+  if (act == 0 || act == 2) {
+    load_grid(b, c, env);
+    process_action<true>(c, act, d);
+  } else if (act == 3) {
+    process_action<true>(c, act, d);  // NoDownStair: a turn passes, the grid is not consulted
+  }
+  st->f_msg = c.msg;
+  st->f_flags = (uint8_t)((c.redraw ? SF_REDRAW : 0) | (c.status_upd ? SF_STATUS : 0) | (c.panic ? SF_PANIC : 0));
+  if (act != 4 && !c.panic && has_active_monster(c)) {
+    if (c.lane == 0) b.mon_list[atomicAdd(b.mon_count + parity, 1u)] = (uint32_t)env;
+  }
+  close_env(b, c, env);
+}
+
+// actions::move_active_enemies (actions.rs:82-119) for the envs that have an active monster
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_HOT_MIN_BLOCKS)
+k_step_monsters(DevBatch b, int parity) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const uint32_t count = b.mon_count[parity];
+  const int warp = threadIdx.x >> 5;
+  for (uint32_t i = blockIdx.x * WARPS_PER_BLOCK + warp; i < count; i += gridDim.x * WARPS_PER_BLOCK) {
+    const int64_t env = (int64_t)b.mon_list[i];
+    Ctx c;
+    fill_ctx(b, c, smem + (size_t)warp * warp_smem(b), env);
+    load_surface(b, c, env);
+    EnvState* st = c.st;
+    c.msg = st->f_msg;
+    if (move_active_enemies(c)) st->ui_dead = 1;
+    st->f_msg = c.msg;
+    st->f_flags |= (uint8_t)((c.status_upd ? SF_STATUS : 0) | (c.dead ? SF_DEAD : 0) | (c.panic ? SF_PANIC : 0));
+    store_state(b, c, env);
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_HOT_MIN_BLOCKS)
+k_step_finish(DevBatch b, int auto_reset, int parity) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Ctx c;
+  const int warp = threadIdx.x >> 5;
+  const int64_t env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
+  if (env >= b.n) return;
+  if (b.st[env].f_flags & SF_SKIP) return;  // answered by the player kernel, or handed to k_step_gen
+  fill_ctx(b, c, smem + (size_t)warp * warp_smem(b), env);
+  EnvState* st = c.st;
+  const uint32_t flags = st->f_flags;
+  const uint32_t gold_before = st->f_gold_before;
+  uint8_t err = 0;
+  if (flags & SF_PANIC) {
+    st->error = RG_ERR_PANIC;
+    err = RG_ERR_PANIC;
+  } else {
+    st->message = st->f_msg;
+    if (flags & SF_STATUS) refresh_status(c);
+    st->steps += 1;
+    st->is_terminal = ((flags & SF_DEAD) || (int64_t)st->steps >= b.max_steps) ? 1 : 0;
+    if (st->is_terminal && auto_reset) {  // the fresh game is built by k_step_gen
+      if (c.lane == 0) b.reward[env] = (int32_t)gold_before;
+      store_state(b, c, env);
+      defer(b, c, env, DEFER_RESET, parity);
+      return;
+    }
+    if (flags & SF_REDRAW) {
+      load_grid(b, c, env);
+      compose(c);
+    }
+  }
+  const int32_t diff = (int32_t)st->status[1] - (int32_t)gold_before;
+  emit_obs(b, c, env, diff > 0 ? diff : 0, err);
+  store_state(b, c, env);
+}
+
+// The whole step as one piece (with the floor generator), for the envs on the full-path list:
+// descents, MoveUntil, and the reset half of a terminal step.
+RG_DEV void step_env_full(const DevBatch& b, Ctx& c, int64_t env, const uint8_t* __restrict__ actions, int auto_reset,
+                          bool reset_only) {
+  EnvState* st = c.st;
+  if (reset_only) {  // second half of a terminal step: k_step_finish left gold_before in reward[]
     const uint32_t gold_before = (uint32_t)b.reward[env];
     reset_env(c);
     uint8_t err = 0;
@@ -133,34 +297,12 @@ RG_DEV void step_env(const DevBatch& b, Ctx& c, int64_t env, const uint8_t* __re
     close_env(b, c, env);
     return;
   }
-  const uint8_t key = actions[env];
-  if (st->error == RG_ERR_PANIC || st->error == RG_ERR_SETTING) {  // the reference's worker is gone
-    emit_obs(b, c, env, 0, st->error);
-    return;
-  }
-  if ((int64_t)st->steps > b.max_steps) {  // state_impls.rs:52-54
-    emit_obs(b, c, env, 0, 0);
-    return;
-  }
+  // the player kernel has already checked the early-outs for this env
   int d;
-  const int act = map_key(key, d);
-  if (act < 0) {  // ErrorKind::InvalidInput: nothing changes (core/src/lib.rs:322-327)
-    emit_obs(b, c, env, 0, RG_ERR_INVALID_INPUT);
-    return;
-  }
-  if (st->ui_dead) {  // UiState::Mordal(Grave) + Act => IgnoredInput (core/src/lib.rs:314)
-    emit_obs(b, c, env, 0, RG_ERR_IGNORED_INPUT);
-    return;
-  }
-  if (HOT && act == 3 && b.surface[env * b.CP + st->py * b.W + st->px] == S_STAIR) {
-    defer(b, c, env, DEFER_STEP, parity);  // nothing has been touched: the whole step runs in k_step_gen
-    return;
-  }
+  const int act = map_key(actions[env], d);
   const uint32_t gold_before = st->status[1];
-  if (act != 4) {
-    load_grid(b, c, env);
-    process_action<HOT>(c, act, d);
-  }
+  load_grid(b, c, env);
+  process_action<false>(c, act, d);
   uint8_t err = 0;
   if (c.panic) {
     st->error = RG_ERR_PANIC;
@@ -171,20 +313,13 @@ RG_DEV void step_env(const DevBatch& b, Ctx& c, int64_t env, const uint8_t* __re
     st->steps += 1;
     st->is_terminal = (c.dead || (int64_t)st->steps >= b.max_steps) ? 1 : 0;
     if (st->is_terminal && auto_reset) {
-      if (HOT) {  // write the finished turn back; the fresh game is built by k_step_gen
-        if (c.lane == 0) b.reward[env] = (int32_t)gold_before;
-        close_env(b, c, env);
-        defer(b, c, env, DEFER_RESET, parity);
-        return;
-      } else {
-        if constexpr (!HOT) reset_env(c);
-        if (c.panic) {
-          st->error = RG_ERR_PANIC;
-          err = RG_ERR_PANIC;
-        }
-        st->is_terminal = 1;
-        c.redraw = 1;
+      reset_env(c);
+      if (c.panic) {
+        st->error = RG_ERR_PANIC;
+        err = RG_ERR_PANIC;
       }
+      st->is_terminal = 1;
+      c.redraw = 1;
     }
     if (c.redraw) compose(c);
   }
@@ -193,20 +328,7 @@ RG_DEV void step_env(const DevBatch& b, Ctx& c, int64_t env, const uint8_t* __re
   close_env(b, c, env);
 }
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_step(DevBatch b, const uint8_t* __restrict__ actions,
-                                                                 int auto_reset, int parity) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  if (blockIdx.x == 0 && threadIdx.x == 0) b.defer_count[parity ^ 1] = 0;  // next step's counter
-  Ctx c;
-  const int warp = threadIdx.x >> 5;
-  const int64_t env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
-  if (env >= b.n) return;
-  fill_ctx(b, c, smem + (size_t)warp * warp_smem(b), env);
-  step_env<true>(b, c, env, actions, auto_reset, parity, false);
-}
-
-// Finishes the envs the hot kernel deferred: full-step path with floor generation, or the reset
-// half of a terminal step. Grid-stride over the work list; exits at once when the list is empty.
+// Grid-stride over the full-path list; exits at once when the list is empty.
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_step_gen(DevBatch b, const uint8_t* __restrict__ actions,
                                                                   int auto_reset, int parity) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -217,7 +339,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_step_gen(DevBatch b, c
     const int64_t env = (int64_t)(item & 0x7FFFFFFFu);
     Ctx c;
     fill_ctx(b, c, smem + (size_t)warp * warp_smem(b), env);
-    step_env<false>(b, c, env, actions, auto_reset, parity, (item & DEFER_RESET) != 0);
+    step_env_full(b, c, env, actions, auto_reset, (item & DEFER_RESET) != 0);
     __syncwarp();
   }
 }
@@ -238,6 +360,22 @@ __global__ void k_test_move_enemy(DevBatch b, int64_t env_id, int fx, int fy, in
     out3[2] = oy;
   }
   close_env(b, c, env);
+}
+
+// Parity harness: finish every suspended DistCache map so that rg_dump_env can show whole maps.
+// Does not change anything observable (a finished map holds the values the reference holds).
+__global__ void __launch_bounds__(32) k_complete_maps(DevBatch b, int64_t env_lo, int64_t env_hi) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int64_t env = env_lo + blockIdx.x;
+  if (env >= env_hi) return;
+  Ctx c;
+  fill_ctx(b, c, smem, env);
+  complete_all_maps(c);
+  __syncwarp();
+  // only the cache directory changed
+  uint4* dst = reinterpret_cast<uint4*>(b.st + env);
+  const uint4* src = reinterpret_cast<const uint4*>(c.st);
+  for (int i = c.lane; i < (int)(sizeof(EnvState) / 16); i += 32) dst[i] = src[i];
 }
 
 // ---------------------------------------------------------------- observation encoders
@@ -411,9 +549,15 @@ cudaError_t configure_kernels(const DevBatch& b) {
   size_t sm = block_smem(b);
   cudaError_t e = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  e = cudaFuncSetAttribute(k_step_player, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_step_monsters, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_step_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_step_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_complete_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one_warp_smem(b));
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(k_test_move_enemy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one_warp_smem(b));
 }
@@ -423,12 +567,20 @@ cudaError_t launch_reset(const DevBatch& b, cudaStream_t s) {
   return cudaGetLastError();
 }
 cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_reset, int parity, cudaStream_t s) {
-  int blocks = (int)((b.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-  k_step<<<blocks, WARPS_PER_BLOCK * 32, block_smem(b), s>>>(b, actions, auto_reset, parity);
+  const int blocks = (int)((b.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+  const size_t sm = block_smem(b);
+  k_step_player<<<blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, actions, auto_reset, parity);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  int gen_blocks = blocks < b.gen_blocks ? blocks : b.gen_blocks;
-  k_step_gen<<<gen_blocks, WARPS_PER_BLOCK * 32, block_smem(b), s>>>(b, actions, auto_reset, parity);
+  int mon_blocks = b.mon_warps / WARPS_PER_BLOCK;
+  if (mon_blocks > blocks) mon_blocks = blocks;
+  k_step_monsters<<<mon_blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, parity);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  k_step_finish<<<blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, auto_reset, parity);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  int gen_blocks = b.gen_warps / WARPS_PER_BLOCK;
+  if (gen_blocks > blocks) gen_blocks = blocks;
+  k_step_gen<<<gen_blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, actions, auto_reset, parity);
   return cudaGetLastError();
 }
 cudaError_t launch_test_move_enemy(const DevBatch& b, int64_t env, int fx, int fy, int tx, int ty, int* out3,
@@ -439,6 +591,11 @@ cudaError_t launch_test_move_enemy(const DevBatch& b, int64_t env, int fx, int f
 cudaError_t launch_encode(const DevBatch& b, int mode, uint32_t flag, int with_hist, int channels, float* out,
                           cudaStream_t s) {
   k_encode<<<(unsigned)b.n, 256, 0, s>>>(b, mode, flag, with_hist, channels, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_complete_maps(const DevBatch& b, int64_t env_lo, int64_t env_hi, cudaStream_t s) {
+  if (env_hi <= env_lo) return cudaSuccess;
+  k_complete_maps<<<(unsigned)(env_hi - env_lo), 32, one_warp_smem(b), s>>>(b, env_lo, env_hi);
   return cudaGetLastError();
 }
 cudaError_t launch_seed(const DevBatch& b, const uint64_t* lo, const uint64_t* hi, int seeded, cudaStream_t s) {

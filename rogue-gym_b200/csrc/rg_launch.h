@@ -7,12 +7,13 @@
 namespace rg {
 cudaError_t configure_kernels(const DevBatch& b);
 cudaError_t launch_reset(const DevBatch& b, cudaStream_t s);
-// one env-step = the hot kernel + the generation kernel for the envs it deferred (2 launches)
+// one env-step = player, monster, finish and full-path kernels (4 launches)
 cudaError_t launch_step(const DevBatch& b, const uint8_t* actions_dev, int auto_reset, int parity, cudaStream_t s);
 cudaError_t launch_test_move_enemy(const DevBatch& b, int64_t env, int fx, int fy, int tx, int ty, int* out3_dev,
                                    cudaStream_t s);
 cudaError_t launch_encode(const DevBatch& b, int mode, uint32_t flag, int with_hist, int channels, float* out_dev,
                           cudaStream_t s);
+cudaError_t launch_complete_maps(const DevBatch& b, int64_t env_lo, int64_t env_hi, cudaStream_t s);
 cudaError_t launch_seed(const DevBatch& b, const uint64_t* lo_dev, const uint64_t* hi_dev, int seeded, cudaStream_t s);
 cudaError_t launch_unpack_hist(const DevBatch& b, uint8_t* out_dev, cudaStream_t s);
 cudaError_t launch_state_hash(const DevBatch& b, uint64_t* out_dev, cudaStream_t s);

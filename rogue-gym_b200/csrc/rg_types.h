@@ -8,6 +8,7 @@
 //   hist      u8  [N][HB]      visited bitmap shown to the agent(PlayerState.history, :33)
 //   walk      u32 [N][H][WW]   monster-walkable bitboard rows   (derived from surface; feeds the BFS)
 //   dist      u16 [N][9][CP]   DistCache maps                   (rogue/mod.rs:492-518)
+//   bfs       u32 [N][9][2][H][WW] frontier / visited bitboards of suspended (lazy) BFS maps
 //   st        EnvState [N]     everything scalar / small        (RunTime + GameStateImpl + PlayerState.status)
 // CP = W*H rounded up to 16, HB = CP/8 rounded up to 16, WW = ceil(W/32).
 #pragma once
@@ -31,6 +32,7 @@ enum : uint8_t {
 enum : uint8_t { K_NORMAL = 0, K_MAZE = 1, K_EMPTY = 2 };
 enum : uint8_t { RF_DARK = 1, RF_VISITED = 2, RF_GOLD = 4 };
 enum : uint8_t { MF_PRESENT = 1, MF_ACTIVE = 2 };
+enum : uint8_t { SF_REDRAW = 1, SF_STATUS = 2, SF_DEAD = 4, SF_SKIP = 8, SF_PANIC = 16 };
 // EnemyAttr bits that the path reads (enemies.rs:125-137)
 enum : uint32_t { EA_MEAN = 1u, EA_RANDOM = 0x200u, EA_CONFUSED = 0x400u };
 // MessageFlagInner (python/src/flags.rs:9-17)
@@ -68,6 +70,12 @@ struct alignas(16) EnvState {
   uint8_t cache_n, cache_head, pad0, pad1;
   uint8_t cache_x[NCACHE + 1], cache_y[NCACHE + 1];
   uint32_t pad2;
+  uint16_t cache_lvl[NCACHE + 1];  // BFS levels finished per slot, 0xFFFF = map complete (lazy DistCache)
+  // per-step hand-over between the phase kernels (player -> monsters -> finish)
+  uint32_t f_msg;          // message bits collected so far
+  uint32_t f_gold_before;  // displayed gold when the step began (reward = max(0, after - before))
+  uint8_t f_flags;         // SF_*
+  uint8_t pad3[3];
   RoomD rooms[MAX_ROOMS];
   uint16_t item_pos[MAX_ROOMS];  // y*W+x or 0xFFFF ; slot = room id
   uint32_t item_amt[MAX_ROOMS];
@@ -79,7 +87,7 @@ struct DevBatch {
   int64_t n;
   int32_t W, H, C, CP, HB, WW;
   int32_t nx, ny, rsx, rsy;  // room grid and sector size (rooms.rs:176)
-  int32_t gen_blocks;        // grid of the generation kernel
+  int32_t gen_warps;         // warps of the (grid-stride) generation kernel
   int64_t max_steps;
   const rg_params* P;  // device copy
   const uint8_t* room_lut;  // [160] sector column of x, then [48] sector row of y (0xFF = no sector)
@@ -89,6 +97,7 @@ struct DevBatch {
   uint8_t* hist;
   uint32_t* walk;
   uint16_t* dist;
+  uint32_t* bfs;       // u32 [N][9][2][H][WW] suspended-BFS frontier / visited rows
   EnvState* st;
   // observation block
   uint32_t* status;
@@ -97,8 +106,11 @@ struct DevBatch {
   uint32_t* message;
   uint8_t* error;
   uint32_t* errflag;  // OR of all errors raised since the last rg_sync
-  uint32_t* defer_list;   // [N] env id | DEFER_* : work handed from k_step to k_step_gen
+  uint32_t* defer_list;   // [N] env id | DEFER_* : work handed to the full-path kernel k_step_gen
   uint32_t* defer_count;  // [2] ping-pong by step parity
+  uint32_t* mon_list;     // [N] envs with an active monster this step (player kernel -> monster kernel)
+  uint32_t* mon_count;    // [2] ping-pong by step parity
+  int32_t mon_warps;      // warps of the (grid-stride) monster kernel
 };
 
 }  // namespace rg

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(HERE, "..", "..", "librogue_b200.so"))
+LIB_PATH = os.environ.get("ROGUE_B200_LIB") or os.path.normpath(os.path.join(HERE, "..", "..", "librogue_b200.so"))
 
 MAX_ENEMY_KINDS, MAX_DICE, MAX_EXPS, MAX_INIT_DRAWS, MAX_ROOMS, DIST_CACHE = 32, 4, 32, 8, 16, 9
 (RG_OK, RG_ERR_INVALID_INPUT, RG_ERR_IGNORED_INPUT, RG_ERR_PANIC, RG_ERR_SETTING, RG_ERR_PARSE, RG_ERR_CUDA,
