@@ -200,11 +200,13 @@ def main():
     ev0.record(stream)
     for t in range(Wm, total):
         shard.step_device(base_ptr + t * n)
+    shard.quiesce()  # the background next-episode generation is part of the job: wait for it too
     ev1.record(stream)
     barrier()
     clocks = sampler.finish()
     ms = ev0.elapsed_time(ev1)
     launches = shard.launches() - launches0
+    stats = shard.stats()
     shard.sync()
     err = shard.errors()
     live = int((err == 0).sum())
@@ -229,6 +231,7 @@ def main():
         e0.record(stream)
         for t in range(Wm, total):
             shard.step_host(hp + t * n, obs)  # H2D actions -> kernel -> D2H observation -> stream sync, every step
+        shard.quiesce()
         e1.record(stream)
         barrier()
         e2e_ms = e0.elapsed_time(e1)
@@ -270,7 +273,7 @@ def main():
                        "cache": "inputs larger than L2: each step touches ~%.0f MB of env state per GPU (L2 is 126 MB)" % (n * 9000 / 1e6),
                        "live_envs": int(live_all), "panicked_envs": int(total_envs - live_all),
                        "panic_note": "envs in a state where the reference panics (monster at x=0 probing x=-1, rogue/mod.rs:361) are sticky-dead like the reference's worker and are not counted",
-                       "state_digest_rank0": "%016x" % digest},
+                       "state_digest_rank0": "%016x" % digest, "events_rank0_since_create": stats},
             "clocks": clocks,
             "e2e": None if e2e_ms is None else {
                 "value": live_all * K / (e2e_ms_all * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d * world,

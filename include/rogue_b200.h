@@ -181,6 +181,13 @@ int rg_seed(rg_batch* b, const uint64_t* seed_lo, const uint64_t* seed_hi /* nul
 int rg_reset(rg_batch* b);
 int rg_step(rg_batch* b, const uint8_t* actions_dev, int auto_reset);
 int rg_step_host(rg_batch* b, const uint8_t* actions_host, int auto_reset, rg_host_obs* out);
+/* Makes the batch's stream wait for the background generation of next-episode games queued so
+ * far (asynchronous; used by benchmarks so that a timed region ends with no work in flight). */
+int rg_quiesce(rg_batch* b);
+/* Event counters since creation: [0] episode ends served by a prefetched game, [1] episode ends
+ * generated synchronously, [2] steps taken on the full path (descents, MoveUntil), [3] games built in
+ * the background, [4] prefetched games found stale, [5] env-steps with an active monster, [6..7] spare. */
+int rg_stats(rg_batch* b, uint64_t* out8);
 int rg_sync(rg_batch* b);          /* waits for the stream and raises per-env errors like the reference */
 int rg_views_get(rg_batch* b, rg_views* out);
 int rg_fetch(rg_batch* b, rg_host_obs* out);

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <string>
@@ -26,6 +27,10 @@ struct rg_batch {
   int64_t max_steps = 0;
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t bg = nullptr;      // background stream: k_prefetch
+  cudaEvent_t ev_main = nullptr;  // "this step's kernels are queued up to here"
+  cudaEvent_t ev_bg = nullptr;    // last k_prefetch
+  bool prefetch_running = false;
   DevBatch d{};
   rg_params* dP = nullptr;
   uint8_t* d_actions = nullptr;
@@ -179,6 +184,30 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
   RG_TRY(dev_alloc(b, &d.defer_list, N));
   RG_TRY(dev_alloc(b, &d.defer_count, 4));
   RG_TRY(cudaMemsetAsync(d.defer_count, 0, 16, b->stream));
+  {  // next-episode buffers + background stream (RG_PREFETCH=0 turns the pipeline off)
+    const char* pf = getenv("RG_PREFETCH");
+    d.prefetch = (pf && pf[0] == '0') ? 0 : 1;
+    if (d.prefetch) {
+      RG_TRY(dev_alloc(b, &d.sp_surface, N * d.CP));
+      RG_TRY(dev_alloc(b, &d.sp_attr, N * d.CP));
+      RG_TRY(dev_alloc(b, &d.sp_screen, N * d.CP));
+      RG_TRY(dev_alloc(b, &d.sp_hist, N * d.HB));
+      RG_TRY(dev_alloc(b, &d.sp_walk, N * (size_t)d.H * d.WW));
+      RG_TRY(dev_alloc(b, &d.sp_st, N));
+      RG_TRY(dev_alloc(b, &d.sp_state, N));
+      RG_TRY(cudaMemsetAsync(d.sp_state, 0, N, b->stream));
+      int lo = 0, hi = 0;
+      RG_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      {
+        const char* pr = getenv("RG_BG_PRIO");
+        RG_TRY(cudaStreamCreateWithPriority(&b->bg, cudaStreamNonBlocking, (pr && pr[0] == 'h') ? hi : lo));
+      }
+      RG_TRY(cudaEventCreateWithFlags(&b->ev_main, cudaEventDisableTiming));
+      RG_TRY(cudaEventCreateWithFlags(&b->ev_bg, cudaEventDisableTiming));
+    }
+  }
+  RG_TRY(dev_alloc(b, &d.stats, 8));
+  RG_TRY(cudaMemsetAsync(d.stats, 0, 64, b->stream));
   RG_TRY(dev_alloc(b, &d.mon_list, N));
   RG_TRY(dev_alloc(b, &d.mon_count, 4));
   RG_TRY(cudaMemsetAsync(d.mon_count, 0, 16, b->stream));
@@ -229,6 +258,26 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
   if (rc != RG_OK) return fail(rc);
 #undef RG_TRY
   *out = b;
+  return RG_OK;
+}
+
+// The prefetched games were built for seeds / episode counters that are about to change.
+int invalidate_prefetched(rg_batch* b) {
+  if (!b->d.prefetch) return RG_OK;
+  RG_CUDA(b, cudaStreamSynchronize(b->bg));
+  RG_CUDA(b, cudaMemsetAsync(b->d.sp_state, 0, (size_t)b->n, b->stream));
+  return RG_OK;
+}
+
+// Queue one background pass after everything queued on the main stream so far.
+int kick_prefetch(rg_batch* b) {
+  if (!b->d.prefetch) return RG_OK;
+  RG_CUDA(b, cudaEventRecord(b->ev_main, b->stream));
+  RG_CUDA(b, cudaStreamWaitEvent(b->bg, b->ev_main, 0));
+  RG_CUDA(b, rg::launch_prefetch(b->d, b->bg));
+  RG_CUDA(b, cudaEventRecord(b->ev_bg, b->bg));
+  b->launches += 1;
+  b->prefetch_running = true;
   return RG_OK;
 }
 
@@ -289,6 +338,10 @@ void rg_destroy(rg_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
+  if (b->bg) cudaStreamSynchronize(b->bg);
+  if (b->ev_main) cudaEventDestroy(b->ev_main);
+  if (b->ev_bg) cudaEventDestroy(b->ev_bg);
+  if (b->bg) cudaStreamDestroy(b->bg);
   for (void* p : b->dev_allocs) cudaFree(p);
   if (b->h_errflag) cudaFreeHost(b->h_errflag);
   if (b->h_error) cudaFreeHost(b->h_error);
@@ -300,6 +353,10 @@ int rg_seed(rg_batch* b, const uint64_t* seed_lo, const uint64_t* seed_hi) {
   if (!b || !seed_lo) return set_err(b, RG_ERR_ARG, "rg_seed: null argument");
   const size_t N = (size_t)b->n;
   RG_CUDA(b, cudaSetDevice(b->device));
+  {
+    int rc = invalidate_prefetched(b);
+    if (rc != RG_OK) return rc;
+  }
   RG_CUDA(b, cudaMemcpyAsync(b->d_u64, seed_lo, N * 8, cudaMemcpyHostToDevice, b->stream));
   if (seed_hi) RG_CUDA(b, cudaMemcpyAsync(b->d_u64 + N, seed_hi, N * 8, cudaMemcpyHostToDevice, b->stream));
   RG_CUDA(b, rg::launch_seed(b->d, b->d_u64, seed_hi ? b->d_u64 + N : nullptr, 1, b->stream));
@@ -311,6 +368,8 @@ int rg_seed(rg_batch* b, const uint64_t* seed_lo, const uint64_t* seed_hi) {
 int rg_reset(rg_batch* b) {
   if (!b) return set_err(b, RG_ERR_ARG, "rg_reset: null batch");
   RG_CUDA(b, cudaSetDevice(b->device));
+  int rc = invalidate_prefetched(b);
+  if (rc != RG_OK) return rc;
   RG_CUDA(b, rg::launch_reset(b->d, b->stream));
   b->launches += 1;
   return RG_OK;
@@ -322,6 +381,22 @@ int rg_step(rg_batch* b, const uint8_t* actions_dev, int auto_reset) {
   RG_CUDA(b, rg::launch_step(b->d, actions_dev, auto_reset, (int)(b->step_parity & 1), b->stream));
   b->step_parity ^= 1;
   b->launches += 4;
+  if (auto_reset) return kick_prefetch(b);  // refill the next-episode buffers consumed so far
+  return RG_OK;
+}
+
+int rg_stats(rg_batch* b, uint64_t* out8) {
+  if (!b || !out8) return set_err(b, RG_ERR_ARG, "rg_stats: null argument");
+  RG_CUDA(b, cudaSetDevice(b->device));
+  RG_CUDA(b, cudaStreamSynchronize(b->stream));
+  if (b->bg) RG_CUDA(b, cudaStreamSynchronize(b->bg));
+  RG_CUDA(b, cudaMemcpy(out8, b->d.stats, 64, cudaMemcpyDeviceToHost));
+  return RG_OK;
+}
+
+int rg_quiesce(rg_batch* b) {
+  if (!b) return set_err(b, RG_ERR_ARG, "rg_quiesce: null batch");
+  if (b->d.prefetch && b->prefetch_running) RG_CUDA(b, cudaStreamWaitEvent(b->stream, b->ev_bg, 0));
   return RG_OK;
 }
 

@@ -24,6 +24,15 @@
 namespace rg {
 
 #define RG_FULL 0xffffffffu
+// Every kernel stages its env in the one dynamic shared array. Device functions re-derive the
+// plane / state pointers from this symbol (RG_PLANES) instead of carrying generic pointers, so
+// that accesses compile to LDS/STS even across non-inlined calls.
+extern __shared__ __align__(16) unsigned char rg_smem[];
+#define RG_PLANES(c)                                                          \
+  uint8_t* const S = rg_smem + (c).soff;                                      \
+  uint8_t* const A = S + (c).CP;                                              \
+  EnvState* const st = reinterpret_cast<EnvState*>(A + (c).CP);               \
+  (void)S; (void)A; (void)st
 #define RG_DEV __device__ __forceinline__
 
 // Direction order Up, Down, Left, Right, LeftUp, RightUp, LeftDown, RightDown, Stay (coord.rs:198-208)
@@ -88,9 +97,10 @@ RG_DEV int nth_set_bit(uint32_t m, uint32_t n) {
 
 // ------------------------------------------------------------------ per-warp context
 struct Ctx {
-  uint8_t* S;         // smem surface plane [CP]
-  uint8_t* A;         // smem attr plane [CP]
-  EnvState* st;       // smem
+  uint32_t soff;      // byte offset of this warp's region in rg_smem: surface [CP], attr [CP], EnvState
+  uint8_t* S;         // the same three as pointers (kernel-level code only)
+  uint8_t* A;
+  EnvState* st;
   const uint8_t* col_room;  // global [160] sector column of x (0xFF = none)
   const uint8_t* row_room;  // global [48]  sector row of y (0xFF = none: rows 0, H-1 and beyond the grid)
   const rg_params* P; // global (read-only)
@@ -134,20 +144,22 @@ RG_DEV int room_of(const Ctx& c, int x, int y) {
 RG_DEV bool in_rect(const RoomD& r, int x, int y) { return x >= r.x0 && x < r.x1 && y >= r.y0 && y < r.y1; }
 RG_DEV bool inb(const Ctx& c, int x, int y) { return x >= 0 && y >= 0 && x < c.W && y < c.H; }
 RG_DEV uint32_t lev_add(const Ctx& c) {  // rogue/mod.rs:483-489
-  uint32_t lv = (uint32_t)c.st->level;
+  RG_PLANES(c);
+  uint32_t lv = (uint32_t)st->level;
   return c.P->amulet_level < lv ? lv - c.P->amulet_level : 0u;
 }
 
 // Floor::can_move_impl floor.rs:169-182
 RG_DEV bool can_move(const Ctx& c, int x, int y, int d, bool is_enemy) {
+  RG_PLANES(c);
   int nx = x + ddx(d), ny = y + ddy(d);
   if (!inb(c, nx, ny)) return false;
   int ni = ny * c.W + nx;
-  bool res = can_walk(c.S[ni]);
-  if (!is_enemy) res = res && !(c.A[ni] & (A_HIDDEN | A_LOCKED));
+  bool res = can_walk(S[ni]);
+  if (!is_enemy) res = res && !(A[ni] & (A_HIDDEN | A_LOCKED));
   if (is_diag(d)) {
-    res = res && can_walk(c.S[y * c.W + nx]);
-    res = res && can_walk(c.S[ny * c.W + x]);
+    res = res && can_walk(S[y * c.W + nx]);
+    res = res && can_walk(S[ny * c.W + x]);
   }
   return res;
 }
@@ -156,11 +168,12 @@ RG_DEV bool can_move(const Ctx& c, int x, int y, int d, bool is_enemy) {
 // maze::dig_maze / dig_impl maze.rs:38-89. The recursion is an explicit stack kept in this
 // env's (not yet composed) screen slice; membership = A_MARK.
 __device__ int dig_maze(Ctx& c, Rng& r, int x0, int y0, int x1, int y1) {
+  RG_PLANES(c);
   uint16_t* stack = reinterpret_cast<uint16_t*>(c.g_screen);
   const int W = c.W;
   int sp = 0, n = 1;
   int cx = x0, cy = y0;
-  c.A[cy * W + cx] |= A_MARK;
+  A[cy * W + cx] |= A_MARK;
   const int max_sp = c.CP / 2;
   for (;;) {
     int pick = -1;
@@ -168,7 +181,7 @@ __device__ int dig_maze(Ctx& c, Rng& r, int x0, int y0, int x1, int y1) {
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
       int tx = cx + 2 * ddx(d), ty = cy + 2 * ddy(d);
-      if (tx >= x0 && tx < x1 && ty >= y0 && ty < y1 && !(c.A[ty * W + tx] & A_MARK)) {
+      if (tx >= x0 && tx < x1 && ty >= y0 && ty < y1 && !(A[ty * W + tx] & A_MARK)) {
         if (r.does_happen(k + 1)) pick = d;  // reservoir pick: every candidate draws (maze.rs:64-75)
         ++k;
       }
@@ -182,8 +195,8 @@ __device__ int dig_maze(Ctx& c, Rng& r, int x0, int y0, int x1, int y1) {
     }
     for (int s = 1; s <= 2; ++s) {
       int mi = (cy + s * ddy(pick)) * W + cx + s * ddx(pick);
-      if (!(c.A[mi] & A_MARK)) {
-        c.A[mi] |= A_MARK;
+      if (!(A[mi] & A_MARK)) {
+        A[mi] |= A_MARK;
         ++n;
       }
     }
@@ -200,6 +213,7 @@ __device__ int dig_maze(Ctx& c, Rng& r, int x0, int y0, int x1, int y1) {
 
 // rooms::gen_rooms + make_room rooms.rs:165-269 (geometry and RNG only; tiles are laid later)
 __device__ void gen_rooms(Ctx& c, Rng& r, uint32_t level) {
+  RG_PLANES(c);
   const rg_params& P = *c.P;
   const int nrooms = c.nrooms;
   uint32_t empty_num = r.range32(0, P.max_empty_rooms + 1);
@@ -248,35 +262,36 @@ __device__ void gen_rooms(Ctx& c, Rng& r, uint32_t level) {
         rm.y1 = (uint8_t)(ly + h);
       }
     }
-    c.st->rooms[i] = rm;
+    st->rooms[i] = rm;
   }
 }
 
 // Room::draw + gen_attr for room tiles: floor.rs:61-71,420-451, rooms.rs:58-82
 __device__ void lay_rooms(Ctx& c, Rng& r, uint32_t level) {
+  RG_PLANES(c);
   const rg_params& P = *c.P;
   const int W = c.W;
   for (int i = 0; i < c.nrooms; ++i) {
-    RoomD rm = c.st->rooms[i];
+    RoomD rm = st->rooms[i];
     if (rm.kind == K_NORMAL) {  // PARALLEL: no RNG is consumed by wall / floor tiles
       int w = rm.x1 - rm.x0, n = w * (rm.y1 - rm.y0);
       uint8_t fl = (rm.flags & RF_DARK) ? A_DARK : 0;
       for (int k = c.lane; k < n; k += 32) {
         int x = rm.x0 + k % w, y = rm.y0 + k / w;
         bool he = (y == rm.y0 || y == rm.y1 - 1), ve = (x == rm.x0 || x == rm.x1 - 1);
-        c.S[y * W + x] = he ? S_WALLX : (ve ? S_WALLY : S_FLOOR);
-        c.A[y * W + x] = (he || ve) ? 0 : fl;
+        S[y * W + x] = he ? S_WALLX : (ve ? S_WALLY : S_FLOOR);
+        A[y * W + x] = (he || ve) ? 0 : fl;
       }
       __syncwarp();
     } else if (rm.kind == K_MAZE) {  // UNIFORM: each passage cell rolls gen_attr in index order
       for (int y = rm.y0; y < rm.y1; ++y)
         for (int x = rm.x0; x < rm.x1; ++x) {
           int idx = y * W + x;
-          if (!(c.A[idx] & A_MARK)) continue;
+          if (!(A[idx] & A_MARK)) continue;
           uint8_t attr = 0;
           if (r.range32(0, P.dark_level) < level && r.does_happen(P.hidden_passage_rate_inv)) attr = A_HIDDEN;
-          c.S[idx] = S_PASSAGE;
-          c.A[idx] = A_MARK | attr;
+          S[idx] = S_PASSAGE;
+          A[idx] = A_MARK | attr;
         }
     }
   }
@@ -284,13 +299,14 @@ __device__ void lay_rooms(Ctx& c, Rng& r, uint32_t level) {
 
 // floor.rs:85-102: one registered passage cell; `ra` is the attribute stream of the replay
 RG_DEV void apply_passage_cell(Ctx& c, Rng& ra, int x, int y, uint8_t surface, uint32_t level) {
+  RG_PLANES(c);
   const rg_params& P = *c.P;
   int idx = y * c.W + x;
   if (!inb(c, x, y)) {
     set_panic(c);
     return;
   }
-  uint8_t keep = c.A[idx] & (A_DOOR | A_MARK);
+  uint8_t keep = A[idx] & (A_DOOR | A_MARK);
   uint8_t attr = 0;
   if (surface == S_DOOR) {
     keep |= A_DOOR;
@@ -298,13 +314,14 @@ RG_DEV void apply_passage_cell(Ctx& c, Rng& ra, int x, int y, uint8_t surface, u
   } else {
     if (ra.range32(0, P.dark_level) < level && ra.does_happen(P.hidden_passage_rate_inv)) attr = A_HIDDEN;
   }
-  c.A[idx] = keep | attr;
-  if (!attr) c.S[idx] = surface;
+  A[idx] = keep | attr;
+  if (!attr) S[idx] = surface;
 }
 
 // passages::select_start_or_end + edges passages.rs:143-219
 __device__ void select_start_or_end(Ctx& c, Rng& r, int room, int d, int& ox, int& oy) {
-  RoomD rm = c.st->rooms[room];
+  RG_PLANES(c);
+  RoomD rm = st->rooms[room];
   if (rm.kind == K_NORMAL) {  // edges(range, d, inclusive) then SliceRandom::choose (usize lane)
     if (d == D_DOWN || d == D_UP) {
       int len = rm.x1 - rm.x0 - 2;
@@ -335,13 +352,13 @@ __device__ void select_start_or_end(Ctx& c, Rng& r, int room, int d, int& ox, in
     for (int t = lo; t < hi; ++t) {
       int x = horiz ? t : fix, y = horiz ? fix : t;
       // Maze::has_cd tests membership in the ORIGINAL range (maze.rs:25-31)
-      if (in_rect(rm, x, y) && (c.A[y * W + x] & A_MARK)) ++cnt;
+      if (in_rect(rm, x, y) && (A[y * W + x] & A_MARK)) ++cnt;
     }
     if (cnt) {
       int n = (int)r.range64(0, (uint64_t)cnt);
       for (int t = lo; t < hi; ++t) {
         int x = horiz ? t : fix, y = horiz ? fix : t;
-        if (in_rect(rm, x, y) && (c.A[y * W + x] & A_MARK)) {
+        if (in_rect(rm, x, y) && (A[y * W + x] & A_MARK)) {
           if (n == 0) {
             ox = x;
             oy = y;
@@ -365,6 +382,7 @@ __device__ void select_start_or_end(Ctx& c, Rng& r, int room, int d, int& ox, in
 // passages::connect_2rooms passages.rs:84-133
 template <bool APPLY>
 __device__ void connect_2rooms(Ctx& c, Rng& rd, Rng& ra, int r1, int r2, int d, uint32_t level) {
+  RG_PLANES(c);
   if (d == D_UP || d == D_LEFT) {
     int t = r1; r1 = r2; r2 = t;
     d = reverse_dir(d);
@@ -373,8 +391,8 @@ __device__ void connect_2rooms(Ctx& c, Rng& rd, Rng& ra, int r1, int r2, int d, 
   select_start_or_end(c, rd, r1, d, sx, sy);
   select_start_or_end(c, rd, r2, reverse_dir(d), ex, ey);
   if (APPLY) {
-    apply_passage_cell(c, ra, sx, sy, c.st->rooms[r1].kind == K_NORMAL ? S_DOOR : S_PASSAGE, level);
-    apply_passage_cell(c, ra, ex, ey, c.st->rooms[r2].kind == K_NORMAL ? S_DOOR : S_PASSAGE, level);
+    apply_passage_cell(c, ra, sx, sy, st->rooms[r1].kind == K_NORMAL ? S_DOOR : S_PASSAGE, level);
+    apply_passage_cell(c, ra, ex, ey, st->rooms[r2].kind == K_NORMAL ? S_DOOR : S_PASSAGE, level);
   }
   int tsx, tsy, tex, tey, tdir;
   if (d == D_DOWN) {
@@ -401,13 +419,20 @@ __device__ void connect_2rooms(Ctx& c, Rng& rd, Rng& ra, int r1, int r2, int d, 
   }
 }
 
-RG_DEV int adj_dir(const Ctx& c, int a, int i) {  // Node::candidates passages.rs:252-262
-  int ax = a % c.nx, ay = a / c.nx, ix = i % c.nx, iy = i / c.nx;
-  if (ix == ax && iy == ay - 1) return D_UP;
-  if (ix == ax && iy == ay + 1) return D_DOWN;
-  if (iy == ay && ix == ax - 1) return D_LEFT;
-  if (iy == ay && ix == ax + 1) return D_RIGHT;
-  return -1;
+// Node::candidates (passages.rs:252-262) of room `a` in ascending room id - the order in which
+// select_candidate (passages.rs:69-82) meets them: Up (a-nx) < Left (a-1) < Right (a+1) < Down (a+nx).
+struct Neigh {
+  int id[4], dir[4], n;
+};
+RG_DEV Neigh neighbours(const Ctx& c, int a) {
+  Neigh r;
+  r.n = 0;
+  const int ay = a / c.nx, ax = a - ay * c.nx;
+  if (ay > 0) { r.id[r.n] = a - c.nx; r.dir[r.n++] = D_UP; }
+  if (ax > 0) { r.id[r.n] = a - 1; r.dir[r.n++] = D_LEFT; }
+  if (ax < c.nx - 1) { r.id[r.n] = a + 1; r.dir[r.n++] = D_RIGHT; }
+  if (ay < c.ny - 1) { r.id[r.n] = a + c.nx; r.dir[r.n++] = D_DOWN; }
+  return r;
 }
 
 // passages::dig_passges passages.rs:16-67. The reference collects every registered cell and
@@ -426,11 +451,11 @@ __device__ void dig_passages(Ctx& c, Rng& rd, Rng& ra, uint32_t level) {
   while (__popc(selected) < n && --guard > 0) {
     int pick = -1, pdir = 0;
     uint32_t k = 0;
-    for (int i = 0; i < n; ++i) {  // select_candidate passages.rs:69-82
-      if ((selected >> i) & 1u) continue;
-      int d = adj_dir(c, cur, i);
-      if (d < 0) continue;
-      if (rd.does_happen(k + 1)) { pick = i; pdir = d; }
+    const Neigh nb = neighbours(c, cur);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {  // select_candidate passages.rs:69-82
+      if (q >= nb.n || ((selected >> nb.id[q]) & 1u)) continue;
+      if (rd.does_happen(k + 1)) { pick = nb.id[q]; pdir = nb.dir[q]; }
       ++k;
     }
     if (pick >= 0) {
@@ -450,11 +475,11 @@ __device__ void dig_passages(Ctx& c, Rng& rd, Rng& ra, uint32_t level) {
     int room1 = (int)rd.range64(0, (uint64_t)n);
     int pick = -1, pdir = 0;
     uint32_t k = 0;
-    for (int i = 0; i < n; ++i) {
-      int d = adj_dir(c, room1, i);
-      if (d < 0) continue;
-      if ((conn >> (room1 * 4 + d)) & 1ull) continue;
-      if (rd.does_happen(k + 1)) { pick = i; pdir = d; }
+    const Neigh nb = neighbours(c, room1);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (q >= nb.n || ((conn >> (room1 * 4 + nb.dir[q])) & 1ull)) continue;
+      if (rd.does_happen(k + 1)) { pick = nb.id[q]; pdir = nb.dir[q]; }
       ++k;
     }
     if (pick >= 0) {
@@ -471,7 +496,8 @@ __device__ void dig_passages(Ctx& c, Rng& rd, Rng& ra, uint32_t level) {
 // (`excl`, a cell index or -1). During generation a room's set never loses more than one
 // member before it is sampled (see DESIGN.md "implicit cell sets").
 __device__ int select_in_room(Ctx& c, Rng& r, int room, int excl) {
-  RoomD rm = c.st->rooms[room];
+  RG_PLANES(c);
+  RoomD rm = st->rooms[room];
   const int W = c.W;
   if (rm.kind == K_EMPTY) return -1;
   if (rm.kind == K_NORMAL) {
@@ -491,7 +517,7 @@ __device__ int select_in_room(Ctx& c, Rng& r, int room, int excl) {
   for (int y = rm.y0; y < rm.y1; ++y)
     for (int x = rm.x0; x < rm.x1; ++x) {
       int idx = y * W + x;
-      if (!(c.A[idx] & A_MARK) || idx == excl) continue;
+      if (!(A[idx] & A_MARK) || idx == excl) continue;
       if (n == 0) return idx;
       --n;
     }
@@ -502,17 +528,18 @@ __device__ int select_in_room(Ctx& c, Rng& r, int room, int excl) {
 // Floor::select_cell floor.rs:333-346. excl_kind: 0 = occupied by this room's gold (object set),
 // 1 = occupied by this room's monster (character set)
 __device__ int select_in_floor(Ctx& c, Rng& r, int excl_kind) {
+  RG_PLANES(c);
   uint32_t cand = 0;
   for (int i = 0; i < c.nrooms; ++i)
-    if (c.st->rooms[i].kind != K_EMPTY) cand |= 1u << i;
+    if (st->rooms[i].kind != K_EMPTY) cand |= 1u << i;
   while (cand) {
     uint32_t cnt = __popc(cand);
     int room = nth_set_bit(cand, (uint32_t)r.range64(0, cnt));
     int excl = -1;
     if (excl_kind == 0) {
-      if (c.st->item_pos[room] != 0xFFFF) excl = c.st->item_pos[room];
+      if (st->item_pos[room] != 0xFFFF) excl = st->item_pos[room];
     } else {
-      MonD m = c.st->mon[room];
+      MonD m = st->mon[room];
       if (m.flags & MF_PRESENT) excl = m.y * c.W + m.x;
     }
     int pos = select_in_room(c, r, room, excl);
@@ -550,76 +577,81 @@ __device__ bool gen_enemy(Ctx& c, Rng& re, uint32_t rmin, uint32_t rmax, bool ha
 // ------------------------------------------------------------------ visibility ("FOV")
 // Floor::enters_room floor.rs:231-247 (+ activate_area from player_in :273-279)
 __device__ void enters_room(Ctx& c, int x, int y) {
+  RG_PLANES(c);
   int id = room_of(c, x, y);
   if (id < 0) { set_panic(c); return; }
-  RoomD rm = c.st->rooms[id];
+  RoomD rm = st->rooms[id];
   if (!(rm.flags & RF_VISITED)) {
-    c.st->rooms[id].flags = rm.flags | RF_VISITED;
+    st->rooms[id].flags = rm.flags | RF_VISITED;
     if (rm.kind == K_NORMAL && !(rm.flags & RF_DARK)) {
       int w = rm.x1 - rm.x0, n = w * (rm.y1 - rm.y0);
-      for (int k = c.lane; k < n; k += 32) c.A[(rm.y0 + k / w) * c.W + rm.x0 + k % w] |= (A_DRAWN | A_VISIBLE);
+      for (int k = c.lane; k < n; k += 32) A[(rm.y0 + k / w) * c.W + rm.x0 + k % w] |= (A_DRAWN | A_VISIBLE);
       __syncwarp();
     }
   }
   // EnemyHandler::activate_area enemies.rs:342-355: placed MEAN monsters inside the assigned area
   for (int m = 0; m < c.nrooms; ++m) {
-    MonD mo = c.st->mon[m];
+    MonD mo = st->mon[m];
     if ((mo.flags & MF_PRESENT) && !(mo.flags & MF_ACTIVE) && (c.P->enemies[mo.kind].attr & EA_MEAN) &&
         room_of(c, mo.x, mo.y) == id)
-      c.st->mon[m].flags = mo.flags | MF_ACTIVE;
+      st->mon[m].flags = mo.flags | MF_ACTIVE;
   }
 }
 // Floor::leaves_room floor.rs:250-261
 __device__ void leaves_room(Ctx& c, int x, int y) {
+  RG_PLANES(c);
   int id = room_of(c, x, y);
   if (id < 0) { set_panic(c); return; }
-  RoomD rm = c.st->rooms[id];
+  RoomD rm = st->rooms[id];
   if (!((rm.flags & RF_VISITED) && (rm.flags & RF_DARK))) return;
   int x0 = rm.x0, y0 = rm.y0, x1 = rm.x1, y1 = rm.y1;
   if (rm.kind == K_EMPTY) room_area(c, id, x0, y0, x1, y1);
   int w = x1 - x0 - 2, h = y1 - y0 - 2;
   if (w <= 0 || h <= 0) return;
-  for (int k = c.lane; k < w * h; k += 32) c.A[(y0 + 1 + k / w) * c.W + x0 + 1 + k % w] &= (uint8_t)~A_VISIBLE;
+  for (int k = c.lane; k < w * h; k += 32) A[(y0 + 1 + k / w) * c.W + x0 + 1 + k % w] &= (uint8_t)~A_VISIBLE;
   __syncwarp();
 }
 // Floor::player_in floor.rs:264-295 ; Cell::approached field.rs:20-26
 __device__ void player_in(Ctx& c, int x, int y, bool init) {
+  RG_PLANES(c);
   const int W = c.W;
-  if (init || (c.A[y * W + x] & A_DOOR)) enters_room(c, x, y);
-  c.A[y * W + x] |= A_VISITED;
+  if (init || (A[y * W + x] & A_DOOR)) enters_room(c, x, y);
+  A[y * W + x] |= A_VISITED;
 #pragma unroll
   for (int d = 0; d < 9; ++d) {
     int nx = x + ddx(d), ny = y + ddy(d);
     if (!inb(c, nx, ny)) continue;
     int idx = ny * W + nx;
-    if (is_diag(d) && c.S[idx] == S_PASSAGE) continue;
-    uint8_t a = c.A[idx];
+    if (is_diag(d) && S[idx] == S_PASSAGE) continue;
+    uint8_t a = A[idx];
     if (a & A_HIDDEN) continue;
-    c.A[idx] = a | A_DRAWN | A_VISIBLE;
+    A[idx] = a | A_DRAWN | A_VISIBLE;
   }
   c.a_dirty = 1;
 }
 // Floor::player_out floor.rs:298-312 ; Cell::left field.rs:30-34
 __device__ void player_out(Ctx& c, int x, int y) {
+  RG_PLANES(c);
   const int W = c.W;
-  if (c.A[y * W + x] & A_DOOR) leaves_room(c, x, y);
+  if (A[y * W + x] & A_DOOR) leaves_room(c, x, y);
 #pragma unroll
   for (int d = 0; d < 9; ++d) {
     int nx = x + ddx(d), ny = y + ddy(d);
     if (!inb(c, nx, ny)) continue;
     int idx = ny * W + nx;
-    if (c.S[idx] == S_FLOOR && (c.A[idx] & A_DARK)) c.A[idx] &= (uint8_t)~A_VISIBLE;
+    if (S[idx] == S_FLOOR && (A[idx] & A_DARK)) A[idx] &= (uint8_t)~A_VISIBLE;
   }
   c.a_dirty = 1;
 }
 
 // Build the monster-walkable bitboard rows from the surface plane (one ballot per 32 cells).
 __device__ void build_walk(Ctx& c) {
+  RG_PLANES(c);
   __syncwarp();
   for (int row = 0; row < c.H; ++row)
     for (int w = 0; w < c.WW; ++w) {
       int x = w * 32 + c.lane;
-      bool b = x < c.W && can_walk(c.S[row * c.W + x]);
+      bool b = x < c.W && can_walk(S[row * c.W + x]);
       uint32_t m = __ballot_sync(RG_FULL, b);
       if (c.lane == 0) c.g_walk[row * c.WW + w] = m;
     }
@@ -633,8 +665,8 @@ __device__ void complete_all_maps(Ctx& c);  // lazy DistCache, defined with the 
 // then actions::new_level's player placement (actions.rs:134-137).
 __device__ __noinline__ void new_level(Ctx* cp, bool is_initial) {
   Ctx& c = *cp;
+  RG_PLANES(c);
   const rg_params& P = *c.P;
-  EnvState* st = c.st;
   const int W = c.W;
   if (!is_initial) {
     complete_all_maps(c);  // suspended DistCache maps belong to the floor that is about to be replaced
@@ -642,7 +674,7 @@ __device__ __noinline__ void new_level(Ctx* cp, bool is_initial) {
     // emit it now, before the planes are overwritten.
     __syncwarp();
     for (int ch = c.lane; ch < c.CP / 16; ch += 32) {
-      uint4 a = *reinterpret_cast<const uint4*>(c.A + ch * 16);
+      uint4 a = *reinterpret_cast<const uint4*>(A + ch * 16);
       uint32_t v[4] = {a.x, a.y, a.z, a.w};
       uint32_t bits = 0;
 #pragma unroll
@@ -656,8 +688,8 @@ __device__ __noinline__ void new_level(Ctx* cp, bool is_initial) {
   // fresh field
   __syncwarp();
   for (int ch = c.lane; ch < c.CP / 16; ch += 32) {
-    *reinterpret_cast<uint4*>(c.S + ch * 16) = make_uint4(0x07070707u, 0x07070707u, 0x07070707u, 0x07070707u);
-    *reinterpret_cast<uint4*>(c.A + ch * 16) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(S + ch * 16) = make_uint4(0x07070707u, 0x07070707u, 0x07070707u, 0x07070707u);
+    *reinterpret_cast<uint4*>(A + ch * 16) = make_uint4(0, 0, 0, 0);
   }
   __syncwarp();
   Rng rd = c.rd;
@@ -689,7 +721,7 @@ __device__ __noinline__ void new_level(Ctx* cp, bool is_initial) {
   {  // Floor::setup_stair
     int pos = select_in_floor(c, rd, 0);
     if (pos < 0) set_panic(c);
-    else c.S[pos] = S_STAIR;
+    else S[pos] = S_STAIR;
   }
   for (int i = 0; i < MAX_ROOMS; ++i) st->mon[i].flags = 0;  // remove_enemies (a fresh handler is empty too)
   if (P.n_enemies != 0) {  // Floor::place_enemies
@@ -709,7 +741,7 @@ __device__ __noinline__ void new_level(Ctx* cp, bool is_initial) {
   }
   if (!P.hide_dungeon) {  // rogue/mod.rs:465-475
     __syncwarp();
-    for (int k = W + c.lane; k < (c.H - 1) * W; k += 32) c.A[k] |= A_VISIBLE;
+    for (int k = W + c.lane; k < (c.H - 1) * W; k += 32) A[k] |= A_VISIBLE;
     __syncwarp();
   }
   if (is_initial) {  // Player::init_items -> weapon.rs:159 draws on the item stream (core/src/lib.rs:206-207)
@@ -723,7 +755,11 @@ __device__ __noinline__ void new_level(Ctx* cp, bool is_initial) {
   st->px = (int16_t)(ppos % W);
   st->py = (int16_t)(ppos / W);
   __syncwarp();
-  for (int k = c.lane; k < c.CP; k += 32) c.A[k] &= (uint8_t)~A_MARK;
+  for (int k = c.lane; k < c.CP / 16; k += 32) {
+    uint4 v = reinterpret_cast<uint4*>(A)[k];
+    v.x &= 0x7F7F7F7Fu; v.y &= 0x7F7F7F7Fu; v.z &= 0x7F7F7F7Fu; v.w &= 0x7F7F7F7Fu;
+    reinterpret_cast<uint4*>(A)[k] = v;
+  }
   __syncwarp();
   build_walk(c);
   player_in(c, st->px, st->py, true);
@@ -896,7 +932,7 @@ __device__ __noinline__ uint32_t bfs_impl(const uint32_t* __restrict__ walk, uin
 
 // Extends the map in `slot` until the 3x3 block around (nx0, ny0) is final (nx0 = -2: until complete).
 __device__ void bfs_extend(Ctx& c, int slot, int nx0, int ny0) {
-  EnvState* st = c.st;
+  RG_PLANES(c);
   const uint32_t lvl = st->cache_lvl[slot];
   if (lvl == BFS_COMPLETE) return;
   uint16_t* out = c.g_dist + (size_t)slot * c.CP;
@@ -924,7 +960,7 @@ __device__ void bfs_extend(Ctx& c, int slot, int nx0, int ny0) {
 
 // Finish every suspended map of this env (called before the walkability they were started on changes).
 __device__ void complete_all_maps(Ctx& c) {
-  EnvState* st = c.st;
+  RG_PLANES(c);
   const int n = st->cache_n, head = st->cache_head;
   for (int k = 0; k < n; ++k) {
     const int slot = (head + k) % NCACHE;
@@ -936,7 +972,7 @@ __device__ void complete_all_maps(Ctx& c) {
 // never flushed (stale maps from earlier floors are used on purpose).
 // Returns the slot; the map is final at least on the 3x3 block around (nx0, ny0).
 __device__ int cached_dist_map(Ctx& c, int tx, int ty, int nx0, int ny0) {
-  EnvState* st = c.st;
+  RG_PLANES(c);
   int n = st->cache_n, head = st->cache_head;
   int slot = -1;
   for (int k = 0; k < n; ++k) {
@@ -964,10 +1000,11 @@ __device__ int cached_dist_map(Ctx& c, int tx, int ty, int nx0, int ny0) {
 // `moved` = monsters already re-inserted this turn; skip(q) = a moved-active or placed monster
 // stands on q (enemies.rs:383-384).
 __device__ __noinline__ bool cell_blocked(const Ctx& c, int x, int y, uint32_t moved) {
+  RG_PLANES(c);
   bool hit = false;
 #pragma unroll 1
   for (int m = 0; m < c.nrooms; ++m) {
-    MonD mo = c.st->mon[m];
+    MonD mo = st->mon[m];
     bool counts = (mo.flags & MF_PRESENT) && (!(mo.flags & MF_ACTIVE) || ((moved >> m) & 1u));
     hit = hit || (counts && mo.x == x && mo.y == y);
   }
@@ -1011,10 +1048,11 @@ __device__ int move_enemy(Ctx& c, int mx, int my, int tx, int ty, uint32_t moved
 }
 // rogue::Dungeon::move_enemy_randomly rogue/mod.rs:376-397
 __device__ int move_enemy_randomly(Ctx& c, int mx, int my, uint32_t moved, int& ox, int& oy) {
+  RG_PLANES(c);
   int d = (int)c.rd.range64(0, 8);
   int nx = mx + ddx(d), ny = my + ddy(d);
   if (cell_blocked(c, nx, ny, moved) || !can_move(c, mx, my, d, true)) return MV_CANT;
-  if (nx == c.st->px && ny == c.st->py) return MV_REACH;
+  if (nx == st->px && ny == st->py) return MV_REACH;
   ox = nx;
   oy = ny;
   return MV_CAN;
@@ -1039,7 +1077,7 @@ __device__ int roll_dice(Rng& re, const int32_t* times, const int32_t* maxs, int
 // actions::move_active_enemies + EnemyHandler::move_actives actions.rs:82-119, enemies.rs:366-424
 // returns true when the player died (Some(Grave))
 __device__ bool move_active_enemies(Ctx& c) {
-  EnvState* st = c.st;
+  RG_PLANES(c);
   const rg_params& P = *c.P;
   uint32_t pending = 0;
   for (int m = 0; m < c.nrooms; ++m) {
@@ -1112,7 +1150,7 @@ __device__ bool move_active_enemies(Ctx& c) {
 
 // Player::heal player.rs:221-240
 __device__ bool heal(Ctx& c) {
-  EnvState* st = c.st;
+  RG_PLANES(c);
   st->quiet += 1;
   int q = (int)st->quiet, lv = st->plevel, amount;
   if (lv < 8) amount = max(min(q + (lv << 1) - 20, 1), 0);
@@ -1130,7 +1168,7 @@ __device__ bool heal(Ctx& c) {
 // kernel over the envs that have an active monster.
 template <bool HOT>
 __device__ bool after_turn(Ctx& c) {
-  EnvState* st = c.st;
+  RG_PLANES(c);
   st->food_left -= 1;  // wraps like the release build
   if (st->food_left != 0) {
     uint32_t hunger = c.P->hunger_time / 10;
@@ -1144,7 +1182,7 @@ __device__ bool after_turn(Ctx& c) {
 
 // Player::level_up + Leveling::check_level player.rs:185-197,346-352
 __device__ bool level_up(Ctx& c, uint32_t gained) {
-  EnvState* st = c.st;
+  RG_PLANES(c);
   const rg_params& P = *c.P;
   st->exp += gained;
   uint32_t cur = (uint32_t)(st->plevel - 1), diff = 0;
@@ -1172,7 +1210,7 @@ struct MoveOut {
   uint32_t redraw, status_upd, msg;
 };
 __device__ MoveOut move_player(Ctx& c, int d) {
-  EnvState* st = c.st;
+  RG_PLANES(c);
   const rg_params& P = *c.P;
   MoveOut o{true, 0, 0, 0};
   const int px = st->px, py = st->py;
@@ -1228,26 +1266,27 @@ __device__ MoveOut move_player(Ctx& c, int d) {
 
 // Floor::search floor.rs:349-370
 __device__ void search(Ctx& c) {
+  RG_PLANES(c);
   const int W = c.W;
-  const int px = c.st->px, py = c.st->py;
+  const int px = st->px, py = st->py;
   bool maps_done = false;
   for (int d = 0; d < 8; ++d) {
     int nx = px + ddx(d), ny = py + ddy(d);
     if (!inb(c, nx, ny)) continue;
     int idx = ny * W + nx;
     bool opened = false;
-    if ((c.A[idx] & (A_HIDDEN | A_LOCKED)) && !maps_done) {  // walkability may change below
+    if ((A[idx] & (A_HIDDEN | A_LOCKED)) && !maps_done) {  // walkability may change below
       complete_all_maps(c);
       maps_done = true;
     }
-    if ((c.A[idx] & A_HIDDEN) && c.rd.does_happen(c.P->passage_unlock_rate_inv)) {
-      c.A[idx] = (c.A[idx] & (uint8_t)~(A_LOCKED | A_HIDDEN)) | A_VISIBLE;
-      c.S[idx] = S_PASSAGE;
+    if ((A[idx] & A_HIDDEN) && c.rd.does_happen(c.P->passage_unlock_rate_inv)) {
+      A[idx] = (A[idx] & (uint8_t)~(A_LOCKED | A_HIDDEN)) | A_VISIBLE;
+      S[idx] = S_PASSAGE;
       opened = true;
     }
-    if ((c.A[idx] & A_LOCKED) && c.rd.does_happen(c.P->door_unlock_rate_inv)) {
-      c.A[idx] = (c.A[idx] & (uint8_t)~(A_LOCKED | A_HIDDEN)) | A_VISIBLE;
-      c.S[idx] = S_DOOR;
+    if ((A[idx] & A_LOCKED) && c.rd.does_happen(c.P->door_unlock_rate_inv)) {
+      A[idx] = (A[idx] & (uint8_t)~(A_LOCKED | A_HIDDEN)) | A_VISIBLE;
+      S[idx] = S_DOOR;
       c.msg |= MSG_SECRET_DOOR;
       opened = true;
     }
@@ -1261,7 +1300,7 @@ __device__ void search(Ctx& c) {
 
 // RunTime::player_status core/src/lib.rs:345-356 -> Status::to_vec player.rs:417-430
 __device__ void refresh_status(Ctx& c) {
-  EnvState* st = c.st;
+  RG_PLANES(c);
   uint32_t hunger = c.P->hunger_time / 10;
   st->status[0] = (uint32_t)st->level;
   st->status[1] = st->gold;
@@ -1280,10 +1319,10 @@ __device__ void refresh_status(Ctx& c) {
 // floor generator is not compiled into the hot kernel at all.
 template <bool HOT>
 __device__ void process_action(Ctx& c, int act, int d) {
-  EnvState* st = c.st;
+  RG_PLANES(c);
   bool ui = false;
   if (act == 3) {
-    if (!HOT && c.S[st->py * c.W + st->px] == S_STAIR) {
+    if (!HOT && S[st->py * c.W + st->px] == S_STAIR) {
       if constexpr (!HOT) new_level(&c, false);
       c.redraw = 1;
       c.status_upd = 1;
@@ -1301,7 +1340,7 @@ __device__ void process_action(Ctx& c, int act, int d) {
         MoveOut o = move_player(c, d);
         int idx = st->py * c.W + st->px;
         // Dungeon::tile: the VISIBLE tile (rogue/mod.rs:321-328); keep running only on '.' / '#'
-        bool on_open = (c.A[idx] & A_VISIBLE) && (c.S[idx] == S_FLOOR || c.S[idx] == S_PASSAGE);
+        bool on_open = (A[idx] & A_VISIBLE) && (S[idx] == S_FLOOR || S[idx] == S_PASSAGE);
         // the reactions of every sub-move matter only through these idempotent flags
         c.redraw |= o.redraw; c.status_upd |= o.status_upd; c.msg |= o.msg;
         if (o.done || !on_open) break;
@@ -1320,13 +1359,13 @@ __device__ void process_action(Ctx& c, int act, int d) {
 // RunTime::draw_screen core/src/lib.rs:264-285 + Dungeon::draw / draw_ranges / draw_enemy
 // rogue/mod.rs:278-300,398-404 + Floor::history_map floor.rs:372-379.
 __device__ void compose(Ctx& c) {
+  RG_PLANES(c);
   const int W = c.W, H = c.H;
-  EnvState* st = c.st;
   __syncwarp();
   const int lo = W, hi = (H - 1) * W;  // rows 0 and H-1 are never written (python/src/lib.rs:44)
   for (int ch = c.lane; ch < c.CP / 16; ch += 32) {  // PARALLEL, 128-bit in / 128-bit out, 4 cells per op
-    const uint4 s4 = *reinterpret_cast<const uint4*>(c.S + ch * 16);
-    const uint4 a4 = *reinterpret_cast<const uint4*>(c.A + ch * 16);
+    const uint4 s4 = *reinterpret_cast<const uint4*>(S + ch * 16);
+    const uint4 a4 = *reinterpret_cast<const uint4*>(A + ch * 16);
     const uint32_t sv[4] = {s4.x, s4.y, s4.z, s4.w}, av[4] = {a4.x, a4.y, a4.z, a4.w};
     uint32_t ov[4];
     uint32_t hbits = 0;
@@ -1360,7 +1399,7 @@ __device__ void compose(Ctx& c) {
     MonD mo = st->mon[c.lane];
     if (mo.flags & MF_PRESENT) {
       int idx = mo.y * W + mo.x;
-      bool vis = (c.A[idx] & (A_VISIBLE | A_DRAWN)) && mo.y >= 1 && mo.y < H - 1;
+      bool vis = (A[idx] & (A_VISIBLE | A_DRAWN)) && mo.y >= 1 && mo.y < H - 1;
       int dx = px - mo.x, dy = py - mo.y;
       bool show = dx * dx + dy * dy <= 2;  // Coord::is_adjacent
       if (!show) {                         // Floor::in_same_room floor.rs:381-393
@@ -1376,12 +1415,12 @@ __device__ void compose(Ctx& c) {
   __syncwarp();
   if (c.lane < c.nrooms) {
     uint16_t ip = st->item_pos[c.lane];
-    if (ip != 0xFFFF && (c.A[ip] & (A_VISIBLE | A_DRAWN)) && ip >= W && ip < (H - 1) * W) c.g_screen[ip] = '*';
+    if (ip != 0xFFFF && (A[ip] & (A_VISIBLE | A_DRAWN)) && ip >= W && ip < (H - 1) * W) c.g_screen[ip] = '*';
   }
   __syncwarp();
   if (c.lane == 0) {
     int idx = py * W + px;
-    if ((c.A[idx] & (A_VISIBLE | A_DRAWN)) && py >= 1 && py < H - 1) c.g_screen[idx] = '@';
+    if ((A[idx] & (A_VISIBLE | A_DRAWN)) && py >= 1 && py < H - 1) c.g_screen[idx] = '@';
   }
   __syncwarp();
 }
@@ -1389,7 +1428,7 @@ __device__ void compose(Ctx& c) {
 // GameConfig::build + GameStateImpl::reset + PlayerState::reset
 // core/src/lib.rs:193-228, python/src/state_impls.rs:38-44, python/src/lib.rs:52-58
 __device__ void reset_env(Ctx& c) {
-  EnvState* st = c.st;
+  RG_PLANES(c);
   const rg_params& P = *c.P;
   c.rd.seed(st->seed);
   c.ri.seed(st->seed);

@@ -20,6 +20,7 @@ RG_DEV size_t warp_smem(const DevBatch& b) { return 2 * (size_t)b.CP + sizeof(En
 
 // Stage one env's small state into shared memory and fill the context.
 RG_DEV void fill_ctx(const DevBatch& b, Ctx& c, unsigned char* base, int64_t env) {
+  c.soff = (uint32_t)(base - rg_smem);
   c.S = base;
   c.A = base + b.CP;
   c.st = reinterpret_cast<EnvState*>(base + 2 * (size_t)b.CP);
@@ -88,8 +89,12 @@ RG_DEV void emit_obs(const DevBatch& b, Ctx& c, int64_t env, int32_t reward, uin
 
 // Work the hot step kernel hands to the generation kernel (one entry per env, any order).
 enum : uint32_t { DEFER_STEP = 0u, DEFER_RESET = 0x80000000u };
+RG_DEV void count_event(const DevBatch& b, const Ctx& c, int which) {
+  if (c.lane == 0) atomicAdd(b.stats + which, 1ull);
+}
 RG_DEV void defer(const DevBatch& b, Ctx& c, int64_t env, uint32_t code, int parity) {
   if (c.lane == 0) {
+    atomicAdd(b.stats + (code ? RGS_SYNC_RESET : RGS_FULL_STEP), 1ull);
     uint32_t slot = atomicAdd(b.defer_count + parity, 1u);
     b.defer_list[slot] = (uint32_t)env | code;
   }
@@ -97,7 +102,7 @@ RG_DEV void defer(const DevBatch& b, Ctx& c, int64_t env, uint32_t code, int par
 
 // ThreadWorker::run Instruction::Reset for every env (python/src/thread_impls.rs:117-124)
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_reset(DevBatch b) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* const smem = rg_smem;
   Ctx c;
   const int warp = threadIdx.x >> 5;
   const int64_t env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
@@ -165,7 +170,7 @@ RG_DEV void skip_env(const DevBatch& b, Ctx& c, int64_t env) {
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_HOT_MIN_BLOCKS)
 k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset, int parity) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* const smem = rg_smem;
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // next step's counters
     b.defer_count[parity ^ 1] = 0;
     b.mon_count[parity ^ 1] = 0;
@@ -215,6 +220,7 @@ k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset, i
   st->f_flags = (uint8_t)((c.redraw ? SF_REDRAW : 0) | (c.status_upd ? SF_STATUS : 0) | (c.panic ? SF_PANIC : 0));
   if (act != 4 && !c.panic && has_active_monster(c)) {
     if (c.lane == 0) b.mon_list[atomicAdd(b.mon_count + parity, 1u)] = (uint32_t)env;
+    count_event(b, c, RGS_MONSTER_ENVS);
   }
   close_env(b, c, env);
 }
@@ -222,7 +228,7 @@ k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset, i
 // actions::move_active_enemies (actions.rs:82-119) for the envs that have an active monster
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_HOT_MIN_BLOCKS)
 k_step_monsters(DevBatch b, int parity) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* const smem = rg_smem;
   const uint32_t count = b.mon_count[parity];
   const int warp = threadIdx.x >> 5;
   for (uint32_t i = blockIdx.x * WARPS_PER_BLOCK + warp; i < count; i += gridDim.x * WARPS_PER_BLOCK) {
@@ -240,9 +246,39 @@ k_step_monsters(DevBatch b, int parity) {
   }
 }
 
+// Copies env's prefetched game (planes, screen, history, walk rows, EnvState) over the live one.
+RG_DEV void swap_in_prefetched(const DevBatch& b, Ctx& c, int64_t env) {
+  const int n16 = b.CP / 16;
+  const uint4* s0 = reinterpret_cast<const uint4*>(b.sp_surface + env * b.CP);
+  const uint4* s1 = reinterpret_cast<const uint4*>(b.sp_attr + env * b.CP);
+  const uint4* s2 = reinterpret_cast<const uint4*>(b.sp_screen + env * b.CP);
+  uint4* d0 = reinterpret_cast<uint4*>(b.surface + env * b.CP);
+  uint4* d1 = reinterpret_cast<uint4*>(b.attr + env * b.CP);
+  uint4* d2 = reinterpret_cast<uint4*>(b.screen + env * b.CP);
+  for (int i = c.lane; i < n16; i += 32) {
+    d0[i] = s0[i];
+    d1[i] = s1[i];
+    d2[i] = s2[i];
+  }
+  const uint4* h0 = reinterpret_cast<const uint4*>(b.sp_hist + env * b.HB);
+  uint4* h1 = reinterpret_cast<uint4*>(b.hist + env * b.HB);
+  for (int i = c.lane; i < b.HB / 16; i += 32) h1[i] = h0[i];
+  const uint32_t* w0 = b.sp_walk + env * (int64_t)(b.H * b.WW);
+  uint32_t* w1 = b.walk + env * (int64_t)(b.H * b.WW);
+  for (int i = c.lane; i < b.H * b.WW; i += 32) w1[i] = w0[i];
+  const uint4* e0 = reinterpret_cast<const uint4*>(b.sp_st + env);
+  uint4* e1 = reinterpret_cast<uint4*>(c.st);
+  __syncwarp();
+  for (int i = c.lane; i < (int)(sizeof(EnvState) / 16); i += 32) e1[i] = e0[i];
+  __syncwarp();
+  c.rd.load(c.st->rng);
+  c.ri.load(c.st->rng + 4);
+  c.re.load(c.st->rng + 8);
+}
+
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_HOT_MIN_BLOCKS)
 k_step_finish(DevBatch b, int auto_reset, int parity) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* const smem = rg_smem;
   Ctx c;
   const int warp = threadIdx.x >> 5;
   const int64_t env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
@@ -261,7 +297,33 @@ k_step_finish(DevBatch b, int auto_reset, int parity) {
     if (flags & SF_STATUS) refresh_status(c);
     st->steps += 1;
     st->is_terminal = ((flags & SF_DEAD) || (int64_t)st->steps >= b.max_steps) ? 1 : 0;
-    if (st->is_terminal && auto_reset) {  // the fresh game is built by k_step_gen
+    if (st->is_terminal && auto_reset) {
+      bool ready = b.prefetch && *reinterpret_cast<volatile uint8_t*>(b.sp_state + env) == 1;
+      if (ready) {
+        __threadfence();
+        // built from this episode's seed / counter? (a synchronous reset may have overtaken it)
+        if (*reinterpret_cast<volatile uint32_t*>(&b.sp_st[env].episode) != st->episode + 1) {
+          ready = false;
+          count_event(b, c, RGS_PREFETCH_STALE);
+          __syncwarp();
+          if (c.lane == 0) *reinterpret_cast<volatile uint8_t*>(b.sp_state + env) = 0;
+        }
+      }
+      if (ready) {
+        // The next episode of this env was generated ahead of time (k_prefetch): move it in.
+        count_event(b, c, RGS_SWAP_IN);
+        swap_in_prefetched(b, c, env);
+        const uint8_t perr = st->error;
+        st->is_terminal = 1;
+        const int32_t d0 = (int32_t)st->status[1] - (int32_t)gold_before;
+        emit_obs(b, c, env, d0 > 0 ? d0 : 0, perr);
+        store_state(b, c, env);
+        __threadfence();
+        __syncwarp();
+        if (c.lane == 0) *reinterpret_cast<volatile uint8_t*>(b.sp_state + env) = 0;
+        return;
+      }
+      // not ready (or prefetch off): the fresh game is built synchronously by k_step_gen
       if (c.lane == 0) b.reward[env] = (int32_t)gold_before;
       store_state(b, c, env);
       defer(b, c, env, DEFER_RESET, parity);
@@ -331,7 +393,7 @@ RG_DEV void step_env_full(const DevBatch& b, Ctx& c, int64_t env, const uint8_t*
 // Grid-stride over the full-path list; exits at once when the list is empty.
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_step_gen(DevBatch b, const uint8_t* __restrict__ actions,
                                                                   int auto_reset, int parity) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* const smem = rg_smem;
   const uint32_t count = b.defer_count[parity];
   const int warp = threadIdx.x >> 5;
   for (uint32_t i = blockIdx.x * WARPS_PER_BLOCK + warp; i < count; i += gridDim.x * WARPS_PER_BLOCK) {
@@ -344,9 +406,54 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_step_gen(DevBatch b, c
   }
 }
 
+// Background generation of every env's NEXT episode (GameConfig::build for the seed its next reset
+// will use - fixed, or already derived for `seed: null` - core/src/lib.rs:157-165,193-228). Runs on
+// a second, low-priority stream concurrently with the step kernels, so the ~1000 dependent RNG
+// draws of a floor are off the step's critical path; k_step_finish moves the finished game in
+// when the episode ends. Ownership of a buffer is handed over through sp_state (0: this kernel
+// may write it, 1: the step kernels may read it), with a fence on each side.
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_prefetch(DevBatch b) {
+  unsigned char* const smem = rg_smem;
+  const int warp = threadIdx.x >> 5;
+  for (int64_t env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp; env < b.n;
+       env += (int64_t)gridDim.x * WARPS_PER_BLOCK) {
+    if (*reinterpret_cast<volatile uint8_t*>(b.sp_state + env) != 0) continue;
+    __threadfence();
+    Ctx c;
+    fill_ctx(b, c, smem + (size_t)warp * warp_smem(b), env);  // live seed / episode counter
+    c.g_screen = b.sp_screen + env * b.CP;
+    c.g_hist = b.sp_hist + env * b.HB;
+    c.g_walk = b.sp_walk + env * (int64_t)(b.H * b.WW);
+    reset_env(c);
+    if (c.panic) c.st->error = RG_ERR_PANIC;
+    compose(c);
+    __syncwarp();
+    if (c.lane == 0) {
+      c.rd.store(c.st->rng);
+      c.ri.store(c.st->rng + 4);
+      c.re.store(c.st->rng + 8);
+    }
+    __syncwarp();
+    uint4* gs = reinterpret_cast<uint4*>(b.sp_surface + env * b.CP);
+    uint4* ga = reinterpret_cast<uint4*>(b.sp_attr + env * b.CP);
+    for (int i = c.lane; i < b.CP / 16; i += 32) {
+      gs[i] = reinterpret_cast<const uint4*>(c.S)[i];
+      ga[i] = reinterpret_cast<const uint4*>(c.A)[i];
+    }
+    uint4* dst = reinterpret_cast<uint4*>(b.sp_st + env);
+    const uint4* src = reinterpret_cast<const uint4*>(c.st);
+    for (int i = c.lane; i < (int)(sizeof(EnvState) / 16); i += 32) dst[i] = src[i];
+    __threadfence();
+    __syncwarp();
+    if (c.lane == 0) *reinterpret_cast<volatile uint8_t*>(b.sp_state + env) = 1;
+    count_event(b, c, RGS_PREFETCH_BUILT);
+    __syncwarp();
+  }
+}
+
 // Dungeon::move_enemy with an always-false skip, for the known-answer test (rogue/mod.rs:566-578)
 __global__ void k_test_move_enemy(DevBatch b, int64_t env_id, int fx, int fy, int tx, int ty, int* out3) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* const smem = rg_smem;
   Ctx c;
   const int64_t env = env_id;
   if ((threadIdx.x >> 5) != 0) return;
@@ -365,7 +472,7 @@ __global__ void k_test_move_enemy(DevBatch b, int64_t env_id, int fx, int fy, in
 // Parity harness: finish every suspended DistCache map so that rg_dump_env can show whole maps.
 // Does not change anything observable (a finished map holds the values the reference holds).
 __global__ void __launch_bounds__(32) k_complete_maps(DevBatch b, int64_t env_lo, int64_t env_hi) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* const smem = rg_smem;
   const int64_t env = env_lo + blockIdx.x;
   if (env >= env_hi) return;
   Ctx c;
@@ -557,6 +664,8 @@ cudaError_t configure_kernels(const DevBatch& b) {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_step_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_prefetch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_complete_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one_warp_smem(b));
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(k_test_move_enemy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one_warp_smem(b));
@@ -581,6 +690,13 @@ cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_rese
   int gen_blocks = b.gen_warps / WARPS_PER_BLOCK;
   if (gen_blocks > blocks) gen_blocks = blocks;
   k_step_gen<<<gen_blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, actions, auto_reset, parity);
+  return cudaGetLastError();
+}
+cudaError_t launch_prefetch(const DevBatch& b, cudaStream_t s) {
+  const int64_t blocks_all = (b.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+  int blocks = b.gen_warps / WARPS_PER_BLOCK;
+  if (blocks > blocks_all) blocks = (int)blocks_all;
+  k_prefetch<<<blocks, WARPS_PER_BLOCK * 32, block_smem(b), s>>>(b);
   return cudaGetLastError();
 }
 cudaError_t launch_test_move_enemy(const DevBatch& b, int64_t env, int fx, int fy, int tx, int ty, int* out3,

@@ -32,6 +32,8 @@ enum : uint8_t {
 enum : uint8_t { K_NORMAL = 0, K_MAZE = 1, K_EMPTY = 2 };
 enum : uint8_t { RF_DARK = 1, RF_VISITED = 2, RF_GOLD = 4 };
 enum : uint8_t { MF_PRESENT = 1, MF_ACTIVE = 2 };
+enum { RGS_SWAP_IN = 0, RGS_SYNC_RESET = 1, RGS_FULL_STEP = 2, RGS_PREFETCH_BUILT = 3, RGS_PREFETCH_STALE = 4,
+       RGS_MONSTER_ENVS = 5, RGS_BFS_LEVELS = 6 };
 enum : uint8_t { SF_REDRAW = 1, SF_STATUS = 2, SF_DEAD = 4, SF_SKIP = 8, SF_PANIC = 16 };
 // EnemyAttr bits that the path reads (enemies.rs:125-137)
 enum : uint32_t { EA_MEAN = 1u, EA_RANDOM = 0x200u, EA_CONFUSED = 0x400u };
@@ -108,6 +110,17 @@ struct DevBatch {
   uint32_t* errflag;  // OR of all errors raised since the last rg_sync
   uint32_t* defer_list;   // [N] env id | DEFER_* : work handed to the full-path kernel k_step_gen
   uint32_t* defer_count;  // [2] ping-pong by step parity
+  // "next episode" buffers, filled in the background by k_prefetch and swapped in by k_step_finish
+  // when an env's episode ends (sp_state: 0 = empty / being built, 1 = ready)
+  uint8_t* sp_surface;    // [N][CP]
+  uint8_t* sp_attr;       // [N][CP]
+  uint8_t* sp_screen;     // [N][CP]
+  uint8_t* sp_hist;       // [N][HB]
+  uint32_t* sp_walk;      // [N][H][WW]
+  EnvState* sp_st;        // [N]
+  uint8_t* sp_state;      // [N]
+  unsigned long long* stats;  // [8] RGS_* event counters since creation (observability)
+  int32_t prefetch;       // 0 = off (every reset is generated synchronously by k_step_gen)
   uint32_t* mon_list;     // [N] envs with an active monster this step (player kernel -> monster kernel)
   uint32_t* mon_count;    // [2] ping-pong by step parity
   int32_t mon_warps;      // warps of the (grid-stride) monster kernel

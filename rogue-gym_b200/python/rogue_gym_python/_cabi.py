@@ -101,6 +101,8 @@ SYMBOLS = {
     "rg_step": (_i, [_vp, _vp, _i]),
     "rg_step_host": (_i, [_vp, _vp, _i, C.POINTER(HostObs)]),
     "rg_sync": (_i, [_vp]),
+    "rg_quiesce": (_i, [_vp]),
+    "rg_stats": (_i, [_vp, _vp]),
     "rg_views_get": (_i, [_vp, C.POINTER(Views)]),
     "rg_fetch": (_i, [_vp, C.POINTER(HostObs)]),
     "rg_stream": (_vp, [_vp]),

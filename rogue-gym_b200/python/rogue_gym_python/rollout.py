@@ -74,6 +74,10 @@ class Shard:
         if rc not in (_cabi.RG_OK, _cabi.RG_ERR_PANIC):
             _cabi.check(rc, self.h)
 
+    def quiesce(self):
+        """Main stream waits for the background next-episode generation queued so far (async)."""
+        _cabi.check(self.L.rg_quiesce(self.h), self.h)
+
     def sync(self):
         rc = self.L.rg_sync(self.h)
         if rc not in (_cabi.RG_OK, _cabi.RG_ERR_PANIC):
@@ -89,6 +93,12 @@ class Shard:
         out = np.zeros(self.n, np.uint64)
         _cabi.check(self.L.rg_state_hash(self.h, out.ctypes.data), self.h)
         return out
+
+    def stats(self):
+        out = np.zeros(8, np.uint64)
+        _cabi.check(self.L.rg_stats(self.h, out.ctypes.data), self.h)
+        names = ("swap_in", "sync_reset", "full_step", "prefetch_built", "prefetch_stale", "monster_env_steps")
+        return {k: int(v) for k, v in zip(names, out)}
 
     def launches(self):
         return int(self.L.rg_launch_count(self.h))
