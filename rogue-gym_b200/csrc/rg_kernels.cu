@@ -16,10 +16,63 @@ namespace rg {
 // done, so a warp that runs a BFS does not pin three finished neighbours (measured: 4 warps/block
 // 0.668 ms per step, 1 warp/block 0.626 ms at 64 registers, 65 536 envs).
 constexpr int WARPS_PER_BLOCK = RG_WPB;
-RG_DEV size_t warp_smem(const DevBatch& b) { return 2 * (size_t)b.CP + sizeof(EnvState); }
+RG_DEV size_t warp_smem(const DevBatch& b) { return 2 * (size_t)b.CP + sizeof(EnvState) + 16; }
 
-// Stage one env's small state into shared memory and fill the context.
-RG_DEV void fill_ctx(const DevBatch& b, Ctx& c, unsigned char* base, int64_t env) {
+// ---- staging through shared memory with the bulk-copy engine (TMA, 1-D): one elected lane
+// issues cp.async.bulk for the env's EnvState and tile planes, all in flight at once, completion
+// on an mbarrier; write-back is a bulk shared->global group. (A loop of per-lane 128-bit loads
+// left the kernels waiting on one DRAM round trip per iteration: 48 % of the player kernel's
+// stall samples were long-scoreboard in load_grid / fill_ctx.)
+RG_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+struct Stager {
+  uint32_t bar;    // shared address of this warp's mbarrier
+  uint32_t phase;  // parity of the next completion
+};
+RG_DEV Stager stager_init(const DevBatch& b, unsigned char* base) {
+  Stager s;
+  s.bar = smem_u32(base + 2 * (size_t)b.CP + sizeof(EnvState));
+  s.phase = 0;
+  if ((threadIdx.x & 31) == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s.bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  return s;
+}
+RG_DEV void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+RG_DEV void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+enum { PL_NONE = 0, PL_S = 1, PL_A = 2, PL_BOTH = 3 };
+// Loads EnvState (+ the requested planes) of `env` into the warp's region and waits for them.
+RG_DEV void stage_load(const DevBatch& b, Stager& s, unsigned char* base, int64_t env, int planes) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic accesses to this region first
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    const uint32_t bytes = (uint32_t)sizeof(EnvState) + ((planes & PL_S) ? b.CP : 0) + ((planes & PL_A) ? b.CP : 0);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s.bar), "r"(bytes) : "memory");
+    bulk_g2s(smem_u32(base + 2 * (size_t)b.CP), b.st + env, (uint32_t)sizeof(EnvState), s.bar);
+    if (planes & PL_S) bulk_g2s(smem_u32(base), b.surface + env * b.CP, (uint32_t)b.CP, s.bar);
+    if (planes & PL_A) bulk_g2s(smem_u32(base + b.CP), b.attr + env * b.CP, (uint32_t)b.CP, s.bar);
+  }
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(s.bar), "r"(s.phase)
+        : "memory");
+  } while (!ok);
+  s.phase ^= 1u;
+}
+
+// Stage one env into shared memory and fill the context.
+RG_DEV void fill_ctx(const DevBatch& b, Ctx& c, Stager& sg, unsigned char* base, int64_t env, int planes) {
+  stage_load(b, sg, base, env, planes);
   c.soff = (uint32_t)(base - rg_smem);
   c.S = base;
   c.A = base + b.CP;
@@ -38,43 +91,33 @@ RG_DEV void fill_ctx(const DevBatch& b, Ctx& c, unsigned char* base, int64_t env
   c.g_dist = b.dist + env * (int64_t)NCACHE * b.CP;
   c.g_bfs = b.bfs + env * (int64_t)NCACHE * 2 * b.H * b.WW;
   c.redraw = c.status_upd = c.dead = c.msg = c.hist_done = c.a_dirty = c.s_dirty = c.panic = 0;
-  // small state: 128-bit coalesced
-  const uint4* src = reinterpret_cast<const uint4*>(b.st + env);
-  uint4* dst = reinterpret_cast<uint4*>(c.st);
-  for (int i = c.lane; i < (int)(sizeof(EnvState) / 16); i += 32) dst[i] = src[i];
-  __syncwarp();
   c.rd.load(c.st->rng);
   c.ri.load(c.st->rng + 4);
   c.re.load(c.st->rng + 8);
 }
-RG_DEV void load_grid(const DevBatch& b, Ctx& c, int64_t env) {
-  const uint4* gs = reinterpret_cast<const uint4*>(b.surface + env * b.CP);
-  const uint4* ga = reinterpret_cast<const uint4*>(b.attr + env * b.CP);
-  for (int i = c.lane; i < b.CP / 16; i += 32) {
-    reinterpret_cast<uint4*>(c.S)[i] = gs[i];
-    reinterpret_cast<uint4*>(c.A)[i] = ga[i];
-  }
-  __syncwarp();
-}
-RG_DEV void close_env(const DevBatch& b, Ctx& c, int64_t env) {
+// Write-back: EnvState always, a plane only when it was modified. One bulk group; the issuing
+// lane waits until shared memory has been read (the region may be reused or the block may exit).
+RG_DEV void write_back(const DevBatch& b, Ctx& c, int64_t env, bool with_s, bool with_a, EnvState* st_dst, uint8_t* s_dst,
+                       uint8_t* a_dst) {
   __syncwarp();
   if (c.lane == 0) {
     c.rd.store(c.st->rng);
     c.ri.store(c.st->rng + 4);
     c.re.store(c.st->rng + 8);
   }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncwarp();
-  if (c.s_dirty) {
-    uint4* gs = reinterpret_cast<uint4*>(b.surface + env * b.CP);
-    for (int i = c.lane; i < b.CP / 16; i += 32) gs[i] = reinterpret_cast<const uint4*>(c.S)[i];
+  if (c.lane == 0) {
+    bulk_s2g(st_dst + env, smem_u32(c.st), (uint32_t)sizeof(EnvState));
+    if (with_s) bulk_s2g(s_dst + env * b.CP, smem_u32(c.S), (uint32_t)b.CP);
+    if (with_a) bulk_s2g(a_dst + env * b.CP, smem_u32(c.A), (uint32_t)b.CP);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
-  if (c.a_dirty) {
-    uint4* ga = reinterpret_cast<uint4*>(b.attr + env * b.CP);
-    for (int i = c.lane; i < b.CP / 16; i += 32) ga[i] = reinterpret_cast<const uint4*>(c.A)[i];
-  }
-  uint4* dst = reinterpret_cast<uint4*>(b.st + env);
-  const uint4* src = reinterpret_cast<const uint4*>(c.st);
-  for (int i = c.lane; i < (int)(sizeof(EnvState) / 16); i += 32) dst[i] = src[i];
+  __syncwarp();
+}
+RG_DEV void close_env(const DevBatch& b, Ctx& c, int64_t env) {
+  write_back(b, c, env, c.s_dirty != 0, c.a_dirty != 0, b.st, b.surface, b.attr);
 }
 RG_DEV void emit_obs(const DevBatch& b, Ctx& c, int64_t env, int32_t reward, uint8_t err) {
   if (c.lane < 10) b.status[env * 10 + c.lane] = c.st->status[c.lane];
@@ -107,7 +150,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_reset(DevBatch b) {
   const int warp = threadIdx.x >> 5;
   const int64_t env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
   if (env >= b.n) return;
-  fill_ctx(b, c, smem + (size_t)warp * warp_smem(b), env);
+  unsigned char* const base = smem + (size_t)warp * warp_smem(b);
+  Stager sg = stager_init(b, base);
+  fill_ctx(b, c, sg, base, env, PL_NONE);
   reset_env(c);
   uint8_t err = 0;
   if (c.panic) {
@@ -120,21 +165,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_reset(DevBatch b) {
 }
 
 RG_DEV void store_state(const DevBatch& b, Ctx& c, int64_t env) {
-  __syncwarp();
-  if (c.lane == 0) {
-    c.rd.store(c.st->rng);
-    c.ri.store(c.st->rng + 4);
-    c.re.store(c.st->rng + 8);
-  }
-  __syncwarp();
-  uint4* dst = reinterpret_cast<uint4*>(b.st + env);
-  const uint4* src = reinterpret_cast<const uint4*>(c.st);
-  for (int i = c.lane; i < (int)(sizeof(EnvState) / 16); i += 32) dst[i] = src[i];
-}
-RG_DEV void load_surface(const DevBatch& b, Ctx& c, int64_t env) {
-  const uint4* gs = reinterpret_cast<const uint4*>(b.surface + env * b.CP);
-  for (int i = c.lane; i < b.CP / 16; i += 32) reinterpret_cast<uint4*>(c.S)[i] = gs[i];
-  __syncwarp();
+  write_back(b, c, env, false, false, b.st, b.surface, b.attr);
 }
 RG_DEV bool has_active_monster(const Ctx& c) {
   bool any = false;
@@ -179,9 +210,11 @@ k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset, i
   const int warp = threadIdx.x >> 5;
   const int64_t env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
   if (env >= b.n) return;
-  fill_ctx(b, c, smem + (size_t)warp * warp_smem(b), env);
-  EnvState* st = c.st;
+  unsigned char* const base = smem + (size_t)warp * warp_smem(b);
+  Stager sg = stager_init(b, base);
   const uint8_t key = actions[env];
+  fill_ctx(b, c, sg, base, env, PL_BOTH);  // state and both planes in flight together (9 of 11 actions need them)
+  EnvState* st = c.st;
   if (st->error == RG_ERR_PANIC || st->error == RG_ERR_SETTING) {  // the reference's worker is gone
     emit_obs(b, c, env, 0, st->error);
     skip_env(b, c, env);
@@ -211,7 +244,6 @@ k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset, i
   }
   st->f_gold_before = st->status[1];
   if (act == 0 || act == 2) {
-    load_grid(b, c, env);
     process_action<true>(c, act, d);
   } else if (act == 3) {
     process_action<true>(c, act, d);  // NoDownStair: a turn passes, the grid is not consulted
@@ -231,11 +263,12 @@ k_step_monsters(DevBatch b, int parity) {
   unsigned char* const smem = rg_smem;
   const uint32_t count = b.mon_count[parity];
   const int warp = threadIdx.x >> 5;
+  unsigned char* const base = smem + (size_t)warp * warp_smem(b);
+  Stager sg = stager_init(b, base);
   for (uint32_t i = blockIdx.x * WARPS_PER_BLOCK + warp; i < count; i += gridDim.x * WARPS_PER_BLOCK) {
     const int64_t env = (int64_t)b.mon_list[i];
     Ctx c;
-    fill_ctx(b, c, smem + (size_t)warp * warp_smem(b), env);
-    load_surface(b, c, env);
+    fill_ctx(b, c, sg, base, env, PL_S);
     EnvState* st = c.st;
     c.msg = st->f_msg;
     if (move_active_enemies(c)) st->ui_dead = 1;
@@ -283,8 +316,11 @@ k_step_finish(DevBatch b, int auto_reset, int parity) {
   const int warp = threadIdx.x >> 5;
   const int64_t env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
   if (env >= b.n) return;
-  if (b.st[env].f_flags & SF_SKIP) return;  // answered by the player kernel, or handed to k_step_gen
-  fill_ctx(b, c, smem + (size_t)warp * warp_smem(b), env);
+  const uint8_t flags0 = b.st[env].f_flags;
+  if (flags0 & SF_SKIP) return;  // answered by the player kernel, or handed to k_step_gen
+  unsigned char* const base = smem + (size_t)warp * warp_smem(b);
+  Stager sg = stager_init(b, base);
+  fill_ctx(b, c, sg, base, env, (flags0 & SF_REDRAW) ? PL_BOTH : PL_NONE);
   EnvState* st = c.st;
   const uint32_t flags = st->f_flags;
   const uint32_t gold_before = st->f_gold_before;
@@ -329,10 +365,7 @@ k_step_finish(DevBatch b, int auto_reset, int parity) {
       defer(b, c, env, DEFER_RESET, parity);
       return;
     }
-    if (flags & SF_REDRAW) {
-      load_grid(b, c, env);
-      compose(c);
-    }
+    if (flags & SF_REDRAW) compose(c);
   }
   const int32_t diff = (int32_t)st->status[1] - (int32_t)gold_before;
   emit_obs(b, c, env, diff > 0 ? diff : 0, err);
@@ -363,7 +396,6 @@ RG_DEV void step_env_full(const DevBatch& b, Ctx& c, int64_t env, const uint8_t*
   int d;
   const int act = map_key(actions[env], d);
   const uint32_t gold_before = st->status[1];
-  load_grid(b, c, env);
   process_action<false>(c, act, d);
   uint8_t err = 0;
   if (c.panic) {
@@ -396,11 +428,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_step_gen(DevBatch b, c
   unsigned char* const smem = rg_smem;
   const uint32_t count = b.defer_count[parity];
   const int warp = threadIdx.x >> 5;
+  unsigned char* const base = smem + (size_t)warp * warp_smem(b);
+  Stager sg = stager_init(b, base);
   for (uint32_t i = blockIdx.x * WARPS_PER_BLOCK + warp; i < count; i += gridDim.x * WARPS_PER_BLOCK) {
     const uint32_t item = b.defer_list[i];
     const int64_t env = (int64_t)(item & 0x7FFFFFFFu);
     Ctx c;
-    fill_ctx(b, c, smem + (size_t)warp * warp_smem(b), env);
+    fill_ctx(b, c, sg, base, env, (item & DEFER_RESET) ? PL_NONE : PL_BOTH);
     step_env_full(b, c, env, actions, auto_reset, (item & DEFER_RESET) != 0);
     __syncwarp();
   }
@@ -415,34 +449,22 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_step_gen(DevBatch b, c
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_prefetch(DevBatch b) {
   unsigned char* const smem = rg_smem;
   const int warp = threadIdx.x >> 5;
+  unsigned char* const base = smem + (size_t)warp * warp_smem(b);
+  Stager sg = stager_init(b, base);
   for (int64_t env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp; env < b.n;
        env += (int64_t)gridDim.x * WARPS_PER_BLOCK) {
     if (*reinterpret_cast<volatile uint8_t*>(b.sp_state + env) != 0) continue;
     __threadfence();
     Ctx c;
-    fill_ctx(b, c, smem + (size_t)warp * warp_smem(b), env);  // live seed / episode counter
+    fill_ctx(b, c, sg, base, env, PL_NONE);  // live seed / episode counter
     c.g_screen = b.sp_screen + env * b.CP;
     c.g_hist = b.sp_hist + env * b.HB;
     c.g_walk = b.sp_walk + env * (int64_t)(b.H * b.WW);
     reset_env(c);
     if (c.panic) c.st->error = RG_ERR_PANIC;
     compose(c);
-    __syncwarp();
-    if (c.lane == 0) {
-      c.rd.store(c.st->rng);
-      c.ri.store(c.st->rng + 4);
-      c.re.store(c.st->rng + 8);
-    }
-    __syncwarp();
-    uint4* gs = reinterpret_cast<uint4*>(b.sp_surface + env * b.CP);
-    uint4* ga = reinterpret_cast<uint4*>(b.sp_attr + env * b.CP);
-    for (int i = c.lane; i < b.CP / 16; i += 32) {
-      gs[i] = reinterpret_cast<const uint4*>(c.S)[i];
-      ga[i] = reinterpret_cast<const uint4*>(c.A)[i];
-    }
-    uint4* dst = reinterpret_cast<uint4*>(b.sp_st + env);
-    const uint4* src = reinterpret_cast<const uint4*>(c.st);
-    for (int i = c.lane; i < (int)(sizeof(EnvState) / 16); i += 32) dst[i] = src[i];
+    write_back(b, c, env, true, true, b.sp_st, b.sp_surface, b.sp_attr);
+    if (c.lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the writes themselves, not just the reads
     __threadfence();
     __syncwarp();
     if (c.lane == 0) *reinterpret_cast<volatile uint8_t*>(b.sp_state + env) = 1;
@@ -457,8 +479,8 @@ __global__ void k_test_move_enemy(DevBatch b, int64_t env_id, int fx, int fy, in
   Ctx c;
   const int64_t env = env_id;
   if ((threadIdx.x >> 5) != 0) return;
-  fill_ctx(b, c, smem, env);
-  load_grid(b, c, env);
+  Stager sg = stager_init(b, smem);
+  fill_ctx(b, c, sg, smem, env, PL_BOTH);
   int ox = -1, oy = -1;
   int kind = move_enemy(c, fx, fy, tx, ty, 0, true, ox, oy);
   if (c.lane == 0) {
@@ -476,13 +498,10 @@ __global__ void __launch_bounds__(32) k_complete_maps(DevBatch b, int64_t env_lo
   const int64_t env = env_lo + blockIdx.x;
   if (env >= env_hi) return;
   Ctx c;
-  fill_ctx(b, c, smem, env);
+  Stager sg = stager_init(b, smem);
+  fill_ctx(b, c, sg, smem, env, PL_NONE);
   complete_all_maps(c);
-  __syncwarp();
-  // only the cache directory changed
-  uint4* dst = reinterpret_cast<uint4*>(b.st + env);
-  const uint4* src = reinterpret_cast<const uint4*>(c.st);
-  for (int i = c.lane; i < (int)(sizeof(EnvState) / 16); i += 32) dst[i] = src[i];
+  store_state(b, c, env);  // only the cache directory changed
 }
 
 // ---------------------------------------------------------------- observation encoders
@@ -649,7 +668,7 @@ __global__ void k_unpack_hist(DevBatch b, uint8_t* __restrict__ out) {
 }
 
 // ---------------------------------------------------------------- launchers
-static size_t one_warp_smem(const DevBatch& b) { return 2 * (size_t)b.CP + sizeof(EnvState); }
+static size_t one_warp_smem(const DevBatch& b) { return 2 * (size_t)b.CP + sizeof(EnvState) + 16; }
 static size_t block_smem(const DevBatch& b) { return (size_t)WARPS_PER_BLOCK * one_warp_smem(b); }
 
 cudaError_t configure_kernels(const DevBatch& b) {
