@@ -28,9 +28,17 @@ struct rg_batch {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t bg = nullptr;      // background stream: k_prefetch
+  cudaStream_t side = nullptr;    // full-path steps, forked after the player kernel and joined at the end of the step
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_main = nullptr;  // "this step's kernels are queued up to here"
   cudaEvent_t ev_bg = nullptr;    // last k_prefetch
   bool prefetch_running = false;
+  int prefetch_every = 1;   // kick the background pass every k-th auto-reset step
+  int prefetch_warps = 0;   // grid-stride warps of k_prefetch (0 = as many as the full-path kernel)
+  int64_t auto_steps = 0;
+  int64_t steps_launched = 0;
+  bool use_graph = true;
+  cudaGraphExec_t graph[2] = {nullptr, nullptr};  // [auto_reset]
   DevBatch d{};
   rg_params* dP = nullptr;
   uint8_t* d_actions = nullptr;
@@ -174,6 +182,7 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
   RG_TRY(dev_alloc(b, &d.walk, N * (size_t)d.H * d.WW));
   RG_TRY(dev_alloc(b, &d.dist, N * (size_t)rg::NCACHE * d.CP));
   RG_TRY(dev_alloc(b, &d.bfs, N * (size_t)rg::NCACHE * 2 * d.H * d.WW));
+  RG_TRY(dev_alloc(b, &d.wsnap, N * (size_t)rg::NCACHE * d.H * d.WW));
   RG_TRY(dev_alloc(b, &d.st, N));
   RG_TRY(dev_alloc(b, &d.status, N * 10));
   RG_TRY(dev_alloc(b, &d.reward, N));
@@ -187,15 +196,18 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
   {  // next-episode buffers + background stream (RG_PREFETCH=0 turns the pipeline off)
     const char* pf = getenv("RG_PREFETCH");
     d.prefetch = (pf && pf[0] == '0') ? 0 : 1;
+    if (const char* e = getenv("RG_PREFETCH_EVERY")) b->prefetch_every = std::max(1, atoi(e));
+    if (const char* e = getenv("RG_PREFETCH_WARPS")) b->prefetch_warps = std::max(32, atoi(e));
     if (d.prefetch) {
-      RG_TRY(dev_alloc(b, &d.sp_surface, N * d.CP));
-      RG_TRY(dev_alloc(b, &d.sp_attr, N * d.CP));
-      RG_TRY(dev_alloc(b, &d.sp_screen, N * d.CP));
-      RG_TRY(dev_alloc(b, &d.sp_hist, N * d.HB));
-      RG_TRY(dev_alloc(b, &d.sp_walk, N * (size_t)d.H * d.WW));
-      RG_TRY(dev_alloc(b, &d.sp_st, N));
-      RG_TRY(dev_alloc(b, &d.sp_state, N));
-      RG_TRY(cudaMemsetAsync(d.sp_state, 0, N, b->stream));
+      const size_t NS = N * rg::SP_DEPTH;
+      RG_TRY(dev_alloc(b, &d.sp_surface, NS * d.CP));
+      RG_TRY(dev_alloc(b, &d.sp_attr, NS * d.CP));
+      RG_TRY(dev_alloc(b, &d.sp_screen, NS * d.CP));
+      RG_TRY(dev_alloc(b, &d.sp_hist, NS * d.HB));
+      RG_TRY(dev_alloc(b, &d.sp_walk, NS * (size_t)d.H * d.WW));
+      RG_TRY(dev_alloc(b, &d.sp_st, NS));
+      RG_TRY(dev_alloc(b, &d.sp_state, NS));
+      RG_TRY(cudaMemsetAsync(d.sp_state, 0, NS, b->stream));
       int lo = 0, hi = 0;
       RG_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
       {
@@ -206,8 +218,23 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
       RG_TRY(cudaEventCreateWithFlags(&b->ev_bg, cudaEventDisableTiming));
     }
   }
+  if (const char* tr = getenv("RG_TRACE"); tr && tr[0] == '1') {
+    RG_TRY(dev_alloc(b, &d.trace, 512 * 8 * 2));
+    std::vector<unsigned long long> init(512 * 8 * 2);
+    for (size_t i = 0; i < init.size(); ++i) init[i] = (i & 1) ? 0ull : ~0ull;
+    RG_TRY(cudaMemcpy(d.trace, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
+  }
   RG_TRY(dev_alloc(b, &d.stats, 8));
   RG_TRY(cudaMemsetAsync(d.stats, 0, 64, b->stream));
+  RG_TRY(dev_alloc(b, &d.dstep, 4));
+  RG_TRY(cudaMemsetAsync(d.dstep, 0, 16, b->stream));
+  if (const char* g = getenv("RG_GRAPH")) b->use_graph = g[0] != '0';
+  RG_TRY(dev_alloc(b, &d.reset_list, N));
+  RG_TRY(dev_alloc(b, &d.reset_count, 4));
+  RG_TRY(cudaMemsetAsync(d.reset_count, 0, 16, b->stream));
+  RG_TRY(cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking));
+  RG_TRY(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+  RG_TRY(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
   RG_TRY(dev_alloc(b, &d.mon_list, N));
   RG_TRY(dev_alloc(b, &d.mon_count, 4));
   RG_TRY(cudaMemsetAsync(d.mon_count, 0, 16, b->stream));
@@ -265,7 +292,7 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
 int invalidate_prefetched(rg_batch* b) {
   if (!b->d.prefetch) return RG_OK;
   RG_CUDA(b, cudaStreamSynchronize(b->bg));
-  RG_CUDA(b, cudaMemsetAsync(b->d.sp_state, 0, (size_t)b->n, b->stream));
+  RG_CUDA(b, cudaMemsetAsync(b->d.sp_state, 0, (size_t)b->n * rg::SP_DEPTH, b->stream));
   return RG_OK;
 }
 
@@ -274,7 +301,7 @@ int kick_prefetch(rg_batch* b) {
   if (!b->d.prefetch) return RG_OK;
   RG_CUDA(b, cudaEventRecord(b->ev_main, b->stream));
   RG_CUDA(b, cudaStreamWaitEvent(b->bg, b->ev_main, 0));
-  RG_CUDA(b, rg::launch_prefetch(b->d, b->bg));
+  RG_CUDA(b, rg::launch_prefetch(b->d, b->prefetch_warps, b->bg));
   RG_CUDA(b, cudaEventRecord(b->ev_bg, b->bg));
   b->launches += 1;
   b->prefetch_running = true;
@@ -339,6 +366,12 @@ void rg_destroy(rg_batch* b) {
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
   if (b->bg) cudaStreamSynchronize(b->bg);
+  if (b->side) cudaStreamSynchronize(b->side);
+  for (int i = 0; i < 2; ++i)
+    if (b->graph[i]) cudaGraphExecDestroy(b->graph[i]);
+  if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+  if (b->ev_join) cudaEventDestroy(b->ev_join);
+  if (b->side) cudaStreamDestroy(b->side);
   if (b->ev_main) cudaEventDestroy(b->ev_main);
   if (b->ev_bg) cudaEventDestroy(b->ev_bg);
   if (b->bg) cudaStreamDestroy(b->bg);
@@ -378,10 +411,30 @@ int rg_reset(rg_batch* b) {
 int rg_step(rg_batch* b, const uint8_t* actions_dev, int auto_reset) {
   if (!b || !actions_dev) return set_err(b, RG_ERR_ARG, "rg_step: null argument");
   RG_CUDA(b, cudaSetDevice(b->device));
-  RG_CUDA(b, rg::launch_step(b->d, actions_dev, auto_reset, (int)(b->step_parity & 1), b->stream));
-  b->step_parity ^= 1;
-  b->launches += 4;
-  if (auto_reset) return kick_prefetch(b);  // refill the next-episode buffers consumed so far
+  auto_reset = auto_reset ? 1 : 0;
+  // the step kernels read the batch's own action buffer, so that the launch sequence has no
+  // per-step argument and can be replayed as a graph
+  if (actions_dev != b->d_actions)
+    RG_CUDA(b, cudaMemcpyAsync(b->d_actions, actions_dev, (size_t)b->n, cudaMemcpyDeviceToDevice, b->stream));
+  b->d.trace_step = (int32_t)(b->steps_launched++ % 512);
+  if (b->use_graph) {
+    if (!b->graph[auto_reset]) {
+      cudaGraph_t g = nullptr;
+      RG_CUDA(b, cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
+      cudaError_t le = rg::launch_step(b->d, b->d_actions, auto_reset, b->stream, b->side, b->ev_fork, b->ev_join);
+      cudaError_t ce = cudaStreamEndCapture(b->stream, &g);
+      if (le != cudaSuccess) return cuda_fail(b, le, "launch_step (capture)");
+      if (ce != cudaSuccess) return cuda_fail(b, ce, "cudaStreamEndCapture");
+      RG_CUDA(b, cudaGraphInstantiate(&b->graph[auto_reset], g, 0));
+      cudaGraphDestroy(g);
+    }
+    RG_CUDA(b, cudaGraphLaunch(b->graph[auto_reset], b->stream));
+  } else {
+    RG_CUDA(b, rg::launch_step(b->d, b->d_actions, auto_reset, b->stream, b->side, b->ev_fork, b->ev_join));
+  }
+  b->launches += auto_reset ? 6 : 5;
+  if (auto_reset && (b->auto_steps++ % b->prefetch_every) == 0)
+    return kick_prefetch(b);  // refill the next-episode buffers consumed so far
   return RG_OK;
 }
 
@@ -391,6 +444,17 @@ int rg_stats(rg_batch* b, uint64_t* out8) {
   RG_CUDA(b, cudaStreamSynchronize(b->stream));
   if (b->bg) RG_CUDA(b, cudaStreamSynchronize(b->bg));
   RG_CUDA(b, cudaMemcpy(out8, b->d.stats, 64, cudaMemcpyDeviceToHost));
+  return RG_OK;
+}
+
+int rg_trace(rg_batch* b, uint64_t* out, int64_t* steps_launched) {
+  if (!b || !out) return set_err(b, RG_ERR_ARG, "rg_trace: null argument");
+  if (!b->d.trace) return set_err(b, RG_ERR_ARG, "rg_trace: tracing is off (set RG_TRACE=1 before creating the batch)");
+  RG_CUDA(b, cudaSetDevice(b->device));
+  RG_CUDA(b, cudaStreamSynchronize(b->stream));
+  if (b->bg) RG_CUDA(b, cudaStreamSynchronize(b->bg));
+  RG_CUDA(b, cudaMemcpy(out, b->d.trace, 512 * 8 * 2 * 8, cudaMemcpyDeviceToHost));
+  if (steps_launched) *steps_launched = b->steps_launched;
   return RG_OK;
 }
 

@@ -112,6 +112,7 @@ struct Ctx {
   uint32_t* g_walk;
   uint16_t* g_dist;
   uint32_t* g_bfs;    // per cache slot: frontier rows then visited rows of a suspended BFS
+  uint32_t* g_wsnap;  // per cache slot: private walkability snapshot (see snapshot_suspended_maps)
   Rng rd, ri, re;     // dungeon / item / enemy streams (registers)
   // per-step reaction summary (state_impls.rs:57-75 collapses to these)
   uint32_t redraw, status_upd, dead, msg, hist_done, a_dirty, s_dirty, panic;
@@ -658,7 +659,7 @@ __device__ void build_walk(Ctx& c) {
   __syncwarp();
 }
 
-__device__ void complete_all_maps(Ctx& c);  // lazy DistCache, defined with the BFS below
+__device__ void snapshot_suspended_maps(Ctx& c);  // lazy DistCache, defined with the BFS below
 
 // rogue::Dungeon::new_level_ rogue/mod.rs:434-481 + Floor::gen_floor floor.rs:50-104
 // + setup_items :132-153 + setup_stair :156-167 + place_enemies :106-130,
@@ -669,7 +670,7 @@ __device__ __noinline__ void new_level(Ctx* cp, bool is_initial) {
   const rg_params& P = *c.P;
   const int W = c.W;
   if (!is_initial) {
-    complete_all_maps(c);  // suspended DistCache maps belong to the floor that is about to be replaced
+    snapshot_suspended_maps(c);  // suspended DistCache maps belong to the floor that is about to be replaced
     // The descending step shows the visited map of the floor being left:
     // emit it now, before the planes are overwritten.
     __syncwarp();
@@ -940,11 +941,12 @@ __device__ void bfs_extend(Ctx& c, int slot, int nx0, int ny0) {
   uint32_t* Vg = Fg + c.H * c.WW;
   const int fx = st->cache_x[slot], fy = st->cache_y[slot];
   const int rpl = (c.H + 31) / 32;
+  const uint32_t* walk = ((st->cache_snap >> slot) & 1u) ? c.g_wsnap + (size_t)slot * c.H * c.WW : c.g_walk;
   uint32_t r = BFS_COMPLETE;
   bool ok = false;
 #define RG_BFS_CASE(WD, RP)                                                                                   \
   if (c.WW == WD && rpl == RP) {                                                                              \
-    r = bfs_impl<WD, RP>(c.g_walk, out, Fg, Vg, c.W, c.H, c.CP, fx, fy, lvl, nx0, ny0, c.lane);                 \
+    r = bfs_impl<WD, RP>(walk, out, Fg, Vg, c.W, c.H, c.CP, fx, fy, lvl, nx0, ny0, c.lane);                      \
     ok = true;                                                                                                \
   }
   RG_BFS_CASE(3, 1) else RG_BFS_CASE(1, 1) else RG_BFS_CASE(2, 1) else RG_BFS_CASE(4, 1) else RG_BFS_CASE(5, 1)
@@ -958,7 +960,7 @@ __device__ void bfs_extend(Ctx& c, int slot, int nx0, int ny0) {
   __syncwarp();
 }
 
-// Finish every suspended map of this env (called before the walkability they were started on changes).
+// Finish every suspended map of this env (parity harness: rg_dump_env shows whole maps).
 __device__ void complete_all_maps(Ctx& c) {
   RG_PLANES(c);
   const int n = st->cache_n, head = st->cache_head;
@@ -966,6 +968,27 @@ __device__ void complete_all_maps(Ctx& c) {
     const int slot = (head + k) % NCACHE;
     if (st->cache_lvl[slot] != BFS_COMPLETE) bfs_extend(c, slot, -2, -2);
   }
+}
+
+// Called before the walkability changes (search unlocking a cell, descending): every suspended
+// map that still resumes on the shared bitboard gets a private copy of it, so that whenever it is
+// extended later it sees the floor it was started on - exactly what the reference's eagerly
+// computed map saw. (Copying 288 B per suspended map replaces finishing up to nine whole BFS.)
+__device__ void snapshot_suspended_maps(Ctx& c) {
+  RG_PLANES(c);
+  const int n = st->cache_n, head = st->cache_head;
+  const int words = c.H * c.WW;
+  uint32_t snap = st->cache_snap;
+  for (int k = 0; k < n; ++k) {
+    const int slot = (head + k) % NCACHE;
+    if (st->cache_lvl[slot] == BFS_COMPLETE || ((snap >> slot) & 1u)) continue;
+    uint32_t* dst = c.g_wsnap + (size_t)slot * words;
+    for (int i = c.lane; i < words; i += 32) dst[i] = c.g_walk[i];
+    snap |= 1u << slot;
+  }
+  __syncwarp();
+  st->cache_snap = (uint16_t)snap;
+  __syncwarp();
 }
 
 // DistCache::make_dist_map rogue/mod.rs:504-517: FIFO of 9 keyed by the target coordinate,
@@ -990,6 +1013,7 @@ __device__ int cached_dist_map(Ctx& c, int tx, int ty, int nx0, int ny0) {
     st->cache_x[slot] = (uint8_t)tx;
     st->cache_y[slot] = (uint8_t)ty;
     st->cache_lvl[slot] = 0;
+    st->cache_snap = (uint16_t)(st->cache_snap & ~(1u << slot));  // a new map starts on the current floor
     __syncwarp();
   }
   bfs_extend(c, slot, nx0, ny0);
@@ -1276,7 +1300,7 @@ __device__ void search(Ctx& c) {
     int idx = ny * W + nx;
     bool opened = false;
     if ((A[idx] & (A_HIDDEN | A_LOCKED)) && !maps_done) {  // walkability may change below
-      complete_all_maps(c);
+      snapshot_suspended_maps(c);
       maps_done = true;
     }
     if ((A[idx] & A_HIDDEN) && c.rd.does_happen(c.P->passage_unlock_rate_inv)) {
@@ -1448,6 +1472,7 @@ __device__ void reset_env(Ctx& c) {
   st->level = 0;
   st->cache_n = 0;
   st->cache_head = 0;
+  st->cache_snap = 0;
   st->hp = st->hp_max = P.init_hp;
   st->exp = 0;
   st->plevel = 1;

@@ -90,6 +90,7 @@ RG_DEV void fill_ctx(const DevBatch& b, Ctx& c, Stager& sg, unsigned char* base,
   c.g_walk = b.walk + env * (int64_t)(b.H * b.WW);
   c.g_dist = b.dist + env * (int64_t)NCACHE * b.CP;
   c.g_bfs = b.bfs + env * (int64_t)NCACHE * 2 * b.H * b.WW;
+  c.g_wsnap = b.wsnap + env * (int64_t)NCACHE * b.H * b.WW;
   c.redraw = c.status_upd = c.dead = c.msg = c.hist_done = c.a_dirty = c.s_dirty = c.panic = 0;
   c.rd.load(c.st->rng);
   c.ri.load(c.st->rng + 4);
@@ -130,6 +131,28 @@ RG_DEV void emit_obs(const DevBatch& b, Ctx& c, int64_t env, int32_t reward, uin
   }
 }
 
+// Optional timeline (RG_TRACE=1): first start / last end of every kernel of a step, sampled by
+// one block in 64, read back with rg_trace.
+enum { TK_PLAYER = 0, TK_MONSTERS = 1, TK_FINISH = 2, TK_FULL = 3, TK_RESETS = 4, TK_PREFETCH = 5 };
+RG_DEV unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+struct TraceScope {
+  unsigned long long* slot;
+  RG_DEV TraceScope(const DevBatch& b, int kernel) {
+    slot = nullptr;
+    if (b.trace && (blockIdx.x & 63) == 0 && threadIdx.x == 0) {
+      slot = b.trace + ((size_t)(kernel == TK_PREFETCH ? b.trace_step : (int)(*b.dstep % 512u)) * 8 + kernel) * 2;
+      atomicMin(slot, gtime());
+    }
+  }
+  RG_DEV ~TraceScope() {
+    if (slot) atomicMax(slot + 1, gtime());
+  }
+};
+
 // Work the hot step kernel hands to the generation kernel (one entry per env, any order).
 enum : uint32_t { DEFER_STEP = 0u, DEFER_RESET = 0x80000000u };
 RG_DEV void count_event(const DevBatch& b, const Ctx& c, int which) {
@@ -138,8 +161,11 @@ RG_DEV void count_event(const DevBatch& b, const Ctx& c, int which) {
 RG_DEV void defer(const DevBatch& b, Ctx& c, int64_t env, uint32_t code, int parity) {
   if (c.lane == 0) {
     atomicAdd(b.stats + (code ? RGS_SYNC_RESET : RGS_FULL_STEP), 1ull);
-    uint32_t slot = atomicAdd(b.defer_count + parity, 1u);
-    b.defer_list[slot] = (uint32_t)env | code;
+    // two lists: full-path steps are known after the player kernel (their kernel overlaps the monster
+    // and finish kernels on a side stream), synchronous resets only after the finish kernel
+    uint32_t* cnt = (code ? b.reset_count : b.defer_count) + parity;
+    uint32_t* list = code ? b.reset_list : b.defer_list;
+    list[atomicAdd(cnt, 1u)] = (uint32_t)env | code;
   }
 }
 
@@ -200,10 +226,13 @@ RG_DEV void skip_env(const DevBatch& b, Ctx& c, int64_t env) {
 }
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_HOT_MIN_BLOCKS)
-k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset, int parity) {
+k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset) {
   unsigned char* const smem = rg_smem;
+  const int parity = (int)(*b.dstep & 1u);
+  TraceScope trace(b, TK_PLAYER);
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // next step's counters
     b.defer_count[parity ^ 1] = 0;
+    b.reset_count[parity ^ 1] = 0;
     b.mon_count[parity ^ 1] = 0;
   }
   Ctx c;
@@ -259,8 +288,10 @@ k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset, i
 
 // actions::move_active_enemies (actions.rs:82-119) for the envs that have an active monster
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_HOT_MIN_BLOCKS)
-k_step_monsters(DevBatch b, int parity) {
+k_step_monsters(DevBatch b) {
   unsigned char* const smem = rg_smem;
+  const int parity = (int)(*b.dstep & 1u);
+  TraceScope trace(b, TK_MONSTERS);
   const uint32_t count = b.mon_count[parity];
   const int warp = threadIdx.x >> 5;
   unsigned char* const base = smem + (size_t)warp * warp_smem(b);
@@ -280,11 +311,11 @@ k_step_monsters(DevBatch b, int parity) {
 }
 
 // Copies env's prefetched game (planes, screen, history, walk rows, EnvState) over the live one.
-RG_DEV void swap_in_prefetched(const DevBatch& b, Ctx& c, int64_t env) {
+RG_DEV void swap_in_prefetched(const DevBatch& b, Ctx& c, int64_t env, int64_t sp) {
   const int n16 = b.CP / 16;
-  const uint4* s0 = reinterpret_cast<const uint4*>(b.sp_surface + env * b.CP);
-  const uint4* s1 = reinterpret_cast<const uint4*>(b.sp_attr + env * b.CP);
-  const uint4* s2 = reinterpret_cast<const uint4*>(b.sp_screen + env * b.CP);
+  const uint4* s0 = reinterpret_cast<const uint4*>(b.sp_surface + sp * b.CP);
+  const uint4* s1 = reinterpret_cast<const uint4*>(b.sp_attr + sp * b.CP);
+  const uint4* s2 = reinterpret_cast<const uint4*>(b.sp_screen + sp * b.CP);
   uint4* d0 = reinterpret_cast<uint4*>(b.surface + env * b.CP);
   uint4* d1 = reinterpret_cast<uint4*>(b.attr + env * b.CP);
   uint4* d2 = reinterpret_cast<uint4*>(b.screen + env * b.CP);
@@ -293,13 +324,13 @@ RG_DEV void swap_in_prefetched(const DevBatch& b, Ctx& c, int64_t env) {
     d1[i] = s1[i];
     d2[i] = s2[i];
   }
-  const uint4* h0 = reinterpret_cast<const uint4*>(b.sp_hist + env * b.HB);
+  const uint4* h0 = reinterpret_cast<const uint4*>(b.sp_hist + sp * b.HB);
   uint4* h1 = reinterpret_cast<uint4*>(b.hist + env * b.HB);
   for (int i = c.lane; i < b.HB / 16; i += 32) h1[i] = h0[i];
-  const uint32_t* w0 = b.sp_walk + env * (int64_t)(b.H * b.WW);
+  const uint32_t* w0 = b.sp_walk + sp * (int64_t)(b.H * b.WW);
   uint32_t* w1 = b.walk + env * (int64_t)(b.H * b.WW);
   for (int i = c.lane; i < b.H * b.WW; i += 32) w1[i] = w0[i];
-  const uint4* e0 = reinterpret_cast<const uint4*>(b.sp_st + env);
+  const uint4* e0 = reinterpret_cast<const uint4*>(b.sp_st + sp);
   uint4* e1 = reinterpret_cast<uint4*>(c.st);
   __syncwarp();
   for (int i = c.lane; i < (int)(sizeof(EnvState) / 16); i += 32) e1[i] = e0[i];
@@ -310,8 +341,10 @@ RG_DEV void swap_in_prefetched(const DevBatch& b, Ctx& c, int64_t env) {
 }
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_HOT_MIN_BLOCKS)
-k_step_finish(DevBatch b, int auto_reset, int parity) {
+k_step_finish(DevBatch b, int auto_reset) {
   unsigned char* const smem = rg_smem;
+  const int parity = (int)(*b.dstep & 1u);
+  TraceScope trace(b, TK_FINISH);
   Ctx c;
   const int warp = threadIdx.x >> 5;
   const int64_t env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
@@ -334,21 +367,23 @@ k_step_finish(DevBatch b, int auto_reset, int parity) {
     st->steps += 1;
     st->is_terminal = ((flags & SF_DEAD) || (int64_t)st->steps >= b.max_steps) ? 1 : 0;
     if (st->is_terminal && auto_reset) {
-      bool ready = b.prefetch && *reinterpret_cast<volatile uint8_t*>(b.sp_state + env) == 1;
+      // the game for episode e+1 lives in ring slot (e+1) % SP_DEPTH
+      const int64_t sp = env * SP_DEPTH + (int64_t)((st->episode + 1) % SP_DEPTH);
+      bool ready = b.prefetch && *reinterpret_cast<volatile uint8_t*>(b.sp_state + sp) == 1;
       if (ready) {
         __threadfence();
-        // built from this episode's seed / counter? (a synchronous reset may have overtaken it)
-        if (*reinterpret_cast<volatile uint32_t*>(&b.sp_st[env].episode) != st->episode + 1) {
+        // built for exactly this episode? (a synchronous reset may have overtaken the background pass)
+        if (*reinterpret_cast<volatile uint32_t*>(&b.sp_st[sp].episode) != st->episode + 1) {
           ready = false;
           count_event(b, c, RGS_PREFETCH_STALE);
           __syncwarp();
-          if (c.lane == 0) *reinterpret_cast<volatile uint8_t*>(b.sp_state + env) = 0;
+          if (c.lane == 0) *reinterpret_cast<volatile uint8_t*>(b.sp_state + sp) = 0;
         }
       }
       if (ready) {
         // The next episode of this env was generated ahead of time (k_prefetch): move it in.
         count_event(b, c, RGS_SWAP_IN);
-        swap_in_prefetched(b, c, env);
+        swap_in_prefetched(b, c, env, sp);
         const uint8_t perr = st->error;
         st->is_terminal = 1;
         const int32_t d0 = (int32_t)st->status[1] - (int32_t)gold_before;
@@ -356,7 +391,7 @@ k_step_finish(DevBatch b, int auto_reset, int parity) {
         store_state(b, c, env);
         __threadfence();
         __syncwarp();
-        if (c.lane == 0) *reinterpret_cast<volatile uint8_t*>(b.sp_state + env) = 0;
+        if (c.lane == 0) *reinterpret_cast<volatile uint8_t*>(b.sp_state + sp) = 0;
         return;
       }
       // not ready (or prefetch off): the fresh game is built synchronously by k_step_gen
@@ -422,16 +457,23 @@ RG_DEV void step_env_full(const DevBatch& b, Ctx& c, int64_t env, const uint8_t*
   close_env(b, c, env);
 }
 
+__global__ void k_step_end(DevBatch b) {
+  if (threadIdx.x == 0) *b.dstep += 1u;
+}
+
 // Grid-stride over the full-path list; exits at once when the list is empty.
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_step_gen(DevBatch b, const uint8_t* __restrict__ actions,
-                                                                  int auto_reset, int parity) {
+                                                                  int auto_reset, int resets) {
   unsigned char* const smem = rg_smem;
-  const uint32_t count = b.defer_count[parity];
+  const int parity = (int)(*b.dstep & 1u);
+  TraceScope trace(b, resets ? TK_RESETS : TK_FULL);
+  const uint32_t count = resets ? b.reset_count[parity] : b.defer_count[parity];
+  const uint32_t* const work = resets ? b.reset_list : b.defer_list;
   const int warp = threadIdx.x >> 5;
   unsigned char* const base = smem + (size_t)warp * warp_smem(b);
   Stager sg = stager_init(b, base);
   for (uint32_t i = blockIdx.x * WARPS_PER_BLOCK + warp; i < count; i += gridDim.x * WARPS_PER_BLOCK) {
-    const uint32_t item = b.defer_list[i];
+    const uint32_t item = work[i];
     const int64_t env = (int64_t)(item & 0x7FFFFFFFu);
     Ctx c;
     fill_ctx(b, c, sg, base, env, (item & DEFER_RESET) ? PL_NONE : PL_BOTH);
@@ -448,28 +490,51 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_step_gen(DevBatch b, c
 // may write it, 1: the step kernels may read it), with a fence on each side.
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_prefetch(DevBatch b) {
   unsigned char* const smem = rg_smem;
+  TraceScope trace(b, TK_PREFETCH);
   const int warp = threadIdx.x >> 5;
   unsigned char* const base = smem + (size_t)warp * warp_smem(b);
   Stager sg = stager_init(b, base);
   for (int64_t env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp; env < b.n;
        env += (int64_t)gridDim.x * WARPS_PER_BLOCK) {
-    if (*reinterpret_cast<volatile uint8_t*>(b.sp_state + env) != 0) continue;
+    bool all_ready = true;
+    for (int k = 0; k < SP_DEPTH; ++k)
+      all_ready = all_ready && *reinterpret_cast<volatile uint8_t*>(b.sp_state + env * SP_DEPTH + k) != 0;
+    if (all_ready) continue;
     __threadfence();
-    Ctx c;
-    fill_ctx(b, c, sg, base, env, PL_NONE);  // live seed / episode counter
-    c.g_screen = b.sp_screen + env * b.CP;
-    c.g_hist = b.sp_hist + env * b.HB;
-    c.g_walk = b.sp_walk + env * (int64_t)(b.H * b.WW);
-    reset_env(c);
-    if (c.panic) c.st->error = RG_ERR_PANIC;
-    compose(c);
-    write_back(b, c, env, true, true, b.sp_st, b.sp_surface, b.sp_attr);
-    if (c.lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the writes themselves, not just the reads
-    __threadfence();
-    __syncwarp();
-    if (c.lane == 0) *reinterpret_cast<volatile uint8_t*>(b.sp_state + env) = 1;
-    count_event(b, c, RGS_PREFETCH_BUILT);
-    __syncwarp();
+    const uint32_t e0 = *reinterpret_cast<volatile uint32_t*>(&b.st[env].episode);  // live episode counter
+    // Episode e0+k is built from the state that precedes it: the live env (k = 1) or the
+    // already-built game of episode e0+k-1 (its EnvState carries the seed the next reset uses).
+    for (uint32_t k = 1; k <= (uint32_t)SP_DEPTH; ++k) {
+      const int64_t sp = env * SP_DEPTH + (int64_t)((e0 + k) % SP_DEPTH);
+      const bool have = *reinterpret_cast<volatile uint8_t*>(b.sp_state + sp) == 1 &&
+                        *reinterpret_cast<volatile uint32_t*>(&b.sp_st[sp].episode) == e0 + k;
+      if (have) continue;
+      if (*reinterpret_cast<volatile uint8_t*>(b.sp_state + sp) == 1) break;  // holds a game the step kernels may still take
+      __threadfence();
+      Ctx c;
+      if (k == 1) {
+        fill_ctx(b, c, sg, base, env, PL_NONE);
+      } else {
+        const int64_t prev = env * SP_DEPTH + (int64_t)((e0 + k - 1) % SP_DEPTH);
+        DevBatch bb = b;
+        bb.st = b.sp_st;  // basis = the previous prefetched game
+        fill_ctx(bb, c, sg, base, prev, PL_NONE);
+      }
+      if (c.st->episode != e0 + k - 1) break;  // the basis moved on under us: next pass
+      c.g_screen = b.sp_screen + sp * b.CP;
+      c.g_hist = b.sp_hist + sp * b.HB;
+      c.g_walk = b.sp_walk + sp * (int64_t)(b.H * b.WW);
+      reset_env(c);
+      if (c.panic) c.st->error = RG_ERR_PANIC;
+      compose(c);
+      write_back(b, c, sp, true, true, b.sp_st, b.sp_surface, b.sp_attr);
+      if (c.lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the writes themselves, not just the reads
+      __threadfence();
+      __syncwarp();
+      if (c.lane == 0) *reinterpret_cast<volatile uint8_t*>(b.sp_state + sp) = 1;
+      count_event(b, c, RGS_PREFETCH_BUILT);
+      __syncwarp();
+    }
   }
 }
 
@@ -694,26 +759,43 @@ cudaError_t launch_reset(const DevBatch& b, cudaStream_t s) {
   k_reset<<<blocks, WARPS_PER_BLOCK * 32, block_smem(b), s>>>(b);
   return cudaGetLastError();
 }
-cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_reset, int parity, cudaStream_t s) {
+// Enqueues one env-step: player kernel, then the full-path kernel on `side` beside the monster and
+// finish kernels, the synchronous-reset pass, the join, and the step counter. No per-step
+// arguments (the step parity lives on the device, the actions are read from a fixed buffer), so
+// the whole sequence is captured once into a CUDA graph and replayed with one launch per step.
+cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_reset, cudaStream_t s, cudaStream_t side,
+                        cudaEvent_t ev_fork, cudaEvent_t ev_join) {
   const int blocks = (int)((b.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
   const size_t sm = block_smem(b);
-  k_step_player<<<blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, actions, auto_reset, parity);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  int mon_blocks = b.mon_warps / WARPS_PER_BLOCK;
-  if (mon_blocks > blocks) mon_blocks = blocks;
-  k_step_monsters<<<mon_blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, parity);
-  if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  k_step_finish<<<blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, auto_reset, parity);
-  if ((e = cudaGetLastError()) != cudaSuccess) return e;
   int gen_blocks = b.gen_warps / WARPS_PER_BLOCK;
   if (gen_blocks > blocks) gen_blocks = blocks;
-  k_step_gen<<<gen_blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, actions, auto_reset, parity);
+  cudaError_t e;
+  k_step_player<<<blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, actions, auto_reset);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  // full-path steps (descents, MoveUntil) are a few long serial chains: run them beside the
+  // monster and finish kernels instead of after them
+  if ((e = cudaEventRecord(ev_fork, s)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(side, ev_fork, 0)) != cudaSuccess) return e;
+  k_step_gen<<<gen_blocks, WARPS_PER_BLOCK * 32, sm, side>>>(b, actions, auto_reset, 0);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if ((e = cudaEventRecord(ev_join, side)) != cudaSuccess) return e;
+  int mon_blocks = b.mon_warps / WARPS_PER_BLOCK;
+  if (mon_blocks > blocks) mon_blocks = blocks;
+  k_step_monsters<<<mon_blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  k_step_finish<<<blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, auto_reset);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (auto_reset) {  // episode ends whose next game was not prefetched in time (normally none)
+    k_step_gen<<<gen_blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, actions, auto_reset, 1);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  if ((e = cudaStreamWaitEvent(s, ev_join, 0)) != cudaSuccess) return e;
+  k_step_end<<<1, 32, 0, s>>>(b);
   return cudaGetLastError();
 }
-cudaError_t launch_prefetch(const DevBatch& b, cudaStream_t s) {
+cudaError_t launch_prefetch(const DevBatch& b, int warps, cudaStream_t s) {
   const int64_t blocks_all = (b.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-  int blocks = b.gen_warps / WARPS_PER_BLOCK;
+  int blocks = (warps > 0 ? warps : b.gen_warps) / WARPS_PER_BLOCK;
   if (blocks > blocks_all) blocks = (int)blocks_all;
   k_prefetch<<<blocks, WARPS_PER_BLOCK * 32, block_smem(b), s>>>(b);
   return cudaGetLastError();

@@ -20,6 +20,7 @@ namespace rg {
 
 constexpr int MAX_ROOMS = RG_MAX_ROOMS;
 constexpr int NCACHE = RG_DIST_CACHE;
+constexpr int SP_DEPTH = 2;  // prefetched next-episode games kept per env
 
 // Surface codes follow the reference's declaration order (rogue/mod.rs:137-146).
 enum : uint8_t { S_PASSAGE = 0, S_FLOOR = 1, S_WALLX = 2, S_WALLY = 3, S_STAIR = 4, S_DOOR = 5, S_TRAP = 6, S_NONE = 7 };
@@ -76,8 +77,9 @@ struct alignas(16) EnvState {
   // per-step hand-over between the phase kernels (player -> monsters -> finish)
   uint32_t f_msg;          // message bits collected so far
   uint32_t f_gold_before;  // displayed gold when the step began (reward = max(0, after - before))
+  uint16_t cache_snap;     // bit s: cache slot s resumes on its private walkability snapshot (wsnap)
   uint8_t f_flags;         // SF_*
-  uint8_t pad3[3];
+  uint8_t pad3;
   RoomD rooms[MAX_ROOMS];
   uint16_t item_pos[MAX_ROOMS];  // y*W+x or 0xFFFF ; slot = room id
   uint32_t item_amt[MAX_ROOMS];
@@ -100,6 +102,7 @@ struct DevBatch {
   uint32_t* walk;
   uint16_t* dist;
   uint32_t* bfs;       // u32 [N][9][2][H][WW] suspended-BFS frontier / visited rows
+  uint32_t* wsnap;     // u32 [N][9][H][WW] walkability a suspended map was started on, once the floor has changed
   EnvState* st;
   // observation block
   uint32_t* status;
@@ -110,15 +113,20 @@ struct DevBatch {
   uint32_t* errflag;  // OR of all errors raised since the last rg_sync
   uint32_t* defer_list;   // [N] env id | DEFER_* : work handed to the full-path kernel k_step_gen
   uint32_t* defer_count;  // [2] ping-pong by step parity
+  uint32_t* reset_list;   // [N] terminal envs whose next game was not prefetched in time (k_step_finish -> k_step_gen)
+  uint32_t* reset_count;  // [2]
   // "next episode" buffers, filled in the background by k_prefetch and swapped in by k_step_finish
   // when an env's episode ends (sp_state: 0 = empty / being built, 1 = ready)
-  uint8_t* sp_surface;    // [N][CP]
-  uint8_t* sp_attr;       // [N][CP]
-  uint8_t* sp_screen;     // [N][CP]
-  uint8_t* sp_hist;       // [N][HB]
-  uint32_t* sp_walk;      // [N][H][WW]
-  EnvState* sp_st;        // [N]
-  uint8_t* sp_state;      // [N]
+  uint8_t* sp_surface;    // [N][SP_DEPTH][CP]
+  uint8_t* sp_attr;       // [N][SP_DEPTH][CP]
+  uint8_t* sp_screen;     // [N][SP_DEPTH][CP]
+  uint8_t* sp_hist;       // [N][SP_DEPTH][HB]
+  uint32_t* sp_walk;      // [N][SP_DEPTH][H][WW]
+  EnvState* sp_st;        // [N][SP_DEPTH]  (slot of episode e = e % SP_DEPTH)
+  uint8_t* sp_state;      // [N][SP_DEPTH]
+  unsigned long long* trace;  // optional (RG_TRACE=1): [512 steps][8 kernels][2] first start / last end, globaltimer ns
+  int32_t trace_step;         // slot of a background pass (step kernels use *dstep)
+  uint32_t* dstep;            // [1] steps executed so far; its low bit selects the work-list buffers
   unsigned long long* stats;  // [8] RGS_* event counters since creation (observability)
   int32_t prefetch;       // 0 = off (every reset is generated synchronously by k_step_gen)
   uint32_t* mon_list;     // [N] envs with an active monster this step (player kernel -> monster kernel)

@@ -103,6 +103,7 @@ SYMBOLS = {
     "rg_sync": (_i, [_vp]),
     "rg_quiesce": (_i, [_vp]),
     "rg_stats": (_i, [_vp, _vp]),
+    "rg_trace": (_i, [_vp, _vp, _vp]),
     "rg_views_get": (_i, [_vp, C.POINTER(Views)]),
     "rg_fetch": (_i, [_vp, C.POINTER(HostObs)]),
     "rg_stream": (_vp, [_vp]),
