@@ -97,6 +97,8 @@ bool same_except_seed(rg_params a, rg_params b) {
   return memcmp(&a, &b, sizeof(a)) == 0;
 }
 
+int invalidate_prefetched(rg_batch* b);
+
 int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64_t n_envs, int64_t max_steps, int device,
                 rg_batch** out) {
   if (!out) return set_err(nullptr, RG_ERR_ARG, "rg_create: out is null");
@@ -149,7 +151,7 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
     cudaDeviceProp prop;
     RG_TRY(cudaGetDeviceProperties(&prop, device));
     d.gen_warps = prop.multiProcessorCount * 16;  // grid-stride warps of the full-path kernel
-    d.mon_warps = prop.multiProcessorCount * 32;  // grid-stride warps of the monster kernel
+    d.mon_warps = prop.multiProcessorCount * 16;  // grid-stride warps of the monster kernel
   }
   RG_TRY(dev_alloc(b, &b->dP, 1));
   RG_TRY(cudaMemcpy(b->dP, &P, sizeof(P), cudaMemcpyHostToDevice));
@@ -208,6 +210,11 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
       RG_TRY(dev_alloc(b, &d.sp_st, NS));
       RG_TRY(dev_alloc(b, &d.sp_state, NS));
       RG_TRY(cudaMemsetAsync(d.sp_state, 0, NS, b->stream));
+      uint32_t cap = 1;
+      while (cap < 4 * N) cap <<= 1;
+      d.refill_cap = cap;
+      RG_TRY(dev_alloc(b, &d.refill_ring, cap));
+      RG_TRY(dev_alloc(b, &d.refill_ctl, 4));
       int lo = 0, hi = 0;
       RG_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
       {
@@ -283,16 +290,26 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
   b->launches += 2;
   rc = rg_sync(b);
   if (rc != RG_OK) return fail(rc);
+  rc = invalidate_prefetched(b);
+  if (rc != RG_OK) return fail(rc);
 #undef RG_TRY
   *out = b;
   return RG_OK;
 }
 
-// The prefetched games were built for seeds / episode counters that are about to change.
+// Empties every env's ring of prefetched games and queues all envs for the background generator
+// (at creation, and whenever the seeds / episode counters the games were built for change).
 int invalidate_prefetched(rg_batch* b) {
   if (!b->d.prefetch) return RG_OK;
   RG_CUDA(b, cudaStreamSynchronize(b->bg));
-  RG_CUDA(b, cudaMemsetAsync(b->d.sp_state, 0, (size_t)b->n * rg::SP_DEPTH, b->stream));
+  const size_t N = (size_t)b->n;
+  RG_CUDA(b, cudaMemsetAsync(b->d.sp_state, 0, N * rg::SP_DEPTH, b->stream));
+  std::vector<uint32_t> ids(N);
+  for (size_t i = 0; i < N; ++i) ids[i] = (uint32_t)i;
+  const uint32_t ctl[4] = {(uint32_t)N, 0u, 0u, 0u};  // tail = N, served window empty
+  RG_CUDA(b, cudaMemcpyAsync(b->d.refill_ring, ids.data(), N * 4, cudaMemcpyHostToDevice, b->stream));
+  RG_CUDA(b, cudaMemcpyAsync(b->d.refill_ctl, ctl, sizeof(ctl), cudaMemcpyHostToDevice, b->stream));
+  RG_CUDA(b, cudaStreamSynchronize(b->stream));  // ids / ctl are stack memory
   return RG_OK;
 }
 
@@ -303,7 +320,7 @@ int kick_prefetch(rg_batch* b) {
   RG_CUDA(b, cudaStreamWaitEvent(b->bg, b->ev_main, 0));
   RG_CUDA(b, rg::launch_prefetch(b->d, b->prefetch_warps, b->bg));
   RG_CUDA(b, cudaEventRecord(b->ev_bg, b->bg));
-  b->launches += 1;
+  b->launches += 2;
   b->prefetch_running = true;
   return RG_OK;
 }
@@ -432,7 +449,7 @@ int rg_step(rg_batch* b, const uint8_t* actions_dev, int auto_reset) {
   } else {
     RG_CUDA(b, rg::launch_step(b->d, b->d_actions, auto_reset, b->stream, b->side, b->ev_fork, b->ev_join));
   }
-  b->launches += auto_reset ? 6 : 5;
+  b->launches += auto_reset ? 5 : 4;
   if (auto_reset && (b->auto_steps++ % b->prefetch_every) == 0)
     return kick_prefetch(b);  // refill the next-episode buffers consumed so far
   return RG_OK;

@@ -212,101 +212,20 @@ RG_DEV bool has_active_monster(const Ctx& c) {
 //
 //   k_step_player   every env: key -> action -> player move / attack / pickup / search, hunger, heal.
 //                   Descents and MoveUntil go to the full-path list; envs with an active monster
-//                   go to the monster list.
-//   k_step_monsters monster list only: coin flips, lazy-BFS chase, attacks.
-//   k_step_finish   every env: message / status / step count / terminal, compose, observation.
-//                   Terminal envs under auto_reset go to the full-path list.
-//   k_step_gen      full-path list only: the whole step compiled as one piece with the floor
-//                   generator (descents, MoveUntil), or the reset half of a terminal step.
+//                   go to the monster list; every other env is finished here (finish_env).
+//   k_step_monsters monster list only: coin flips, lazy-BFS chase, attacks, then finish_env.
+//   finish_env      message / status / step count / terminal, compose, observation; a terminal env
+//                   under auto_reset takes its prefetched next game or goes to the reset list.
+//   k_step_gen      full-path list (side stream, beside the monster kernel): the whole step compiled
+//                   as one piece with the floor generator; reset list: the reset half of a terminal step.
 //
 // The hand-over between the phases is EnvState::f_flags / f_msg / f_gold_before.
 // ---------------------------------------------------------------------------------------------
-RG_DEV void skip_env(const DevBatch& b, Ctx& c, int64_t env) {
-  if (c.lane == 0) b.st[env].f_flags = SF_SKIP;
-}
-
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_HOT_MIN_BLOCKS)
-k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset) {
-  unsigned char* const smem = rg_smem;
-  const int parity = (int)(*b.dstep & 1u);
-  TraceScope trace(b, TK_PLAYER);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {  // next step's counters
-    b.defer_count[parity ^ 1] = 0;
-    b.reset_count[parity ^ 1] = 0;
-    b.mon_count[parity ^ 1] = 0;
-  }
-  Ctx c;
-  const int warp = threadIdx.x >> 5;
-  const int64_t env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
-  if (env >= b.n) return;
-  unsigned char* const base = smem + (size_t)warp * warp_smem(b);
-  Stager sg = stager_init(b, base);
-  const uint8_t key = actions[env];
-  fill_ctx(b, c, sg, base, env, PL_BOTH);  // state and both planes in flight together (9 of 11 actions need them)
-  EnvState* st = c.st;
-  if (st->error == RG_ERR_PANIC || st->error == RG_ERR_SETTING) {  // the reference's worker is gone
-    emit_obs(b, c, env, 0, st->error);
-    skip_env(b, c, env);
-    return;
-  }
-  if ((int64_t)st->steps > b.max_steps) {  // state_impls.rs:52-54
-    emit_obs(b, c, env, 0, 0);
-    skip_env(b, c, env);
-    return;
-  }
-  int d;
-  const int act = map_key(key, d);
-  if (act < 0) {  // ErrorKind::InvalidInput: nothing changes (core/src/lib.rs:322-327)
-    emit_obs(b, c, env, 0, RG_ERR_INVALID_INPUT);
-    skip_env(b, c, env);
-    return;
-  }
-  if (st->ui_dead) {  // UiState::Mordal(Grave) + Act => IgnoredInput (core/src/lib.rs:314)
-    emit_obs(b, c, env, 0, RG_ERR_IGNORED_INPUT);
-    skip_env(b, c, env);
-    return;
-  }
-  if (act == 1 || (act == 3 && b.surface[env * b.CP + st->py * b.W + st->px] == S_STAIR)) {
-    defer(b, c, env, DEFER_STEP, parity);  // nothing has been touched: the whole step runs in k_step_gen
-    skip_env(b, c, env);
-    return;
-  }
-  st->f_gold_before = st->status[1];
-  if (act == 0 || act == 2) {
-    process_action<true>(c, act, d);
-  } else if (act == 3) {
-    process_action<true>(c, act, d);  // NoDownStair: a turn passes, the grid is not consulted
-  }
-  st->f_msg = c.msg;
-  st->f_flags = (uint8_t)((c.redraw ? SF_REDRAW : 0) | (c.status_upd ? SF_STATUS : 0) | (c.panic ? SF_PANIC : 0));
-  if (act != 4 && !c.panic && has_active_monster(c)) {
-    if (c.lane == 0) b.mon_list[atomicAdd(b.mon_count + parity, 1u)] = (uint32_t)env;
-    count_event(b, c, RGS_MONSTER_ENVS);
-  }
-  close_env(b, c, env);
-}
-
-// actions::move_active_enemies (actions.rs:82-119) for the envs that have an active monster
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_HOT_MIN_BLOCKS)
-k_step_monsters(DevBatch b) {
-  unsigned char* const smem = rg_smem;
-  const int parity = (int)(*b.dstep & 1u);
-  TraceScope trace(b, TK_MONSTERS);
-  const uint32_t count = b.mon_count[parity];
-  const int warp = threadIdx.x >> 5;
-  unsigned char* const base = smem + (size_t)warp * warp_smem(b);
-  Stager sg = stager_init(b, base);
-  for (uint32_t i = blockIdx.x * WARPS_PER_BLOCK + warp; i < count; i += gridDim.x * WARPS_PER_BLOCK) {
-    const int64_t env = (int64_t)b.mon_list[i];
-    Ctx c;
-    fill_ctx(b, c, sg, base, env, PL_S);
-    EnvState* st = c.st;
-    c.msg = st->f_msg;
-    if (move_active_enemies(c)) st->ui_dead = 1;
-    st->f_msg = c.msg;
-    st->f_flags |= (uint8_t)((c.status_upd ? SF_STATUS : 0) | (c.dead ? SF_DEAD : 0) | (c.panic ? SF_PANIC : 0));
-    store_state(b, c, env);
-    __syncwarp();
+// Tell the background generator that env's ring of prefetched games has a free slot.
+RG_DEV void request_refill(const DevBatch& b, const Ctx& c, int64_t env) {
+  if (b.prefetch && c.lane == 0) {
+    const uint32_t t = atomicAdd(b.refill_ctl, 1u);
+    b.refill_ring[t & (b.refill_cap - 1u)] = (uint32_t)env;
   }
 }
 
@@ -340,32 +259,22 @@ RG_DEV void swap_in_prefetched(const DevBatch& b, Ctx& c, int64_t env, int64_t s
   c.re.load(c.st->rng + 8);
 }
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_HOT_MIN_BLOCKS)
-k_step_finish(DevBatch b, int auto_reset) {
-  unsigned char* const smem = rg_smem;
-  const int parity = (int)(*b.dstep & 1u);
-  TraceScope trace(b, TK_FINISH);
-  Ctx c;
-  const int warp = threadIdx.x >> 5;
-  const int64_t env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
-  if (env >= b.n) return;
-  const uint8_t flags0 = b.st[env].f_flags;
-  if (flags0 & SF_SKIP) return;  // answered by the player kernel, or handed to k_step_gen
-  unsigned char* const base = smem + (size_t)warp * warp_smem(b);
-  Stager sg = stager_init(b, base);
-  fill_ctx(b, c, sg, base, env, (flags0 & SF_REDRAW) ? PL_BOTH : PL_NONE);
+// Last part of a step for an env whose state is staged in shared memory (python/src/state_impls.rs:
+// 56-77): message flags, displayed status, step count, terminal; under auto_reset the next episode
+// is moved in (prefetched) or requested (k_step_gen); compose if a Redraw was emitted; observation.
+// Runs at the end of k_step_player (envs without an active monster) or of k_step_monsters.
+RG_DEV void finish_env(const DevBatch& b, Ctx& c, int64_t env, int auto_reset, int parity) {
   EnvState* st = c.st;
-  const uint32_t flags = st->f_flags;
   const uint32_t gold_before = st->f_gold_before;
   uint8_t err = 0;
-  if (flags & SF_PANIC) {
+  if (c.panic) {
     st->error = RG_ERR_PANIC;
     err = RG_ERR_PANIC;
   } else {
-    st->message = st->f_msg;
-    if (flags & SF_STATUS) refresh_status(c);
+    st->message = c.msg;
+    if (c.status_upd) refresh_status(c);
     st->steps += 1;
-    st->is_terminal = ((flags & SF_DEAD) || (int64_t)st->steps >= b.max_steps) ? 1 : 0;
+    st->is_terminal = (c.dead || (int64_t)st->steps >= b.max_steps) ? 1 : 0;
     if (st->is_terminal && auto_reset) {
       // the game for episode e+1 lives in ring slot (e+1) % SP_DEPTH
       const int64_t sp = env * SP_DEPTH + (int64_t)((st->episode + 1) % SP_DEPTH);
@@ -392,19 +301,105 @@ k_step_finish(DevBatch b, int auto_reset) {
         __threadfence();
         __syncwarp();
         if (c.lane == 0) *reinterpret_cast<volatile uint8_t*>(b.sp_state + sp) = 0;
+        __threadfence();
+        request_refill(b, c, env);
         return;
       }
       // not ready (or prefetch off): the fresh game is built synchronously by k_step_gen
+      request_refill(b, c, env);
       if (c.lane == 0) b.reward[env] = (int32_t)gold_before;
       store_state(b, c, env);
       defer(b, c, env, DEFER_RESET, parity);
       return;
     }
-    if (flags & SF_REDRAW) compose(c);
+    if (c.redraw) compose(c);
   }
   const int32_t diff = (int32_t)st->status[1] - (int32_t)gold_before;
   emit_obs(b, c, env, diff > 0 ? diff : 0, err);
-  store_state(b, c, env);
+  close_env(b, c, env);
+}
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_HOT_MIN_BLOCKS)
+k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset) {
+  unsigned char* const smem = rg_smem;
+  const int parity = (int)(*b.dstep & 1u);
+  TraceScope trace(b, TK_PLAYER);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // next step's counters
+    b.defer_count[parity ^ 1] = 0;
+    b.reset_count[parity ^ 1] = 0;
+    b.mon_count[parity ^ 1] = 0;
+  }
+  Ctx c;
+  const int warp = threadIdx.x >> 5;
+  const int64_t env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
+  if (env >= b.n) return;
+  unsigned char* const base = smem + (size_t)warp * warp_smem(b);
+  Stager sg = stager_init(b, base);
+  const uint8_t key = actions[env];
+  fill_ctx(b, c, sg, base, env, PL_BOTH);  // state and both planes in flight together (9 of 11 actions need them)
+  EnvState* st = c.st;
+  if (st->error == RG_ERR_PANIC || st->error == RG_ERR_SETTING) {  // the reference's worker is gone
+    emit_obs(b, c, env, 0, st->error);
+    return;
+  }
+  if ((int64_t)st->steps > b.max_steps) {  // state_impls.rs:52-54
+    emit_obs(b, c, env, 0, 0);
+    return;
+  }
+  int d;
+  const int act = map_key(key, d);
+  if (act < 0) {  // ErrorKind::InvalidInput: nothing changes (core/src/lib.rs:322-327)
+    emit_obs(b, c, env, 0, RG_ERR_INVALID_INPUT);
+    return;
+  }
+  if (st->ui_dead) {  // UiState::Mordal(Grave) + Act => IgnoredInput (core/src/lib.rs:314)
+    emit_obs(b, c, env, 0, RG_ERR_IGNORED_INPUT);
+    return;
+  }
+  if (act == 1 || (act == 3 && b.surface[env * b.CP + st->py * b.W + st->px] == S_STAIR)) {
+    defer(b, c, env, DEFER_STEP, parity);  // nothing has been touched: the whole step runs in k_step_gen
+    return;
+  }
+  st->f_gold_before = st->status[1];
+  if (act == 0 || act == 2) {
+    process_action<true>(c, act, d);
+  } else if (act == 3) {
+    process_action<true>(c, act, d);  // NoDownStair: a turn passes, the grid is not consulted
+  }
+  if (act != 4 && !c.panic && has_active_monster(c)) {
+    // hand over to the monster kernel: it runs the monster phase and then finishes the step
+    st->f_msg = c.msg;
+    st->f_flags = (uint8_t)((c.redraw ? SF_REDRAW : 0) | (c.status_upd ? SF_STATUS : 0));
+    if (c.lane == 0) b.mon_list[atomicAdd(b.mon_count + parity, 1u)] = (uint32_t)env;
+    count_event(b, c, RGS_MONSTER_ENVS);
+    close_env(b, c, env);
+    return;
+  }
+  finish_env(b, c, env, auto_reset, parity);  // no monster moves this turn: the step ends here
+}
+
+// actions::move_active_enemies (actions.rs:82-119) for the envs that have an active monster
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 16)
+k_step_monsters(DevBatch b, int auto_reset) {
+  unsigned char* const smem = rg_smem;
+  const int parity = (int)(*b.dstep & 1u);
+  TraceScope trace(b, TK_MONSTERS);
+  const uint32_t count = b.mon_count[parity];
+  const int warp = threadIdx.x >> 5;
+  unsigned char* const base = smem + (size_t)warp * warp_smem(b);
+  Stager sg = stager_init(b, base);
+  for (uint32_t i = blockIdx.x * WARPS_PER_BLOCK + warp; i < count; i += gridDim.x * WARPS_PER_BLOCK) {
+    const int64_t env = (int64_t)b.mon_list[i];
+    Ctx c;
+    fill_ctx(b, c, sg, base, env, PL_BOTH);  // surface for the moves, both planes if the step ends with a compose
+    EnvState* st = c.st;
+    c.msg = st->f_msg;
+    c.redraw = (st->f_flags & SF_REDRAW) ? 1u : 0u;
+    c.status_upd = (st->f_flags & SF_STATUS) ? 1u : 0u;
+    if (move_active_enemies(c)) st->ui_dead = 1;
+    finish_env(b, c, env, auto_reset, parity);
+    __syncwarp();
+  }
 }
 
 // The whole step as one piece (with the floor generator), for the envs on the full-path list:
@@ -412,7 +407,7 @@ k_step_finish(DevBatch b, int auto_reset) {
 RG_DEV void step_env_full(const DevBatch& b, Ctx& c, int64_t env, const uint8_t* __restrict__ actions, int auto_reset,
                           bool reset_only) {
   EnvState* st = c.st;
-  if (reset_only) {  // second half of a terminal step: k_step_finish left gold_before in reward[]
+  if (reset_only) {  // second half of a terminal step: finish_env left gold_before in reward[]
     const uint32_t gold_before = (uint32_t)b.reward[env];
     reset_env(c);
     uint8_t err = 0;
@@ -485,7 +480,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_step_gen(DevBatch b, c
 // Background generation of every env's NEXT episode (GameConfig::build for the seed its next reset
 // will use - fixed, or already derived for `seed: null` - core/src/lib.rs:157-165,193-228). Runs on
 // a second, low-priority stream concurrently with the step kernels, so the ~1000 dependent RNG
-// draws of a floor are off the step's critical path; k_step_finish moves the finished game in
+// draws of a floor are off the step's critical path; finish_env moves the finished game in
 // when the episode ends. Ownership of a buffer is handed over through sp_state (0: this kernel
 // may write it, 1: the step kernels may read it), with a fence on each side.
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_prefetch(DevBatch b) {
@@ -494,8 +489,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_prefetch(DevBatch b) {
   const int warp = threadIdx.x >> 5;
   unsigned char* const base = smem + (size_t)warp * warp_smem(b);
   Stager sg = stager_init(b, base);
-  for (int64_t env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp; env < b.n;
-       env += (int64_t)gridDim.x * WARPS_PER_BLOCK) {
+  const uint32_t begin = b.refill_ctl[1], end = b.refill_ctl[2];
+  for (uint32_t it = begin + blockIdx.x * WARPS_PER_BLOCK + warp; (int32_t)(end - it) > 0;
+       it += gridDim.x * WARPS_PER_BLOCK) {
+    const int64_t env = (int64_t)b.refill_ring[it & (b.refill_cap - 1u)];
     bool all_ready = true;
     for (int k = 0; k < SP_DEPTH; ++k)
       all_ready = all_ready && *reinterpret_cast<volatile uint8_t*>(b.sp_state + env * SP_DEPTH + k) != 0;
@@ -535,6 +532,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_prefetch(DevBatch b) {
       count_event(b, c, RGS_PREFETCH_BUILT);
       __syncwarp();
     }
+  }
+}
+
+// Fixes the window of refill requests the next k_prefetch pass serves: [previous end, current tail).
+__global__ void k_prefetch_plan(DevBatch b) {
+  if (threadIdx.x == 0) {
+    b.refill_ctl[1] = b.refill_ctl[2];
+    b.refill_ctl[2] = *reinterpret_cast<volatile uint32_t*>(b.refill_ctl);
   }
 }
 
@@ -744,8 +749,6 @@ cudaError_t configure_kernels(const DevBatch& b) {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_step_monsters, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_step_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_step_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_prefetch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -781,9 +784,7 @@ cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_rese
   if ((e = cudaEventRecord(ev_join, side)) != cudaSuccess) return e;
   int mon_blocks = b.mon_warps / WARPS_PER_BLOCK;
   if (mon_blocks > blocks) mon_blocks = blocks;
-  k_step_monsters<<<mon_blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b);
-  if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  k_step_finish<<<blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, auto_reset);
+  k_step_monsters<<<mon_blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, auto_reset);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (auto_reset) {  // episode ends whose next game was not prefetched in time (normally none)
     k_step_gen<<<gen_blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, actions, auto_reset, 1);
@@ -797,6 +798,9 @@ cudaError_t launch_prefetch(const DevBatch& b, int warps, cudaStream_t s) {
   const int64_t blocks_all = (b.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
   int blocks = (warps > 0 ? warps : b.gen_warps) / WARPS_PER_BLOCK;
   if (blocks > blocks_all) blocks = (int)blocks_all;
+  k_prefetch_plan<<<1, 32, 0, s>>>(b);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
   k_prefetch<<<blocks, WARPS_PER_BLOCK * 32, block_smem(b), s>>>(b);
   return cudaGetLastError();
 }

@@ -128,6 +128,9 @@ struct DevBatch {
   int32_t trace_step;         // slot of a background pass (step kernels use *dstep)
   uint32_t* dstep;            // [1] steps executed so far; its low bit selects the work-list buffers
   unsigned long long* stats;  // [8] RGS_* event counters since creation (observability)
+  uint32_t* refill_ring;  // [refill_cap] env ids whose prefetch ring has a free slot (producers: finish_env)
+  uint32_t* refill_ctl;   // [0] tail (producers), [1] begin, [2] end of the pass being executed (k_prefetch_plan)
+  uint32_t refill_cap;    // power of two
   int32_t prefetch;       // 0 = off (every reset is generated synchronously by k_step_gen)
   uint32_t* mon_list;     // [N] envs with an active monster this step (player kernel -> monster kernel)
   uint32_t* mon_count;    // [2] ping-pong by step parity
