@@ -190,7 +190,7 @@ int rg_quiesce(rg_batch* b);
 int rg_stats(rg_batch* b, uint64_t* out8);
 /* Timeline of the last 512 steps (only when the batch was created with RG_TRACE=1 in the environment):
  * out[512][8][2] = first start / last end (globaltimer ns) of kernel k of step slot s; k = 0 player,
- * 1 monsters, 2 finish, 3 full-path, 4 synchronous resets, 5 background prefetch. */
+ * 1 monsters, 2 finish, 3 full-path, 4 synchronous resets, 5 background prefetch. Reading clears the slots. */
 int rg_trace(rg_batch* b, uint64_t* out, int64_t* steps_launched);
 int rg_sync(rg_batch* b);          /* waits for the stream and raises per-env errors like the reference */
 int rg_views_get(rg_batch* b, rg_views* out);

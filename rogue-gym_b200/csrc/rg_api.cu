@@ -194,6 +194,8 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
   RG_TRY(dev_alloc(b, &d.errflag, 1));
   RG_TRY(dev_alloc(b, &d.defer_list, N));
   RG_TRY(dev_alloc(b, &d.defer_count, 4));
+  RG_TRY(dev_alloc(b, &d.full_path, N));
+  RG_TRY(cudaMemsetAsync(d.full_path, 0, N, b->stream));
   RG_TRY(cudaMemsetAsync(d.defer_count, 0, 16, b->stream));
   {  // next-episode buffers + background stream (RG_PREFETCH=0 turns the pipeline off)
     const char* pf = getenv("RG_PREFETCH");
@@ -239,7 +241,11 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
   RG_TRY(dev_alloc(b, &d.reset_list, N));
   RG_TRY(dev_alloc(b, &d.reset_count, 4));
   RG_TRY(cudaMemsetAsync(d.reset_count, 0, 16, b->stream));
-  RG_TRY(cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking));
+  {  // the full-path kernel's few long chains must not queue behind the player kernel's 65 536 blocks
+    int lo = 0, hi = 0;
+    RG_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    RG_TRY(cudaStreamCreateWithPriority(&b->side, cudaStreamNonBlocking, hi));
+  }
   RG_TRY(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
   RG_TRY(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
   RG_TRY(dev_alloc(b, &d.mon_list, N));
@@ -449,7 +455,7 @@ int rg_step(rg_batch* b, const uint8_t* actions_dev, int auto_reset) {
   } else {
     RG_CUDA(b, rg::launch_step(b->d, b->d_actions, auto_reset, b->stream, b->side, b->ev_fork, b->ev_join));
   }
-  b->launches += auto_reset ? 5 : 4;
+  b->launches += auto_reset ? 6 : 5;
   if (auto_reset && (b->auto_steps++ % b->prefetch_every) == 0)
     return kick_prefetch(b);  // refill the next-episode buffers consumed so far
   return RG_OK;
@@ -471,6 +477,11 @@ int rg_trace(rg_batch* b, uint64_t* out, int64_t* steps_launched) {
   RG_CUDA(b, cudaStreamSynchronize(b->stream));
   if (b->bg) RG_CUDA(b, cudaStreamSynchronize(b->bg));
   RG_CUDA(b, cudaMemcpy(out, b->d.trace, 512 * 8 * 2 * 8, cudaMemcpyDeviceToHost));
+  {  // read-and-clear: the slots are min/max accumulators and wrap every 512 steps
+    std::vector<unsigned long long> init(512 * 8 * 2);
+    for (size_t i = 0; i < init.size(); ++i) init[i] = (i & 1) ? 0ull : ~0ull;
+    RG_CUDA(b, cudaMemcpy(b->d.trace, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
+  }
   if (steps_launched) *steps_launched = b->steps_launched;
   return RG_OK;
 }

@@ -210,14 +210,18 @@ RG_DEV bool has_active_monster(const Ctx& c) {
 // resident in the instruction caches (the single-kernel version spent most of its stall samples
 // on instruction fetch: 17-30 k SASS instructions executed divergently by independent warps):
 //
-//   k_step_player   every env: key -> action -> player move / attack / pickup / search, hunger, heal.
-//                   Descents and MoveUntil go to the full-path list; envs with an active monster
-//                   go to the monster list; every other env is finished here (finish_env).
+//   k_step_scan     one thread per env, looks at the key (and, for '>' / capitals, at the position):
+//                   descents and MoveUntil go to the full-path list and are flagged in full_path[].
+//   k_step_gen      full-path list, high-priority side stream, beside the two kernels below: the whole
+//                   step compiled as one piece with the floor generator. A second, normally empty pass
+//                   after the monster kernel does the reset half of terminal steps that found no
+//                   prefetched game.
+//   k_step_player   every other env: key -> action -> player move / attack / pickup / search, hunger,
+//                   heal. Envs with an active monster go to the monster list; every other env is
+//                   finished here (finish_env).
 //   k_step_monsters monster list only: coin flips, lazy-BFS chase, attacks, then finish_env.
 //   finish_env      message / status / step count / terminal, compose, observation; a terminal env
 //                   under auto_reset takes its prefetched next game or goes to the reset list.
-//   k_step_gen      full-path list (side stream, beside the monster kernel): the whole step compiled
-//                   as one piece with the floor generator; reset list: the reset half of a terminal step.
 //
 // The hand-over between the phases is EnvState::f_flags / f_msg / f_gold_before.
 // ---------------------------------------------------------------------------------------------
@@ -319,22 +323,50 @@ RG_DEV void finish_env(const DevBatch& b, Ctx& c, int64_t env, int auto_reset, i
   close_env(b, c, env);
 }
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_HOT_MIN_BLOCKS)
-k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset) {
-  unsigned char* const smem = rg_smem;
+// True when this key takes the env down the full path (k_step_gen): MoveUntil, or DownStair while
+// standing on a stair. Evaluated on the state the step starts from, after the same early-outs the
+// player kernel applies (state_impls.rs:52-54, core/src/lib.rs:314,322-327).
+RG_DEV bool takes_full_path(const DevBatch& b, const EnvState* st, int64_t env, int act) {
+  if (act != 1 && act != 3) return false;
+  if (st->error == RG_ERR_PANIC || st->error == RG_ERR_SETTING) return false;
+  if ((int64_t)st->steps > b.max_steps || st->ui_dead) return false;
+  return act == 1 || b.surface[env * b.CP + st->py * b.W + st->px] == S_STAIR;
+}
+
+// First kernel of a step: one thread per env looks at the key only and, for the few keys that can
+// lead to the full path, at the env's position. The full-path list is therefore complete before the
+// player kernel starts, and k_step_gen (a handful of ~150 us serial chains: a descent builds a floor)
+// runs beside the player and monster kernels instead of after them.
+__global__ void __launch_bounds__(256) k_step_scan(DevBatch b, const uint8_t* __restrict__ actions) {
   const int parity = (int)(*b.dstep & 1u);
-  TraceScope trace(b, TK_PLAYER);
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // next step's counters
     b.defer_count[parity ^ 1] = 0;
     b.reset_count[parity ^ 1] = 0;
     b.mon_count[parity ^ 1] = 0;
   }
+  const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= b.n) return;
+  int d;
+  const int act = map_key(actions[env], d);
+  const bool full = takes_full_path(b, b.st + env, env, act);
+  b.full_path[env] = full ? 1 : 0;  // the player kernel must not look at the env itself: k_step_gen is changing it
+  if (!full) return;
+  atomicAdd(b.stats + RGS_FULL_STEP, 1ull);
+  b.defer_list[atomicAdd(b.defer_count + parity, 1u)] = (uint32_t)env;
+}
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_HOT_MIN_BLOCKS)
+k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset) {
+  unsigned char* const smem = rg_smem;
+  const int parity = (int)(*b.dstep & 1u);
+  TraceScope trace(b, TK_PLAYER);
   Ctx c;
   const int warp = threadIdx.x >> 5;
   const int64_t env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
   if (env >= b.n) return;
   unsigned char* const base = smem + (size_t)warp * warp_smem(b);
   Stager sg = stager_init(b, base);
+  if (b.full_path[env]) return;  // on k_step_scan's list: the whole step runs in k_step_gen, concurrently
   const uint8_t key = actions[env];
   fill_ctx(b, c, sg, base, env, PL_BOTH);  // state and both planes in flight together (9 of 11 actions need them)
   EnvState* st = c.st;
@@ -354,10 +386,6 @@ k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset) {
   }
   if (st->ui_dead) {  // UiState::Mordal(Grave) + Act => IgnoredInput (core/src/lib.rs:314)
     emit_obs(b, c, env, 0, RG_ERR_IGNORED_INPUT);
-    return;
-  }
-  if (act == 1 || (act == 3 && b.surface[env * b.CP + st->py * b.W + st->px] == S_STAIR)) {
-    defer(b, c, env, DEFER_STEP, parity);  // nothing has been touched: the whole step runs in k_step_gen
     return;
   }
   st->f_gold_before = st->status[1];
@@ -762,8 +790,8 @@ cudaError_t launch_reset(const DevBatch& b, cudaStream_t s) {
   k_reset<<<blocks, WARPS_PER_BLOCK * 32, block_smem(b), s>>>(b);
   return cudaGetLastError();
 }
-// Enqueues one env-step: player kernel, then the full-path kernel on `side` beside the monster and
-// finish kernels, the synchronous-reset pass, the join, and the step counter. No per-step
+// Enqueues one env-step: key scan, the full-path kernel on `side` beside the player and monster
+// kernels, the synchronous-reset pass, the join, and the step counter. No per-step
 // arguments (the step parity lives on the device, the actions are read from a fixed buffer), so
 // the whole sequence is captured once into a CUDA graph and replayed with one launch per step.
 cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_reset, cudaStream_t s, cudaStream_t side,
@@ -773,15 +801,17 @@ cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_rese
   int gen_blocks = b.gen_warps / WARPS_PER_BLOCK;
   if (gen_blocks > blocks) gen_blocks = blocks;
   cudaError_t e;
-  k_step_player<<<blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, actions, auto_reset);
+  k_step_scan<<<(unsigned)((b.n + 255) / 256), 256, 0, s>>>(b, actions);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  // full-path steps (descents, MoveUntil) are a few long serial chains: run them beside the
-  // monster and finish kernels instead of after them
+  // full-path steps (descents, MoveUntil) are a few long serial chains: they start first, on the
+  // high-priority side stream, and run beside the player and monster kernels
   if ((e = cudaEventRecord(ev_fork, s)) != cudaSuccess) return e;
   if ((e = cudaStreamWaitEvent(side, ev_fork, 0)) != cudaSuccess) return e;
   k_step_gen<<<gen_blocks, WARPS_PER_BLOCK * 32, sm, side>>>(b, actions, auto_reset, 0);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if ((e = cudaEventRecord(ev_join, side)) != cudaSuccess) return e;
+  k_step_player<<<blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, actions, auto_reset);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
   int mon_blocks = b.mon_warps / WARPS_PER_BLOCK;
   if (mon_blocks > blocks) mon_blocks = blocks;
   k_step_monsters<<<mon_blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, auto_reset);

@@ -113,6 +113,7 @@ struct DevBatch {
   uint32_t* errflag;  // OR of all errors raised since the last rg_sync
   uint32_t* defer_list;   // [N] env id | DEFER_* : work handed to the full-path kernel k_step_gen
   uint32_t* defer_count;  // [2] ping-pong by step parity
+  uint8_t* full_path;     // [N] 1 = this step of the env runs in k_step_gen (written by k_step_scan every step)
   uint32_t* reset_list;   // [N] terminal envs whose next game was not prefetched in time (k_step_finish -> k_step_gen)
   uint32_t* reset_count;  // [2]
   // "next episode" buffers, filled in the background by k_prefetch and swapped in by k_step_finish

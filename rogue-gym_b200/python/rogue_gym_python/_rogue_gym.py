@@ -304,6 +304,23 @@ class ParallelGameState:
     def close(self):
         self._batch.close()
 
+    def encode_states(self, states, mode, flag, with_hist):
+        """float32 [len(states), C, H, W]: the images `PlayerState.{gray,symbol}_image[_with_hist]` give
+        one by one (python/src/lib.rs:158-205), produced by one device launch for the whole list."""
+        b = self._batch
+        b._alive()
+        n = len(states)
+        ch = b.L.rg_encode_channels(b.h, mode, int(flag), int(with_hist))
+        out = np.empty((n, ch, b.H, b.W), np.float32)
+        if n == 0:
+            return out
+        scr = np.ascontiguousarray(np.stack([s._screen for s in states]))
+        hist = np.ascontiguousarray(np.stack([s._history for s in states]))
+        st = np.ascontiguousarray(np.stack([s._status for s in states]))
+        check(b.L.rg_encode_states(b.h, n, scr.ctypes.data, hist.ctypes.data, st.ctypes.data, mode, int(flag),
+                                   int(with_hist), out.ctypes.data, None), b.h)
+        return out
+
     # ---- batched surface (not in the reference): arrays instead of per-env objects
     def step_arrays(self, keys):
         """keys: uint8[N] ASCII. Returns a dict of numpy views refreshed in place each call."""
