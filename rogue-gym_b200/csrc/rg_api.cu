@@ -27,11 +27,12 @@ struct rg_batch {
   int64_t max_steps = 0;
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaStream_t bg = nullptr;      // background stream: k_prefetch
+  cudaStream_t bg[2] = {nullptr, nullptr};  // background streams: k_prefetch passes alternate, so two can be in flight
   cudaStream_t side = nullptr;    // full-path steps, forked after the player kernel and joined at the end of the step
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_main = nullptr;  // "this step's kernels are queued up to here"
-  cudaEvent_t ev_bg = nullptr;    // last k_prefetch
+  cudaEvent_t ev_bg[2] = {nullptr, nullptr};  // end of the last pass on each background stream
+  int64_t passes = 0;             // background passes kicked so far
   bool prefetch_running = false;
   int prefetch_every = 1;   // kick the background pass every k-th auto-reset step
   int prefetch_warps = 0;   // grid-stride warps of k_prefetch (0 = as many as the full-path kernel)
@@ -219,12 +220,22 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
       RG_TRY(dev_alloc(b, &d.refill_ctl, 4));
       int lo = 0, hi = 0;
       RG_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      RG_TRY(dev_alloc(b, &d.refill_win, 16));
+      RG_TRY(cudaMemsetAsync(d.refill_win, 0, 64, b->stream));
+      RG_TRY(dev_alloc(b, &d.sp_lock, N));
+      RG_TRY(dev_alloc(b, &d.sp_cancel, NS));
+      d.prefetch_every = b->prefetch_every;
+      if (const char* e = getenv("RG_PF_WPB")) d.pf_wpb = std::max(1, atoi(e));
       {
+        // a pass is a few hundred one-warp chains: at high priority it starts at once and costs the
+        // step kernels next to nothing; at low priority it only runs in their gaps and falls behind
         const char* pr = getenv("RG_BG_PRIO");
-        RG_TRY(cudaStreamCreateWithPriority(&b->bg, cudaStreamNonBlocking, (pr && pr[0] == 'h') ? hi : lo));
+        for (int i = 0; i < 2; ++i) {
+          RG_TRY(cudaStreamCreateWithPriority(&b->bg[i], cudaStreamNonBlocking, (pr && pr[0] == 'l') ? lo : hi));
+          RG_TRY(cudaEventCreateWithFlags(&b->ev_bg[i], cudaEventDisableTiming));
+        }
       }
       RG_TRY(cudaEventCreateWithFlags(&b->ev_main, cudaEventDisableTiming));
-      RG_TRY(cudaEventCreateWithFlags(&b->ev_bg, cudaEventDisableTiming));
     }
   }
   if (const char* tr = getenv("RG_TRACE"); tr && tr[0] == '1') {
@@ -307,9 +318,11 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
 // (at creation, and whenever the seeds / episode counters the games were built for change).
 int invalidate_prefetched(rg_batch* b) {
   if (!b->d.prefetch) return RG_OK;
-  RG_CUDA(b, cudaStreamSynchronize(b->bg));
+  for (int i = 0; i < 2; ++i) RG_CUDA(b, cudaStreamSynchronize(b->bg[i]));
   const size_t N = (size_t)b->n;
   RG_CUDA(b, cudaMemsetAsync(b->d.sp_state, 0, N * rg::SP_DEPTH, b->stream));
+  RG_CUDA(b, cudaMemsetAsync(b->d.sp_lock, 0, N * 4, b->stream));
+  RG_CUDA(b, cudaMemsetAsync(b->d.sp_cancel, 0, N * rg::SP_DEPTH * 4, b->stream));
   std::vector<uint32_t> ids(N);
   for (size_t i = 0; i < N; ++i) ids[i] = (uint32_t)i;
   const uint32_t ctl[4] = {(uint32_t)N, 0u, 0u, 0u};  // tail = N, served window empty
@@ -319,14 +332,20 @@ int invalidate_prefetched(rg_batch* b) {
   return RG_OK;
 }
 
-// Queue one background pass after everything queued on the main stream so far.
+// Queue background pass k (window slot k % 8, fixed by k_step_end of the step just queued) after
+// everything queued on the main stream so far. Passes alternate between two streams so that a pass
+// that is still building does not delay the next one; the main stream waits for pass k-2 before it
+// goes on, which bounds the time from a refill request to a ready game to about two steps.
 int kick_prefetch(rg_batch* b) {
   if (!b->d.prefetch) return RG_OK;
+  const int64_t k = b->passes++;
+  const int i = (int)(k & 1);
   RG_CUDA(b, cudaEventRecord(b->ev_main, b->stream));
-  RG_CUDA(b, cudaStreamWaitEvent(b->bg, b->ev_main, 0));
-  RG_CUDA(b, rg::launch_prefetch(b->d, b->prefetch_warps, b->bg));
-  RG_CUDA(b, cudaEventRecord(b->ev_bg, b->bg));
-  b->launches += 2;
+  RG_CUDA(b, cudaStreamWaitEvent(b->bg[i], b->ev_main, 0));
+  RG_CUDA(b, rg::launch_prefetch(b->d, b->prefetch_warps, (int)(k % 8), b->bg[i]));
+  if (k >= 2) RG_CUDA(b, cudaStreamWaitEvent(b->stream, b->ev_bg[i], 0));  // pass k-2 (same stream, already queued before pass k)
+  RG_CUDA(b, cudaEventRecord(b->ev_bg[i], b->bg[i]));
+  b->launches += 1;
   b->prefetch_running = true;
   return RG_OK;
 }
@@ -388,7 +407,8 @@ void rg_destroy(rg_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
-  if (b->bg) cudaStreamSynchronize(b->bg);
+  for (int i = 0; i < 2; ++i)
+    if (b->bg[i]) cudaStreamSynchronize(b->bg[i]);
   if (b->side) cudaStreamSynchronize(b->side);
   for (int i = 0; i < 2; ++i)
     if (b->graph[i]) cudaGraphExecDestroy(b->graph[i]);
@@ -396,8 +416,10 @@ void rg_destroy(rg_batch* b) {
   if (b->ev_join) cudaEventDestroy(b->ev_join);
   if (b->side) cudaStreamDestroy(b->side);
   if (b->ev_main) cudaEventDestroy(b->ev_main);
-  if (b->ev_bg) cudaEventDestroy(b->ev_bg);
-  if (b->bg) cudaStreamDestroy(b->bg);
+  for (int i = 0; i < 2; ++i) {
+    if (b->ev_bg[i]) cudaEventDestroy(b->ev_bg[i]);
+    if (b->bg[i]) cudaStreamDestroy(b->bg[i]);
+  }
   for (void* p : b->dev_allocs) cudaFree(p);
   if (b->h_errflag) cudaFreeHost(b->h_errflag);
   if (b->h_error) cudaFreeHost(b->h_error);
@@ -465,7 +487,8 @@ int rg_stats(rg_batch* b, uint64_t* out8) {
   if (!b || !out8) return set_err(b, RG_ERR_ARG, "rg_stats: null argument");
   RG_CUDA(b, cudaSetDevice(b->device));
   RG_CUDA(b, cudaStreamSynchronize(b->stream));
-  if (b->bg) RG_CUDA(b, cudaStreamSynchronize(b->bg));
+  for (int i = 0; i < 2; ++i)
+    if (b->bg[i]) RG_CUDA(b, cudaStreamSynchronize(b->bg[i]));
   RG_CUDA(b, cudaMemcpy(out8, b->d.stats, 64, cudaMemcpyDeviceToHost));
   return RG_OK;
 }
@@ -475,7 +498,8 @@ int rg_trace(rg_batch* b, uint64_t* out, int64_t* steps_launched) {
   if (!b->d.trace) return set_err(b, RG_ERR_ARG, "rg_trace: tracing is off (set RG_TRACE=1 before creating the batch)");
   RG_CUDA(b, cudaSetDevice(b->device));
   RG_CUDA(b, cudaStreamSynchronize(b->stream));
-  if (b->bg) RG_CUDA(b, cudaStreamSynchronize(b->bg));
+  for (int i = 0; i < 2; ++i)
+    if (b->bg[i]) RG_CUDA(b, cudaStreamSynchronize(b->bg[i]));
   RG_CUDA(b, cudaMemcpy(out, b->d.trace, 512 * 8 * 2 * 8, cudaMemcpyDeviceToHost));
   {  // read-and-clear: the slots are min/max accumulators and wrap every 512 steps
     std::vector<unsigned long long> init(512 * 8 * 2);
@@ -488,7 +512,8 @@ int rg_trace(rg_batch* b, uint64_t* out, int64_t* steps_launched) {
 
 int rg_quiesce(rg_batch* b) {
   if (!b) return set_err(b, RG_ERR_ARG, "rg_quiesce: null batch");
-  if (b->d.prefetch && b->prefetch_running) RG_CUDA(b, cudaStreamWaitEvent(b->stream, b->ev_bg, 0));
+  if (b->d.prefetch && b->prefetch_running)
+    for (int i = 0; i < 2; ++i) RG_CUDA(b, cudaStreamWaitEvent(b->stream, b->ev_bg[i], 0));
   return RG_OK;
 }
 

@@ -1,6 +1,8 @@
 // rg_kernels.cu — __global__ entry points (warp per env) and their launchers.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "rg_device.cuh"
 #include "rg_launch.h"
 
@@ -16,6 +18,17 @@ namespace rg {
 // done, so a warp that runs a BFS does not pin three finished neighbours (measured: 4 warps/block
 // 0.668 ms per step, 1 warp/block 0.626 ms at 64 registers, 65 536 envs).
 constexpr int WARPS_PER_BLOCK = RG_WPB;
+// The generator kernels are the opposite case: ~15 k instructions of divergent code run by a few
+// hundred warps beside the step kernels. Spread one warp per SM they evict the step kernels' code from
+// every SM's instruction caches (measured: the player kernel takes 216 us instead of 140 us while a
+// background pass runs); packed into a few many-warp blocks they disturb only the SMs they sit on.
+// k_prefetch takes its warps per block from the launch (DevBatch::pf_wpb, at most PF_MAX_WPB and as many
+// as fit in shared memory). The full-path kernel handles ~10 envs per step: one warp per block, spread.
+constexpr int PF_MAX_WPB = 16;
+#ifndef RG_GEN_WPB
+#define RG_GEN_WPB 1
+#endif
+constexpr int GEN_WPB = RG_GEN_WPB;  // k_step_gen (218 registers)
 RG_DEV size_t warp_smem(const DevBatch& b) { return 2 * (size_t)b.CP + sizeof(EnvState) + 16; }
 
 // ---- staging through shared memory with the bulk-copy engine (TMA, 1-D): one elected lane
@@ -309,7 +322,9 @@ RG_DEV void finish_env(const DevBatch& b, Ctx& c, int64_t env, int auto_reset, i
         request_refill(b, c, env);
         return;
       }
-      // not ready (or prefetch off): the fresh game is built synchronously by k_step_gen
+      // not ready (or prefetch off): the fresh game is built synchronously by k_step_gen; a background
+      // build of the same episode that is still under way must not be published afterwards
+      if (b.prefetch && c.lane == 0) *reinterpret_cast<volatile uint32_t*>(b.sp_cancel + sp) = st->episode + 1;
       request_refill(b, c, env);
       if (c.lane == 0) b.reward[env] = (int32_t)gold_before;
       store_state(b, c, env);
@@ -343,6 +358,7 @@ __global__ void __launch_bounds__(256) k_step_scan(DevBatch b, const uint8_t* __
     b.defer_count[parity ^ 1] = 0;
     b.reset_count[parity ^ 1] = 0;
     b.mon_count[parity ^ 1] = 0;
+    b.mon_count[2 + (parity ^ 1)] = 0;  // the monster kernel's work cursor
   }
   const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= b.n) return;
@@ -416,7 +432,13 @@ k_step_monsters(DevBatch b, int auto_reset) {
   const int warp = threadIdx.x >> 5;
   unsigned char* const base = smem + (size_t)warp * warp_smem(b);
   Stager sg = stager_init(b, base);
-  for (uint32_t i = blockIdx.x * WARPS_PER_BLOCK + warp; i < count; i += gridDim.x * WARPS_PER_BLOCK) {
+  // envs are handed out one at a time: their cost varies by an order of magnitude (a BFS or not),
+  // and warps on SMs that also host a background generator block run slower
+  for (;;) {
+    uint32_t i = 0;
+    if ((threadIdx.x & 31) == 0) i = atomicAdd(b.mon_count + 2 + parity, 1u);
+    i = __shfl_sync(RG_FULL, i, 0);
+    if (i >= count) break;
     const int64_t env = (int64_t)b.mon_list[i];
     Ctx c;
     fill_ctx(b, c, sg, base, env, PL_BOTH);  // surface for the moves, both planes if the step ends with a compose
@@ -480,12 +502,21 @@ RG_DEV void step_env_full(const DevBatch& b, Ctx& c, int64_t env, const uint8_t*
   close_env(b, c, env);
 }
 
-__global__ void k_step_end(DevBatch b) {
-  if (threadIdx.x == 0) *b.dstep += 1u;
+// Last kernel of a step: advances the step counter and, on the steps that kick a background pass,
+// fixes the window of refill requests that pass serves: [end of the previous window, current tail).
+__global__ void k_step_end(DevBatch b, int auto_reset) {
+  if (threadIdx.x != 0) return;
+  b.dstep[0] += 1u;
+  if (!auto_reset || !b.prefetch) return;
+  const uint32_t k = b.dstep[1]++;
+  if (k % (uint32_t)b.prefetch_every) return;
+  uint32_t* win = b.refill_win + 2 * ((k / (uint32_t)b.prefetch_every) % 8u);
+  win[0] = b.refill_ctl[2];
+  win[1] = b.refill_ctl[2] = *reinterpret_cast<volatile uint32_t*>(b.refill_ctl);
 }
 
 // Grid-stride over the full-path list; exits at once when the list is empty.
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_step_gen(DevBatch b, const uint8_t* __restrict__ actions,
+__global__ void __launch_bounds__(GEN_WPB * 32) k_step_gen(DevBatch b, const uint8_t* __restrict__ actions,
                                                                   int auto_reset, int resets) {
   unsigned char* const smem = rg_smem;
   const int parity = (int)(*b.dstep & 1u);
@@ -495,7 +526,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_step_gen(DevBatch b, c
   const int warp = threadIdx.x >> 5;
   unsigned char* const base = smem + (size_t)warp * warp_smem(b);
   Stager sg = stager_init(b, base);
-  for (uint32_t i = blockIdx.x * WARPS_PER_BLOCK + warp; i < count; i += gridDim.x * WARPS_PER_BLOCK) {
+  for (uint32_t i = blockIdx.x * GEN_WPB + warp; i < count; i += gridDim.x * GEN_WPB) {
     const uint32_t item = work[i];
     const int64_t env = (int64_t)(item & 0x7FFFFFFFu);
     Ctx c;
@@ -511,20 +542,29 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_step_gen(DevBatch b, c
 // draws of a floor are off the step's critical path; finish_env moves the finished game in
 // when the episode ends. Ownership of a buffer is handed over through sp_state (0: this kernel
 // may write it, 1: the step kernels may read it), with a fence on each side.
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_prefetch(DevBatch b) {
+__global__ void __launch_bounds__(PF_MAX_WPB * 32, 1) k_prefetch(DevBatch b, int slot) {
+  const uint32_t PF_WPB = blockDim.x >> 5;
   unsigned char* const smem = rg_smem;
   TraceScope trace(b, TK_PREFETCH);
   const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   unsigned char* const base = smem + (size_t)warp * warp_smem(b);
   Stager sg = stager_init(b, base);
-  const uint32_t begin = b.refill_ctl[1], end = b.refill_ctl[2];
-  for (uint32_t it = begin + blockIdx.x * WARPS_PER_BLOCK + warp; (int32_t)(end - it) > 0;
-       it += gridDim.x * WARPS_PER_BLOCK) {
+  const uint32_t begin = b.refill_win[2 * slot], end = b.refill_win[2 * slot + 1];
+  for (uint32_t it = begin + blockIdx.x * PF_WPB + warp; (int32_t)(end - it) > 0; it += gridDim.x * PF_WPB) {
     const int64_t env = (int64_t)b.refill_ring[it & (b.refill_cap - 1u)];
-    bool all_ready = true;
-    for (int k = 0; k < SP_DEPTH; ++k)
-      all_ready = all_ready && *reinterpret_cast<volatile uint8_t*>(b.sp_state + env * SP_DEPTH + k) != 0;
-    if (all_ready) continue;
+    // passes overlap (one per step, two streams): one warp at a time per env; the loser hands the
+    // request on to a later pass
+    uint32_t got = 0;
+    if (lane == 0) got = atomicCAS(b.sp_lock + env, 0u, 1u) == 0u ? 1u : 0u;
+    got = __shfl_sync(RG_FULL, got, 0);
+    if (!got) {
+      if (lane == 0) {
+        const uint32_t t = atomicAdd(b.refill_ctl, 1u);
+        b.refill_ring[t & (b.refill_cap - 1u)] = (uint32_t)env;
+      }
+      continue;
+    }
     __threadfence();
     const uint32_t e0 = *reinterpret_cast<volatile uint32_t*>(&b.st[env].episode);  // live episode counter
     // Episode e0+k is built from the state that precedes it: the live env (k = 1) or the
@@ -535,6 +575,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_prefetch(DevBatch b) {
                         *reinterpret_cast<volatile uint32_t*>(&b.sp_st[sp].episode) == e0 + k;
       if (have) continue;
       if (*reinterpret_cast<volatile uint8_t*>(b.sp_state + sp) == 1) break;  // holds a game the step kernels may still take
+      if (*reinterpret_cast<volatile uint32_t*>(b.sp_cancel + sp) == e0 + k) break;  // that episode was built synchronously
       __threadfence();
       Ctx c;
       if (k == 1) {
@@ -556,18 +597,17 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_prefetch(DevBatch b) {
       if (c.lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the writes themselves, not just the reads
       __threadfence();
       __syncwarp();
+      // the step kernels may have given up on this game in the meantime (finish_env's miss path)
+      const bool cancelled = *reinterpret_cast<volatile uint32_t*>(b.sp_cancel + sp) == e0 + k ||
+                             *reinterpret_cast<volatile uint32_t*>(&b.st[env].episode) >= e0 + k;
+      if (cancelled) break;
       if (c.lane == 0) *reinterpret_cast<volatile uint8_t*>(b.sp_state + sp) = 1;
       count_event(b, c, RGS_PREFETCH_BUILT);
       __syncwarp();
     }
-  }
-}
-
-// Fixes the window of refill requests the next k_prefetch pass serves: [previous end, current tail).
-__global__ void k_prefetch_plan(DevBatch b) {
-  if (threadIdx.x == 0) {
-    b.refill_ctl[1] = b.refill_ctl[2];
-    b.refill_ctl[2] = *reinterpret_cast<volatile uint32_t*>(b.refill_ctl);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicExch(b.sp_lock + env, 0u);
   }
 }
 
@@ -768,6 +808,13 @@ __global__ void k_unpack_hist(DevBatch b, uint8_t* __restrict__ out) {
 // ---------------------------------------------------------------- launchers
 static size_t one_warp_smem(const DevBatch& b) { return 2 * (size_t)b.CP + sizeof(EnvState) + 16; }
 static size_t block_smem(const DevBatch& b) { return (size_t)WARPS_PER_BLOCK * one_warp_smem(b); }
+static int pf_warps_per_block(const DevBatch& b) {
+  int w = b.pf_wpb > 0 ? b.pf_wpb : PF_MAX_WPB;
+  const int fit = (int)((200u << 10) / one_warp_smem(b));  // 227 KB per block at most; leave room for the step kernels
+  if (w > fit) w = fit;
+  if (w > PF_MAX_WPB) w = PF_MAX_WPB;
+  return w < 1 ? 1 : w;
+}
 
 cudaError_t configure_kernels(const DevBatch& b) {
   size_t sm = block_smem(b);
@@ -777,9 +824,9 @@ cudaError_t configure_kernels(const DevBatch& b) {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_step_monsters, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_step_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  e = cudaFuncSetAttribute(k_step_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GEN_WPB * one_warp_smem(b)));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_prefetch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  e = cudaFuncSetAttribute(k_prefetch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pf_warps_per_block(b) * one_warp_smem(b)));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_complete_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one_warp_smem(b));
   if (e != cudaSuccess) return e;
@@ -798,8 +845,8 @@ cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_rese
                         cudaEvent_t ev_fork, cudaEvent_t ev_join) {
   const int blocks = (int)((b.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
   const size_t sm = block_smem(b);
-  int gen_blocks = b.gen_warps / WARPS_PER_BLOCK;
-  if (gen_blocks > blocks) gen_blocks = blocks;
+  int gen_blocks = (int)std::min<int64_t>(b.gen_warps / GEN_WPB, (b.n + GEN_WPB - 1) / GEN_WPB);
+  const size_t gen_sm = GEN_WPB * one_warp_smem(b);
   cudaError_t e;
   k_step_scan<<<(unsigned)((b.n + 255) / 256), 256, 0, s>>>(b, actions);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -807,7 +854,7 @@ cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_rese
   // high-priority side stream, and run beside the player and monster kernels
   if ((e = cudaEventRecord(ev_fork, s)) != cudaSuccess) return e;
   if ((e = cudaStreamWaitEvent(side, ev_fork, 0)) != cudaSuccess) return e;
-  k_step_gen<<<gen_blocks, WARPS_PER_BLOCK * 32, sm, side>>>(b, actions, auto_reset, 0);
+  k_step_gen<<<gen_blocks, GEN_WPB * 32, gen_sm, side>>>(b, actions, auto_reset, 0);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if ((e = cudaEventRecord(ev_join, side)) != cudaSuccess) return e;
   k_step_player<<<blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, actions, auto_reset);
@@ -817,21 +864,20 @@ cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_rese
   k_step_monsters<<<mon_blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, auto_reset);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (auto_reset) {  // episode ends whose next game was not prefetched in time (normally none)
-    k_step_gen<<<gen_blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, actions, auto_reset, 1);
+    k_step_gen<<<gen_blocks, GEN_WPB * 32, gen_sm, s>>>(b, actions, auto_reset, 1);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   if ((e = cudaStreamWaitEvent(s, ev_join, 0)) != cudaSuccess) return e;
-  k_step_end<<<1, 32, 0, s>>>(b);
+  k_step_end<<<1, 32, 0, s>>>(b, auto_reset);
   return cudaGetLastError();
 }
-cudaError_t launch_prefetch(const DevBatch& b, int warps, cudaStream_t s) {
-  const int64_t blocks_all = (b.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-  int blocks = (warps > 0 ? warps : b.gen_warps) / WARPS_PER_BLOCK;
+cudaError_t launch_prefetch(const DevBatch& b, int warps, int slot, cudaStream_t s) {
+  const int PF_WPB = pf_warps_per_block(b);
+  const int64_t blocks_all = (b.n + PF_WPB - 1) / PF_WPB;
+  int blocks = (warps > 0 ? warps : b.gen_warps) / PF_WPB;
   if (blocks > blocks_all) blocks = (int)blocks_all;
-  k_prefetch_plan<<<1, 32, 0, s>>>(b);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  k_prefetch<<<blocks, WARPS_PER_BLOCK * 32, block_smem(b), s>>>(b);
+  if (blocks < 1) blocks = 1;
+  k_prefetch<<<blocks, PF_WPB * 32, PF_WPB * one_warp_smem(b), s>>>(b, slot);
   return cudaGetLastError();
 }
 cudaError_t launch_test_move_enemy(const DevBatch& b, int64_t env, int fx, int fy, int tx, int ty, int* out3,

@@ -10,8 +10,8 @@ cudaError_t launch_reset(const DevBatch& b, cudaStream_t s);
 // one env-step = player, monster, finish and full-path kernels (4 launches)
 cudaError_t launch_step(const DevBatch& b, const uint8_t* actions_dev, int auto_reset, cudaStream_t s, cudaStream_t side,
                         cudaEvent_t ev_fork, cudaEvent_t ev_join);
-// background generation of next-episode games into the sp_* buffers (second stream)
-cudaError_t launch_prefetch(const DevBatch& b, int warps, cudaStream_t s);
+// background generation of next-episode games into the sp_* buffers; serves window `slot` of refill_win
+cudaError_t launch_prefetch(const DevBatch& b, int warps, int slot, cudaStream_t s);
 cudaError_t launch_test_move_enemy(const DevBatch& b, int64_t env, int fx, int fy, int tx, int ty, int* out3_dev,
                                    cudaStream_t s);
 cudaError_t launch_encode(const DevBatch& b, int mode, uint32_t flag, int with_hist, int channels, float* out_dev,

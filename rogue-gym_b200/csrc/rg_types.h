@@ -127,14 +127,19 @@ struct DevBatch {
   uint8_t* sp_state;      // [N][SP_DEPTH]
   unsigned long long* trace;  // optional (RG_TRACE=1): [512 steps][8 kernels][2] first start / last end, globaltimer ns
   int32_t trace_step;         // slot of a background pass (step kernels use *dstep)
-  uint32_t* dstep;            // [1] steps executed so far; its low bit selects the work-list buffers
+  uint32_t* dstep;            // [0] steps executed so far (low bit selects the work-list buffers), [1] auto-reset steps
   unsigned long long* stats;  // [8] RGS_* event counters since creation (observability)
   uint32_t* refill_ring;  // [refill_cap] env ids whose prefetch ring has a free slot (producers: finish_env)
-  uint32_t* refill_ctl;   // [0] tail (producers), [1] begin, [2] end of the pass being executed (k_prefetch_plan)
+  uint32_t* refill_ctl;   // [0] tail (producers), [2] end of the last window handed to a pass
   uint32_t refill_cap;    // power of two
+  uint32_t* refill_win;   // [8][2] window [begin, end) of the ring served by background pass k % 8 (k_step_end)
+  uint32_t* sp_lock;      // [N] 1 = a background pass is working on this env's ring (passes overlap)
+  uint32_t* sp_cancel;    // [N][SP_DEPTH] episode whose game must not be published: it was built synchronously
+  int32_t prefetch_every; // a background pass is kicked every k-th auto-reset step
+  int32_t pf_wpb;         // warps per block of k_prefetch (0 = default)
   int32_t prefetch;       // 0 = off (every reset is generated synchronously by k_step_gen)
   uint32_t* mon_list;     // [N] envs with an active monster this step (player kernel -> monster kernel)
-  uint32_t* mon_count;    // [2] ping-pong by step parity
+  uint32_t* mon_count;    // [0..1] list length by step parity, [2..3] the monster kernel's work cursor
   int32_t mon_warps;      // warps of the (grid-stride) monster kernel
 };
 
