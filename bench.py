@@ -32,6 +32,9 @@ CONFIG = {}  # config-default: every field at its default ("{}" => default, core
 #   read  grid 2C (3840) + small state 1536 + action 1
 #   write screen C (1920) + small state 512 + status/reward/done/msg 49
 BYTES_PER_ENV_STEP = 7858
+# dram__bytes_read.sum + dram__bytes_write.sum of one steady-state step (scan + player + monsters + full-path
+# kernels) at 65 536 envs, from the ncu --set full capture summarised in profiles/r1_ncu_summary.md
+NCU_DRAM_BYTES_PER_STEP = 453.3e6
 WORKLOAD = "65536 envs/GPU, config-default 80x24 (3x3 rooms, monsters, gold, visibility), random 11-action rollout, max_steps 1000, auto-reset"
 
 
@@ -212,47 +215,68 @@ def main():
     live = int((err == 0).sum())
     digest = int(np.bitwise_xor.reduce(shard.hashes()))
 
-    # ---- end to end through the reference-facing C-ABI call with HOST buffers (e2e)
-    e2e_ms, h2d, d2h = None, n, 0
+    # ---- end to end through the reference-facing C-ABI call with HOST buffers (e2e): every step the
+    # actions come from pinned host memory and the whole observation block (screen u8[N,H,W], status,
+    # reward, done, message) is current in host memory before the next step starts.
+    #   e2e            rg_step_mirror: the block lives in a pinned host mirror; kernels compare it with a
+    #                  device-side shadow and store only the 16-byte pieces that changed, over PCIe
+    #   e2e_full_copy  rg_step_host: the block is copied whole (129 MB per step) - the straightforward path
+    e2e_ms, full_ms, h2d, d2h, d2h_full = None, None, n, 0, 0
     if not args.no_e2e:
-        shard.reseed_and_reset()
+        hp = host_actions.data_ptr()
+
+        def timed(step_fn):
+            shard.reseed_and_reset()
+            for t in range(Wm):
+                step_fn(t)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for t in range(Wm, total):
+                step_fn(t)  # H2D actions -> step kernels -> observation into host memory -> stream sync, every step
+            shard.quiesce()
+            e1.record(stream)
+            barrier()
+            return e0.elapsed_time(e1)
+
+        mobs, _ = shard.mirror()
+        sent = []
+        e2e_ms = timed(lambda t: sent.append(shard.step_mirror(hp + t * n)))
+        d2h = sum(sent[Wm:]) / K + 8  # + the 8-byte counter read back with every step
+        import ctypes
+        hdone = np.ctypeslib.as_array(ctypes.cast(mobs.done, ctypes.POINTER(ctypes.c_uint8)), shape=(n,))
+        hstat = np.ctypeslib.as_array(ctypes.cast(mobs.status, ctypes.POINTER(ctypes.c_uint32)), shape=(n * 10,))
+        mirror_digest = (int(hdone.sum()), int(hstat.astype(np.uint64).sum()))
+
         scr = torch.empty((n, shard.W * shard.H), dtype=torch.uint8).pin_memory()
         stat = torch.empty((n, 10), dtype=torch.int32).pin_memory()
         rew = torch.empty(n, dtype=torch.int32).pin_memory()
         done = torch.empty(n, dtype=torch.uint8).pin_memory()
         msg = torch.empty(n, dtype=torch.int32).pin_memory()
         obs = _cabi.HostObs(scr.data_ptr(), None, stat.data_ptr(), rew.data_ptr(), done.data_ptr(), msg.data_ptr(), None)
-        d2h = scr.numel() + stat.numel() * 4 + rew.numel() * 4 + done.numel() + msg.numel() * 4
-        hp = host_actions.data_ptr()
-        for t in range(Wm):
-            shard.step_host(hp + t * n, obs)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for t in range(Wm, total):
-            shard.step_host(hp + t * n, obs)  # H2D actions -> kernel -> D2H observation -> stream sync, every step
-        shard.quiesce()
-        e1.record(stream)
-        barrier()
-        e2e_ms = e0.elapsed_time(e1)
-        assert int(done.sum()) >= 0 and int(rew.sum()) >= 0
+        d2h_full = scr.numel() + stat.numel() * 4 + rew.numel() * 4 + done.numel() + msg.numel() * 4
+        full_ms = timed(lambda t: shard.step_host(hp + t * n, obs))
+        # both paths ran the same seeds and actions: the host-side results must agree
+        full_digest = (int(done.sum()), int(stat.numpy().astype(np.uint32).astype(np.uint64).sum()))
+        assert mirror_digest == full_digest, (mirror_digest, full_digest)
 
     # ---- max over ranks (device time), whole-job aggregate
-    vals = torch.tensor([ms, e2e_ms if e2e_ms is not None else 0.0, float(live)], dtype=torch.float64, device="cuda")
+    vals = torch.tensor([ms, e2e_ms if e2e_ms is not None else 0.0, float(live), full_ms if full_ms is not None else 0.0,
+                         float(d2h)], dtype=torch.float64, device="cuda")
     if dist is not None:
         mx = vals.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = vals.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms, e2e_ms_all, live_all = float(mx[0]), float(mx[1]), float(sm[2])
+        ms, e2e_ms_all, live_all, full_ms_all, d2h_all = float(mx[0]), float(mx[1]), float(sm[2]), float(mx[3]), float(sm[4])
     else:
-        e2e_ms_all, live_all = float(vals[1]), float(vals[2])
+        e2e_ms_all, live_all, full_ms_all, d2h_all = float(vals[1]), float(vals[2]), float(vals[3]), float(vals[4])
     total_envs = n * world
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sample_envs, sample_steps = 4096, 300
+        sample_envs, sample_steps = 8192, 4000  # ~10 s on 16 threads: the first 8192 envs for four episodes' worth of steps
         v, secs = cpu_port_rollout(sample_envs, sample_steps, 0, threads)
         cpu_baseline = {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
                         "sample": "%d of the 65536 envs x %d steps on %d host threads (%.1f s), C++ oracle port; the Rust "
@@ -277,13 +301,24 @@ def main():
             "clocks": clocks,
             "e2e": None if e2e_ms is None else {
                 "value": live_all * K / (e2e_ms_all * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d * world,
-                "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms_all / K,
-                "what": "rg_step_host per step: actions from pinned host memory, kernel, D2H of screen u8[N,24,80] + status + reward + done + message into pinned host memory, stream sync"},
+                "d2h_bytes_per_step": int(d2h_all), "ms_per_step": e2e_ms_all / K,
+                "what": "rg_step_mirror per step: actions from pinned host memory, step kernels, delta write-back of the observation "
+                        "block (screen u8[N,24,80] + status + reward + done + message) into the pinned host mirror - only the 16-byte "
+                        "pieces that changed cross PCIe (measured average in d2h_bytes_per_step) - then stream sync; the host block is "
+                        "byte-identical to a full copy (tests/test_gpu_parity.py::test_host_mirror_equals_full_copy)"},
+            "e2e_full_copy": None if full_ms is None else {
+                "value": live_all * K / (full_ms_all * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d * world,
+                "d2h_bytes_per_step": d2h_full * world, "ms_per_step": full_ms_all / K,
+                "what": "rg_step_host per step: same, but the whole observation block is copied D2H every step (PCIe-bound)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "rg::k_step", "bytes_per_env_step": BYTES_PER_ENV_STEP,
-                         "peak_source": peak_src,
-                         "note": "k_step is the only kernel in the timed region; it is bound by serial per-env game logic (RNG chains, BFS), not by HBM"},
+                         "traffic": NCU_DRAM_BYTES_PER_STEP if (n == ENVS_PER_GPU and not args.config_json) else None,
+                         "kernel": "one step = CUDA graph of rg::k_step_scan -> k_step_player -> k_step_monsters (+ k_step_gen beside them); "
+                                   "k_step_player is the dominant kernel (ncu: 137 us of the ~195 us serial chain, 423 MB of the step's DRAM traffic)",
+                         "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_source": peak_src,
+                         "note": "achieved = algorithmic bytes of one step (7858 B x envs) / average step duration over the timed region "
+                                 "(CUDA events on the batch's stream); traffic = dram read+write of the step's kernels from ncu --set full "
+                                 "(profiles/r1_ncu_summary.md). The step is bound by per-env serial game logic and instruction fetch, not by HBM"},
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)

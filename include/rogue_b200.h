@@ -30,6 +30,9 @@
  *                       Vec<u8> in, Vec<PlayerState> out)     python/src/lib.rs:315-321
  *   rg_views / rg_fetch ParallelGameState::states / GameState::prev
  *                                                             python/src/lib.rs:238-241,310-314
+ *   rg_step_mirror      the same host-facing step; the Vec<PlayerState> it replaces is kept current
+ *                       in a host mirror by delta writes instead of a full copy (no reference
+ *                       counterpart for the mechanism)          python/src/lib.rs:315-321
  *   rg_encode           PlayerState::{gray_image,symbol_image}[_with_hist]
  *                                                             python/src/lib.rs:158-205
  *   rg_status_vec order StatusFlagInner::to_vector            python/src/flags.rs:63-85
@@ -195,6 +198,20 @@ int rg_trace(rg_batch* b, uint64_t* out, int64_t* steps_launched);
 int rg_sync(rg_batch* b);          /* waits for the stream and raises per-env errors like the reference */
 int rg_views_get(rg_batch* b, rg_views* out);
 int rg_fetch(rg_batch* b, rg_host_obs* out);
+/* ---- host mirror: the observation block kept current in HOST memory without copying it whole.
+ * rg_mirror_get allocates (once) pinned host buffers that the device can write, owned by the batch and
+ * valid until rg_destroy: out->screen [N][W*H], status, reward, done, message, error as in rg_host_obs;
+ * out->history is NULL - the visited map is mirrored bit-packed, *history_bits [N][hist_stride] with
+ * bit y*W+x of an env's row = visited (the layout of rg_views.history_bits).
+ * rg_mirror_sync brings the mirror up to date with the device block: kernels compare the block with a
+ * device-side shadow of what the host holds and store only the 16-byte pieces that changed, over PCIe,
+ * into the mirror; it returns after the stream has drained, so the host may read at once.
+ * rg_step_mirror = actions H2D + rg_step + rg_mirror_sync: the host-facing step of rg_step_host
+ * (python/src/lib.rs:315-321) at a fraction of its PCIe traffic. *bytes_to_host (nullable) receives the
+ * bytes the call stored into the mirror. The caller must not write to the mirror. */
+int rg_mirror_get(rg_batch* b, rg_host_obs* out, uint8_t** history_bits);
+int rg_mirror_sync(rg_batch* b, uint64_t* bytes_to_host);
+int rg_step_mirror(rg_batch* b, const uint8_t* actions_host, int auto_reset, uint64_t* bytes_to_host);
 void* rg_stream(rg_batch* b);      /* cudaStream_t the batch launches on */
 int64_t rg_launch_count(rg_batch* b); /* kernels launched so far by this batch */
 

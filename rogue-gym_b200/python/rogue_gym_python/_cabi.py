@@ -106,6 +106,9 @@ SYMBOLS = {
     "rg_trace": (_i, [_vp, _vp, _vp]),
     "rg_views_get": (_i, [_vp, C.POINTER(Views)]),
     "rg_fetch": (_i, [_vp, C.POINTER(HostObs)]),
+    "rg_mirror_get": (_i, [_vp, C.POINTER(HostObs), C.POINTER(_vp)]),
+    "rg_mirror_sync": (_i, [_vp, C.POINTER(C.c_uint64)]),
+    "rg_step_mirror": (_i, [_vp, _vp, _i, C.POINTER(C.c_uint64)]),
     "rg_stream": (_vp, [_vp]),
     "rg_launch_count": (_i64, [_vp]),
     "rg_encode": (_i, [_vp, _i, _u32, _i, _vp, C.POINTER(_i)]),
@@ -141,8 +144,11 @@ def last_error(handle=None):
     return msg.decode("utf-8", "replace") if msg else ""
 
 
-def check(rc, handle=None):
-    """Errors surface the way the PyO3 layer raises them: RuntimeError (python/src/lib.rs:20-26)."""
+def check(rc, handle=None, tolerate_env_errors=False):
+    """Errors surface the way the PyO3 layer raises them: RuntimeError (python/src/lib.rs:20-26).
+    Batched callers that read the per-env `error` array pass tolerate_env_errors=True."""
+    if tolerate_env_errors and rc in (RG_ERR_INVALID_INPUT, RG_ERR_IGNORED_INPUT, RG_ERR_PANIC):
+        return
     if rc != RG_OK:
         err = RuntimeError(last_error(handle) or ("rogue-gym_b200 error %d" % rc))
         err.code = rc

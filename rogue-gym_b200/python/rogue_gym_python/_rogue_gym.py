@@ -106,6 +106,52 @@ class _Batch:
             raise RuntimeError("Error in rogue-gym: expected %d actions, got %s" % (self.n, a.shape))
         check(self.L.rg_step_host(self.h, a.ctypes.data, int(auto_reset), C.byref(self.obs)), self.h)
 
+    # ---- host mirror (include/rogue_b200.h rg_mirror_*): numpy views of pinned memory the device
+    # keeps current by writing only what changed; read-only for the caller
+    def mirror(self):
+        self._alive()
+        if getattr(self, "_mirror", None) is None:
+            obs, hist = _cabi.HostObs(), C.c_void_p()
+            check(self.L.rg_mirror_get(self.h, C.byref(obs), C.byref(hist)), self.h, tolerate_env_errors=True)
+            v = _cabi.Views()
+            check(self.L.rg_views_get(self.h, C.byref(v)), self.h)
+            n = self.n
+
+            def view(ptr, ctype, shape):
+                count = int(np.prod(shape))
+                return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(count,)).reshape(shape)
+
+            self._mirror = dict(
+                screen=view(obs.screen, C.c_uint8, (n, self.H, self.W)),
+                history_bits=view(hist, C.c_uint8, (n, v.hist_stride)),
+                status=view(obs.status, C.c_uint32, (n, 10)), reward=view(obs.reward, C.c_int32, (n,)),
+                done=view(obs.done, C.c_uint8, (n,)), message=view(obs.message, C.c_uint32, (n,)),
+                error=view(obs.error, C.c_uint8, (n,)))
+        return self._mirror
+
+    def mirror_sync(self):
+        nbytes = C.c_uint64()
+        check(self.L.rg_mirror_sync(self.h, C.byref(nbytes)), self.h, tolerate_env_errors=True)
+        return nbytes.value
+
+    def step_mirror(self, keys, auto_reset=True):
+        """One step whose observation lands in mirror(); returns the bytes that crossed PCIe for it."""
+        m = self.mirror()
+        a = np.ascontiguousarray(keys, dtype=np.uint8)
+        if a.shape != (self.n,):
+            raise RuntimeError("Error in rogue-gym: expected %d actions, got %s" % (self.n, a.shape))
+        nbytes = C.c_uint64()
+        check(self.L.rg_step_mirror(self.h, a.ctypes.data, int(auto_reset), C.byref(nbytes)), self.h,
+              tolerate_env_errors=True)
+        del m
+        return nbytes.value
+
+    def mirror_history(self):
+        """uint8 [N, H, W] 0/1 visited map from the mirrored bit rows."""
+        m = self.mirror()
+        bits = np.unpackbits(m["history_bits"], axis=1, bitorder="little")[:, :self.C]
+        return bits.reshape(self.n, self.H, self.W)
+
     def player_state(self, i):
         return PlayerState(self, self.screen[i].copy(), self.history[i].copy(), self.status[i].copy(),
                            int(self.message[i]), bool(self.done[i]))
@@ -323,8 +369,10 @@ class ParallelGameState:
 
     # ---- batched surface (not in the reference): arrays instead of per-env objects
     def step_arrays(self, keys):
-        """keys: uint8[N] ASCII. Returns a dict of numpy views refreshed in place each call."""
+        """keys: uint8[N] ASCII. Steps every env and returns numpy views of the host mirror: screen
+        u8 [N,H,W], history_bits (bit-packed rows, see `_Batch.mirror_history`), status, reward, done,
+        message, error. The views are refreshed in place by every call (only what changed crosses
+        PCIe); envs in an error state are reported through `error`, nothing is raised."""
         b = self._batch
-        b.step(keys, True)
-        return dict(screen=b.screen.reshape(b.n, b.H, b.W), history=b.history.reshape(b.n, b.H, b.W),
-                    status=b.status, reward=b.reward, done=b.done, message=b.message)
+        b.step_mirror(keys, True)
+        return b.mirror()

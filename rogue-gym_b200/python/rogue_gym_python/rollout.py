@@ -74,6 +74,22 @@ class Shard:
         if rc not in (_cabi.RG_OK, _cabi.RG_ERR_PANIC):
             _cabi.check(rc, self.h)
 
+    def mirror(self):
+        """Host mirror of the observation block (rg_mirror_get): HostObs of pinned pointers."""
+        obs, hist = _cabi.HostObs(), C.c_void_p()
+        rc = self.L.rg_mirror_get(self.h, C.byref(obs), C.byref(hist))
+        if rc not in (_cabi.RG_OK, _cabi.RG_ERR_PANIC):
+            _cabi.check(rc, self.h)
+        return obs, hist
+
+    def step_mirror(self, actions_host_ptr):
+        """rg_step_mirror; returns the bytes stored into the host mirror by this step."""
+        nbytes = C.c_uint64()
+        rc = self.L.rg_step_mirror(self.h, actions_host_ptr, 1, C.byref(nbytes))
+        if rc not in (_cabi.RG_OK, _cabi.RG_ERR_PANIC):
+            _cabi.check(rc, self.h)
+        return nbytes.value
+
     def quiesce(self):
         """Main stream waits for the background next-episode generation queued so far (async)."""
         _cabi.check(self.L.rg_quiesce(self.h), self.h)

@@ -370,3 +370,46 @@ def test_full_size_batch_properties(gpu, oracle):
             assert (status[ok][:, 2] <= status[ok][:, 3]).all() and (status[ok][:, 4] == 16).all()
         L.rg_destroy(h)
     assert np.array_equal(digests[0], digests[1])
+
+
+# ---------------------------------------------------------------- host mirror (delta write-back)
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg_name", ["default", "mini", "odd"])
+def test_host_mirror_equals_full_copy(gpu, cfg_name):
+    """rg_step_mirror must leave the host mirror byte-identical to what rg_fetch copies, every step,
+    across auto-resets, stair descents and explicit resets, while moving far fewer bytes."""
+    import json
+
+    from conftest import CONFIGS
+    from helpers import KEYS19
+    n, steps = 192, 150
+    cfg = CONFIGS[cfg_name]
+    pg = gpu.ParallelGameState(25, [json.dumps(cfg)] * n)
+    pg.seed(list(range(3, n + 3)))
+    pg.reset()
+    b = pg._batch
+    m = b.mirror()
+    assert m["screen"].shape == (n, b.H, b.W) and not m["screen"].flags.owndata
+    rng = np.random.RandomState(11)
+    full_bytes = n * (b.C + 40 + 4 + 1 + 4 + 1)
+    sent = []
+    for t in range(steps):
+        keys = KEYS19[rng.randint(0, len(KEYS19), size=n)]
+        sent.append(b.step_mirror(keys, True))
+        b.fetch()  # the full D2H copy of the same block
+        assert np.array_equal(m["screen"].reshape(n, -1), b.screen), "screen differs at step %d" % t
+        assert np.array_equal(b.mirror_history().reshape(n, -1), b.history), "history differs at step %d" % t
+        assert np.array_equal(m["status"], b.status) and np.array_equal(m["reward"], b.reward)
+        assert np.array_equal(m["done"], b.done) and np.array_equal(m["message"], b.message)
+        assert np.array_equal(m["error"], b.error)
+        if t == 70:
+            pg.seed(list(range(1000, n + 1000)))
+            b.reset()
+            assert b.mirror_sync() > 0
+            assert np.array_equal(m["screen"].reshape(n, -1), b.screen)
+    assert b.mirror_sync() == 0  # nothing changed since the last step
+    assert np.median(sent) < 0.25 * full_bytes, (np.median(sent), full_bytes)
+    arr = pg.step_arrays(KEYS19[rng.randint(0, 11, size=n)])
+    b.fetch()
+    assert np.array_equal(arr["screen"].reshape(n, -1), b.screen) and np.array_equal(arr["done"], b.done)
+    pg.close()
