@@ -119,6 +119,13 @@ struct Ctx {
 };
 
 RG_DEV void set_panic(Ctx& c) { c.panic = 1; }
+// rows [y0, y1] of the tile planes changed: the next compose has to recompute them
+RG_DEV void mark_rows(Ctx& c, int y0, int y1) {
+  y0 = max(y0, 0);
+  y1 = min(y1, c.H - 1);
+  if (y1 < y0) return;
+  c.st->dirty_rows |= ((~0ull) >> (63 - (y1 - y0))) << y0;
+}
 
 // Room grid geometry: rooms.rs:176,191-206
 RG_DEV void room_area(const Ctx& c, int i, int& ax0, int& ay0, int& ax1, int& ay1) {
@@ -587,6 +594,7 @@ __device__ void enters_room(Ctx& c, int x, int y) {
     if (rm.kind == K_NORMAL && !(rm.flags & RF_DARK)) {
       int w = rm.x1 - rm.x0, n = w * (rm.y1 - rm.y0);
       for (int k = c.lane; k < n; k += 32) A[(rm.y0 + k / w) * c.W + rm.x0 + k % w] |= (A_DRAWN | A_VISIBLE);
+      mark_rows(c, rm.y0, rm.y1 - 1);
       __syncwarp();
     }
   }
@@ -610,6 +618,7 @@ __device__ void leaves_room(Ctx& c, int x, int y) {
   int w = x1 - x0 - 2, h = y1 - y0 - 2;
   if (w <= 0 || h <= 0) return;
   for (int k = c.lane; k < w * h; k += 32) A[(y0 + 1 + k / w) * c.W + x0 + 1 + k % w] &= (uint8_t)~A_VISIBLE;
+  mark_rows(c, y0 + 1, y1 - 2);
   __syncwarp();
 }
 // Floor::player_in floor.rs:264-295 ; Cell::approached field.rs:20-26
@@ -617,6 +626,7 @@ __device__ void player_in(Ctx& c, int x, int y, bool init) {
   RG_PLANES(c);
   const int W = c.W;
   if (init || (A[y * W + x] & A_DOOR)) enters_room(c, x, y);
+  mark_rows(c, y - 1, y + 1);
   A[y * W + x] |= A_VISITED;
 #pragma unroll
   for (int d = 0; d < 9; ++d) {
@@ -635,6 +645,7 @@ __device__ void player_out(Ctx& c, int x, int y) {
   RG_PLANES(c);
   const int W = c.W;
   if (A[y * W + x] & A_DOOR) leaves_room(c, x, y);
+  mark_rows(c, y - 1, y + 1);
 #pragma unroll
   for (int d = 0; d < 9; ++d) {
     int nx = x + ddx(d), ny = y + ddy(d);
@@ -685,6 +696,7 @@ __device__ __noinline__ void new_level(Ctx* cp, bool is_initial) {
     c.hist_done = 1;
   }
   st->level += 1;
+  st->dirty_rows = ~0ull;  // a new floor: everything is recomposed
   const uint32_t level = (uint32_t)st->level;
   // fresh field
   __syncwarp();
@@ -1293,6 +1305,7 @@ __device__ void search(Ctx& c) {
   RG_PLANES(c);
   const int W = c.W;
   const int px = st->px, py = st->py;
+  mark_rows(c, py - 1, py + 1);
   bool maps_done = false;
   for (int d = 0; d < 8; ++d) {
     int nx = px + ddx(d), ny = py + ddy(d);
@@ -1382,18 +1395,69 @@ __device__ void process_action(Ctx& c, int act, int d) {
 // ------------------------------------------------------------------ observation compose
 // RunTime::draw_screen core/src/lib.rs:264-285 + Dungeon::draw / draw_ranges / draw_enemy
 // rogue/mod.rs:278-300,398-404 + Floor::history_map floor.rs:372-379.
+// Whether monster `mo` is drawn for a player at (px, py): Dungeon::draw_enemy rogue/mod.rs:398-404
+RG_DEV bool monster_shown(const Ctx& c, const MonD& mo, int px, int py) {
+  const uint8_t* A = c.A;
+  const EnvState* st = c.st;
+  if (!(mo.flags & MF_PRESENT)) return false;
+  const int idx = mo.y * c.W + mo.x;
+  const bool vis = (A[idx] & (A_VISIBLE | A_DRAWN)) && mo.y >= 1 && mo.y < c.H - 1;
+  const int dx = px - mo.x, dy = py - mo.y;
+  bool show = dx * dx + dy * dy <= 2;  // Coord::is_adjacent
+  if (!show) {                         // Floor::in_same_room floor.rs:381-393
+    const int id = room_of(c, px, py);
+    if (id >= 0 && room_of(c, mo.x, mo.y) == id) {
+      const RoomD rm = st->rooms[id];
+      show = (rm.kind == K_EMPTY) || (in_rect(rm, px, py) == in_rect(rm, mo.x, mo.y));
+    }
+  }
+  return vis && show;
+}
+
+// The screen in HBM is persistent (the reference keeps PlayerState.map between redraws too), so a
+// redraw recomputes only the rows that can differ from what is there: rows whose tile planes changed
+// since the last compose (EnvState::dirty_rows, marked where the planes are written), rows where the
+// last compose drew an overlay (ov_rows: monsters move without a redraw) and rows where one is drawn
+// now. The result is what a full redraw gives; a typical move touches 3-6 of the 24 rows.
 __device__ void compose(Ctx& c) {
   RG_PLANES(c);
   const int W = c.W, H = c.H;
   __syncwarp();
+  const int px = st->px, py = st->py;
+  // overlays first (positions only): monsters, items, player (core/src/lib.rs:272-283)
+  int mon_idx = -1, item_idx = -1;
+  uint64_t rows_now = 0;
+  if (c.lane < c.nrooms) {
+    const MonD mo = st->mon[c.lane];
+    if (monster_shown(c, mo, px, py)) {
+      mon_idx = mo.y * W + mo.x;
+      rows_now |= 1ull << mo.y;
+    }
+    const uint16_t ip = st->item_pos[c.lane];
+    if (ip != 0xFFFF && (A[ip] & (A_VISIBLE | A_DRAWN)) && ip >= W && ip < (H - 1) * W) {
+      item_idx = ip;
+      rows_now |= 1ull << (ip / W);
+    }
+  }
+  const bool player_drawn = (A[py * W + px] & (A_VISIBLE | A_DRAWN)) && py >= 1 && py < H - 1;
+  if (player_drawn) rows_now |= 1ull << py;
+  {
+    uint32_t lo = (uint32_t)rows_now, hi = (uint32_t)(rows_now >> 32);
+    lo = __reduce_or_sync(RG_FULL, lo);
+    hi = __reduce_or_sync(RG_FULL, hi);
+    rows_now = ((uint64_t)hi << 32) | lo;
+  }
+  const uint64_t need = st->dirty_rows | st->ov_rows | rows_now;
   const int lo = W, hi = (H - 1) * W;  // rows 0 and H-1 are never written (python/src/lib.rs:44)
   for (int ch = c.lane; ch < c.CP / 16; ch += 32) {  // PARALLEL, 128-bit in / 128-bit out, 4 cells per op
-    const uint4 s4 = *reinterpret_cast<const uint4*>(S + ch * 16);
-    const uint4 a4 = *reinterpret_cast<const uint4*>(A + ch * 16);
+    const int base = ch * 16;
+    const int r0 = base / W, r1 = min(base + 15, c.C - 1) / W;  // a 16-cell piece lies in one or two rows
+    if (!(((need >> r0) | (need >> r1)) & 1ull)) continue;
+    const uint4 s4 = *reinterpret_cast<const uint4*>(S + base);
+    const uint4 a4 = *reinterpret_cast<const uint4*>(A + base);
     const uint32_t sv[4] = {s4.x, s4.y, s4.z, s4.w}, av[4] = {a4.x, a4.y, a4.z, a4.w};
     uint32_t ov[4];
     uint32_t hbits = 0;
-    const int base = ch * 16;
     const bool inside = base >= lo && base + 16 <= hi;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -1417,34 +1481,17 @@ __device__ void compose(Ctx& c) {
     if (!c.hist_done) reinterpret_cast<uint16_t*>(c.g_hist)[ch] = (uint16_t)hbits;
   }
   __syncwarp();
-  // overlays in increasing priority: monsters, items, player (core/src/lib.rs:272-283)
-  const int px = st->px, py = st->py;
-  if (c.lane < c.nrooms) {
-    MonD mo = st->mon[c.lane];
-    if (mo.flags & MF_PRESENT) {
-      int idx = mo.y * W + mo.x;
-      bool vis = (A[idx] & (A_VISIBLE | A_DRAWN)) && mo.y >= 1 && mo.y < H - 1;
-      int dx = px - mo.x, dy = py - mo.y;
-      bool show = dx * dx + dy * dy <= 2;  // Coord::is_adjacent
-      if (!show) {                         // Floor::in_same_room floor.rs:381-393
-        int id = room_of(c, px, py);
-        if (id >= 0 && room_of(c, mo.x, mo.y) == id) {
-          RoomD rm = st->rooms[id];
-          show = (rm.kind == K_EMPTY) || (in_rect(rm, px, py) == in_rect(rm, mo.x, mo.y));
-        }
-      }
-      if (vis && show) c.g_screen[idx] = (uint8_t)c.P->enemies[mo.kind].tile;
-    }
-  }
+  // overlays in increasing priority: a later store to the same cell wins
+  if (mon_idx >= 0) c.g_screen[mon_idx] = (uint8_t)c.P->enemies[st->mon[c.lane].kind].tile;
   __syncwarp();
-  if (c.lane < c.nrooms) {
-    uint16_t ip = st->item_pos[c.lane];
-    if (ip != 0xFFFF && (A[ip] & (A_VISIBLE | A_DRAWN)) && ip >= W && ip < (H - 1) * W) c.g_screen[ip] = '*';
-  }
+  if (item_idx >= 0) c.g_screen[item_idx] = '*';
   __syncwarp();
   if (c.lane == 0) {
-    int idx = py * W + px;
-    if ((A[idx] & (A_VISIBLE | A_DRAWN)) && py >= 1 && py < H - 1) c.g_screen[idx] = '@';
+    if (player_drawn) c.g_screen[py * W + px] = '@';
+    // the step that leaves a floor shows the old floor's visited map (hist_done): the new floor's map is
+    // written by the next compose, which therefore has to visit every row once more
+    st->dirty_rows = c.hist_done ? ~0ull : 0ull;
+    st->ov_rows = rows_now;
   }
   __syncwarp();
 }

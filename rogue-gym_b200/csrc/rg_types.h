@@ -80,6 +80,9 @@ struct alignas(16) EnvState {
   uint16_t cache_snap;     // bit s: cache slot s resumes on its private walkability snapshot (wsnap)
   uint8_t f_flags;         // SF_*
   uint8_t pad3;
+  // incremental compose: the screen is persistent, so only rows that can differ are recomputed
+  uint64_t dirty_rows;     // bit r: a cell of row r changed in the tile planes since the last compose
+  uint64_t ov_rows;        // bit r: the last compose drew an overlay (monster, item, player) in row r
   RoomD rooms[MAX_ROOMS];
   uint16_t item_pos[MAX_ROOMS];  // y*W+x or 0xFFFF ; slot = room id
   uint32_t item_amt[MAX_ROOMS];
