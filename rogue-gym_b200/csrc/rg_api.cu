@@ -167,6 +167,7 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
     b->sm_count = prop.multiProcessorCount;
     d.gen_warps = prop.multiProcessorCount * 16;  // grid-stride warps of the full-path kernel
     d.mon_warps = prop.multiProcessorCount * 16;  // grid-stride warps of the monster kernel
+    if (const char* e = getenv("RG_PLAYER_BLOCKS")) d.player_blocks = atoi(e);
   }
   RG_TRY(dev_alloc(b, &b->dP, 1));
   RG_TRY(cudaMemcpy(b->dP, &P, sizeof(P), cudaMemcpyHostToDevice));

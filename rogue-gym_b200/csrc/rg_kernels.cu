@@ -371,18 +371,11 @@ __global__ void __launch_bounds__(256) k_step_scan(DevBatch b, const uint8_t* __
   b.defer_list[atomicAdd(b.defer_count + parity, 1u)] = (uint32_t)env;
 }
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_HOT_MIN_BLOCKS)
-k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset) {
-  unsigned char* const smem = rg_smem;
-  const int parity = (int)(*b.dstep & 1u);
-  TraceScope trace(b, TK_PLAYER);
-  Ctx c;
-  const int warp = threadIdx.x >> 5;
-  const int64_t env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
-  if (env >= b.n) return;
-  unsigned char* const base = smem + (size_t)warp * warp_smem(b);
-  Stager sg = stager_init(b, base);
+// Player phase of one env (see k_step_player).
+RG_DEV void player_env(const DevBatch& b, Stager& sg, unsigned char* base, int64_t env, const uint8_t* __restrict__ actions,
+                       int auto_reset, int parity) {
   if (b.full_path[env]) return;  // on k_step_scan's list: the whole step runs in k_step_gen, concurrently
+  Ctx c;
   const uint8_t key = actions[env];
   fill_ctx(b, c, sg, base, env, PL_BOTH);  // state and both planes in flight together (9 of 11 actions need them)
   EnvState* st = c.st;
@@ -420,6 +413,20 @@ k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset) {
     return;
   }
   finish_env(b, c, env, auto_reset, parity);  // no monster moves this turn: the step ends here
+}
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_HOT_MIN_BLOCKS)
+k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset) {
+  unsigned char* const smem = rg_smem;
+  const int parity = (int)(*b.dstep & 1u);
+  TraceScope trace(b, TK_PLAYER);
+  const int warp = threadIdx.x >> 5;
+  unsigned char* const base = smem + (size_t)warp * warp_smem(b);
+  Stager sg = stager_init(b, base);
+  for (int64_t env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp; env < b.n; env += (int64_t)gridDim.x * WARPS_PER_BLOCK) {
+    player_env(b, sg, base, env, actions, auto_reset, parity);
+    __syncwarp();
+  }
 }
 
 // actions::move_active_enemies (actions.rs:82-119) for the envs that have an active monster
@@ -765,6 +772,58 @@ __global__ void __launch_bounds__(256) k_encode(DevBatch b, int mode, uint32_t f
   }
 }
 
+// Gray images (mode 0) have 1 + S (+1) planes only: one block per env leaves the GPU launch-bound
+// (7.7 KB of output per block). Flat version: a thread owns one float4 position (plane, 4 cells) and
+// writes it for GRAY_ENVS consecutive envs, so the index arithmetic is done once and consecutive threads
+// write consecutive float4s of the same plane. Same values as k_encode (python/src/lib.rs:72-111).
+constexpr int GRAY_ENVS = 8;
+__global__ void __launch_bounds__(256) k_encode_gray(DevBatch b, uint32_t flag, int channels, float* __restrict__ out) {
+  const int C = b.C, C4 = C / 4;  // only launched when C % 4 == 0
+  const int per_env = channels * C4;
+  // tile byte -> gray level (Symbol::from_tile / symbols, the same f32 division as k_encode), -1 = no symbol
+  __shared__ float gray_of_tile[256];
+  {
+    const int sym = tile_sym(threadIdx.x);
+    gray_of_tile[threadIdx.x] = sym < 0 ? -1.f : (float)sym / (float)b.P->symbols;
+  }
+  __syncthreads();
+  const int r = (int)(blockIdx.y * blockDim.x + threadIdx.x);
+  if (r >= per_env) return;
+  const int ch = r / C4, q = r - ch * C4;
+  const int nstat = __popc(flag & 0x1FFu);
+  int sidx = 0;
+  if (ch >= 1 && ch <= nstat) {  // StatusFlagInner::copy_status python/src/flags.rs:87-115: the (ch-1)-th set bit
+    const int bit = nth_set_bit(flag & 0x1FFu, (uint32_t)(ch - 1));
+    sidx = bit == 0 ? 0 : bit + 1;
+  }
+  const int64_t env0 = (int64_t)blockIdx.x * GRAY_ENVS;
+#pragma unroll 4
+  for (int e = 0; e < GRAY_ENVS; ++e) {
+    const int64_t env = env0 + e;
+    if (env >= b.n) break;
+    float4 v;
+    if (ch == 0) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(b.screen + env * b.CP + 4 * q);
+      v = make_float4(gray_of_tile[w & 0xFFu], gray_of_tile[(w >> 8) & 0xFFu], gray_of_tile[(w >> 16) & 0xFFu],
+                      gray_of_tile[w >> 24]);
+      if (v.x < 0.f || v.y < 0.f || v.z < 0.f || v.w < 0.f) {  // InvalidTileError symbol.rs:60-64
+        b.error[env] = RG_ERR_SETTING;
+        atomicOr(b.errflag, 1u << RG_ERR_SETTING);
+        v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+      }
+    } else if (ch <= nstat) {
+      const float f = (float)(int32_t)b.status[env * 10 + sidx];
+      v = make_float4(f, f, f, f);
+    } else {  // copy_hist python/src/lib.rs:105-111
+      const uint32_t byte = (b.hist + env * b.HB)[(4 * q) >> 3];
+      const int sh = (4 * q) & 7;
+      v = make_float4((byte >> sh) & 1u ? 1.f : 0.f, (byte >> (sh + 1)) & 1u ? 1.f : 0.f, (byte >> (sh + 2)) & 1u ? 1.f : 0.f,
+                      (byte >> (sh + 3)) & 1u ? 1.f : 0.f);
+    }
+    reinterpret_cast<float4*>(out)[env * per_env + r] = v;
+  }
+}
+
 // per-env state hash for large-N parity checks (matches oracle orc_state_hash)
 __global__ void k_state_hash(DevBatch b, uint64_t* out) {
   const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -936,7 +995,7 @@ cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_rese
   k_step_gen<<<gen_blocks, GEN_WPB * 32, gen_sm, side>>>(b, actions, auto_reset, 0);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if ((e = cudaEventRecord(ev_join, side)) != cudaSuccess) return e;
-  k_step_player<<<blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, actions, auto_reset);
+  k_step_player<<<b.player_blocks > 0 ? std::min(blocks, b.player_blocks) : blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, actions, auto_reset);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   int mon_blocks = b.mon_warps / WARPS_PER_BLOCK;
   if (mon_blocks > blocks) mon_blocks = blocks;
@@ -966,7 +1025,13 @@ cudaError_t launch_test_move_enemy(const DevBatch& b, int64_t env, int fx, int f
 }
 cudaError_t launch_encode(const DevBatch& b, int mode, uint32_t flag, int with_hist, int channels, float* out,
                           cudaStream_t s) {
-  k_encode<<<(unsigned)b.n, 256, 0, s>>>(b, mode, flag, with_hist, channels, out);
+  if (mode == 0 && (b.C & 3) == 0) {
+    const int per_env = channels * (b.C / 4);
+    dim3 grid((unsigned)((b.n + GRAY_ENVS - 1) / GRAY_ENVS), (unsigned)((per_env + 255) / 256));
+    k_encode_gray<<<grid, 256, 0, s>>>(b, flag, channels, out);
+  } else {
+    k_encode<<<(unsigned)b.n, 256, 0, s>>>(b, mode, flag, with_hist, channels, out);
+  }
   return cudaGetLastError();
 }
 cudaError_t launch_complete_maps(const DevBatch& b, int64_t env_lo, int64_t env_hi, cudaStream_t s) {

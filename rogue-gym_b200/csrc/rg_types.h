@@ -144,6 +144,7 @@ struct DevBatch {
   uint32_t* mon_list;     // [N] envs with an active monster this step (player kernel -> monster kernel)
   uint32_t* mon_count;    // [0..1] list length by step parity, [2..3] the monster kernel's work cursor
   int32_t mon_warps;      // warps of the (grid-stride) monster kernel
+  int32_t player_blocks;  // > 0: the player kernel runs as that many persistent blocks (grid-stride); 0: one block per env
 };
 
 }  // namespace rg
