@@ -161,6 +161,16 @@ class RogueEnv(Env):
         with open(fname, "w") as f:
             f.write(self.game.dump_history())
 
+    def replay_actions(self, fname: str) -> Tuple[PlayerState, float, bool, dict]:
+        """Re-simulates an action history written by `save_actions` (or by the reference: the
+        `saved_inputs` JSON, core/src/lib.rs:357-375) from a fresh reset. Not in the reference, whose
+        `replay` is a terminal viewer; returns what `step` returns for the whole sequence."""
+        from rogue_gym_python._rogue_gym import keys_from_history
+        with open(fname, "r") as f:
+            keys = keys_from_history(f.read())
+        self.reset()
+        return self.step(keys.decode("ascii"))
+
     def replay(self, interval_ms: int = 100) -> None:
         raise RuntimeError("Currently replay is only supported on UNIX")  # TUI: out of scope here
 

@@ -36,6 +36,34 @@ def _input_code(key):
     return {"Act": {"s": "Search", ".": "NoOp", ">": "DownStair"}[ch]}
 
 
+_KEY_OF_DIR = {v: k for k, v in _DIRS.items()}
+
+
+def keys_from_history(text):
+    """Inverse of `dump_history`: the JSON list RunTime::saved_inputs_as_json writes (core/src/lib.rs:
+    357-375; entries like {"Act": {"Move": "RightUp"}} or {"Act": "Search"}, InputCode / Action of
+    core/src/input.rs:24-60) back to the ASCII keys of KeyMap::ai, so that a recorded episode - e.g.
+    the reference's data/learned/*/best-actions.json - can be re-simulated."""
+    entries = json.loads(text) if isinstance(text, (str, bytes)) else text
+    keys = bytearray()
+    for e in entries:
+        act = e.get("Act") if isinstance(e, dict) else None
+        if isinstance(act, dict) and len(act) == 1:
+            (kind, direction), = act.items()
+            key = _KEY_OF_DIR.get(direction)
+            if key is not None and kind == "Move":
+                keys.append(ord(key))
+                continue
+            if key is not None and kind == "MoveUntil":
+                keys.append(ord(key.upper()))
+                continue
+        elif act in ("Search", "NoOp", "DownStair"):
+            keys.append(ord({"Search": "s", "NoOp": ".", "DownStair": ">"}[act]))
+            continue
+        raise ValueError("unsupported entry in action history: %r (only what KeyMap::ai can produce is replayable)" % (e,))
+    return bytes(keys)
+
+
 class _Batch:
     """Owns one rg_batch handle."""
 

@@ -58,6 +58,23 @@ out = {
         "cmd_str": data.CMD_STR, "cmd_str5": data.CMD_STR5,
     },
 }
+# A recorded episode the reference ships (RunTime::saved_inputs_as_json format, core/src/lib.rs:357-375):
+# kept as its config plus the action list in the reference's own JSON shape, run-length encoded.
+_learned = "/root/reference/data/learned/ddqn-minidungeon"
+with open(os.path.join(_learned, "best-actions.json")) as f:
+    _acts = json.load(f)
+_rle = []
+for a in _acts:
+    if _rle and _rle[-1][0] == a:
+        _rle[-1][1] += 1
+    else:
+        _rle.append([a, 1])
+with open(os.path.join(_learned, "config.json")) as f:
+    _cfg = json.load(f)
+out["recorded_episode"] = {
+    "cite": "data/learned/ddqn-minidungeon/{best-actions,config}.json; format core/src/lib.rs:357-375, input.rs:24-60",
+    "config": _cfg, "n_actions": len(_acts), "actions_rle": _rle,
+}
 dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_fixtures.json")
 with open(dst, "w") as f:
     json.dump(out, f, indent=1)

@@ -57,6 +57,24 @@ def test_env_needs_the_gpu_and_says_so(cabi):
         RogueEnv(seed=1)
 
 
+def _recorded(fixtures):
+    fx = fixtures["recorded_episode"]
+    acts = [a for a, n in fx["actions_rle"] for _ in range(n)]
+    assert len(acts) == fx["n_actions"]
+    return fx["config"], acts
+
+
+def test_action_history_round_trip(fixtures):
+    from rogue_gym_python._rogue_gym import _input_code, keys_from_history
+    _, acts = _recorded(fixtures)
+    keys = keys_from_history(json.dumps(acts))
+    assert len(keys) == 1000 and set(keys) <= set(b"hjklyubn.s>")
+    assert [_input_code(k) for k in keys] == acts  # the writer side reproduces the reference's file
+    assert keys_from_history('[{"Act": {"MoveUntil": "Left"}}, {"Act": "NoOp"}]') == b"H."
+    with pytest.raises(ValueError):
+        keys_from_history('[{"Sys": "Quit"}]')
+
+
 # --------------------------------------------------------------------------- GPU: reference cases
 @pytest.fixture()
 def envs(gpu):
@@ -167,6 +185,28 @@ def test_save_actions_and_config(envs, tmp_path):
     assert json.load(open(tmp_path / "c.json")) == {"seed": 3, "hide_dungeon": True}
     with pytest.raises(RuntimeError):
         env.replay()
+
+
+@pytest.mark.gpu
+def test_recorded_episode_replays_like_the_oracle(envs, fixtures, oracle, tmp_path):
+    """data/learned/ddqn-minidungeon/best-actions.json (1 000 inputs, reference format) re-simulated on
+    the GPU from its own config: same final screen / status as the oracle, and dump_history gives
+    the file back."""
+    cfg, acts = _recorded(fixtures)
+    path = tmp_path / "best-actions.json"
+    path.write_text(json.dumps(acts))
+    env = envs.RogueEnv(config_dict=cfg, max_steps=2000)
+    state, reward, done, _ = env.replay_actions(str(path))
+    from rogue_gym_python._rogue_gym import keys_from_history
+    o = oracle.OracleEnv(cfg, max_steps=2000)
+    for k in keys_from_history(json.dumps(acts)):
+        o.react(k)
+    assert state.dungeon == o.dungeon()
+    assert list(state.status.values()) == [int(v) for v in o.obs()["status"]]
+    assert not done and reward == state.gold
+    assert json.loads(env.game.dump_history()) == acts
+    got = env.get_config()
+    assert got["dungeon"] == cfg["dungeon"] and got["enemies"] == cfg["enemies"] and got["seed"] == 5
 
 
 NUM_WORKERS = 8
