@@ -208,6 +208,8 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
   RG_TRY(dev_alloc(b, &d.message, N));
   RG_TRY(dev_alloc(b, &d.error, N));
   RG_TRY(dev_alloc(b, &d.errflag, 1));
+  RG_TRY(dev_alloc(b, &d.scr_rows, N));
+  RG_TRY(cudaMemsetAsync(d.scr_rows, 0xFF, N * 8, b->stream));
   RG_TRY(dev_alloc(b, &d.defer_list, N));
   RG_TRY(dev_alloc(b, &d.defer_count, 4));
   RG_TRY(dev_alloc(b, &d.full_path, N));
@@ -646,7 +648,7 @@ int rg_mirror_sync(rg_batch* b, uint64_t* bytes_to_host) {
   RG_CUDA(b, cudaMemsetAsync(b->m_count, 0, 8, b->stream));
   RG_CUDA(b, rg::launch_mirror(b->d, b->m_dev, b->m_hist_dev, b->ms_screen, b->ms_hist, b->ms_small, b->m_count,
                                b->sm_count, b->stream));
-  b->launches += 2;
+  b->launches += 1;
   RG_CUDA(b, cudaMemcpyAsync(b->h_count, b->m_count, 8, cudaMemcpyDeviceToHost, b->stream));
   int rc = rg_sync(b);  // drains the stream: the mirror is readable now
   if (bytes_to_host) *bytes_to_host = *b->h_count;

@@ -109,6 +109,7 @@ struct Ctx {
   int nx, ny, rsx, rsy, nrooms;
   uint8_t* g_screen;  // this env's slices in HBM
   uint8_t* g_hist;
+  uint64_t* g_rows;   // this env's "screen rows rewritten" mask for the host mirror (nullptr: not the live screen)
   uint32_t* g_walk;
   uint16_t* g_dist;
   uint32_t* g_bfs;    // per cache slot: frontier rows then visited rows of a suspended BFS
@@ -1492,6 +1493,7 @@ __device__ void compose(Ctx& c) {
     // written by the next compose, which therefore has to visit every row once more
     st->dirty_rows = c.hist_done ? ~0ull : 0ull;
     st->ov_rows = rows_now;
+    if (c.g_rows) *c.g_rows |= need;
   }
   __syncwarp();
 }

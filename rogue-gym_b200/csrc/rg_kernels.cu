@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "rg_device.cuh"
 #include "rg_launch.h"
@@ -100,6 +101,7 @@ RG_DEV void fill_ctx(const DevBatch& b, Ctx& c, Stager& sg, unsigned char* base,
   c.nrooms = c.nx * c.ny;
   c.g_screen = b.screen + env * b.CP;
   c.g_hist = b.hist + env * b.HB;
+  c.g_rows = b.scr_rows + env;
   c.g_walk = b.walk + env * (int64_t)(b.H * b.WW);
   c.g_dist = b.dist + env * (int64_t)NCACHE * b.CP;
   c.g_bfs = b.bfs + env * (int64_t)NCACHE * 2 * b.H * b.WW;
@@ -266,6 +268,7 @@ RG_DEV void swap_in_prefetched(const DevBatch& b, Ctx& c, int64_t env, int64_t s
   const uint32_t* w0 = b.sp_walk + sp * (int64_t)(b.H * b.WW);
   uint32_t* w1 = b.walk + env * (int64_t)(b.H * b.WW);
   for (int i = c.lane; i < b.H * b.WW; i += 32) w1[i] = w0[i];
+  if (c.lane == 0) b.scr_rows[env] = ~0ull;
   const uint4* e0 = reinterpret_cast<const uint4*>(b.sp_st + sp);
   uint4* e1 = reinterpret_cast<uint4*>(c.st);
   __syncwarp();
@@ -377,7 +380,12 @@ RG_DEV void player_env(const DevBatch& b, Stager& sg, unsigned char* base, int64
   if (b.full_path[env]) return;  // on k_step_scan's list: the whole step runs in k_step_gen, concurrently
   Ctx c;
   const uint8_t key = actions[env];
-  fill_ctx(b, c, sg, base, env, PL_BOTH);  // state and both planes in flight together (9 of 11 actions need them)
+  int d;
+  const int act = map_key(key, d);
+  // NoOp and DownStair-without-a-stair (descents went to k_step_gen) never look at the tile planes and
+  // never redraw: only the state is staged for them. Everything else gets state and both planes in
+  // flight together.
+  fill_ctx(b, c, sg, base, env, (act == 3 || act == 4) ? PL_NONE : PL_BOTH);
   EnvState* st = c.st;
   if (st->error == RG_ERR_PANIC || st->error == RG_ERR_SETTING) {  // the reference's worker is gone
     emit_obs(b, c, env, 0, st->error);
@@ -387,8 +395,6 @@ RG_DEV void player_env(const DevBatch& b, Stager& sg, unsigned char* base, int64
     emit_obs(b, c, env, 0, 0);
     return;
   }
-  int d;
-  const int act = map_key(key, d);
   if (act < 0) {  // ErrorKind::InvalidInput: nothing changes (core/src/lib.rs:322-327)
     emit_obs(b, c, env, 0, RG_ERR_INVALID_INPUT);
     return;
@@ -595,6 +601,7 @@ __global__ void __launch_bounds__(PF_MAX_WPB * 32, 1) k_prefetch(DevBatch b, int
       }
       if (c.st->episode != e0 + k - 1) break;  // the basis moved on under us: next pass
       c.g_screen = b.sp_screen + sp * b.CP;
+      c.g_rows = nullptr;  // a prefetched game's screen is not the live one (the swap-in marks every row)
       c.g_hist = b.sp_hist + sp * b.HB;
       c.g_walk = b.sp_walk + sp * (int64_t)(b.H * b.WW);
       reset_env(c);
@@ -870,7 +877,8 @@ __global__ void k_unpack_hist(DevBatch b, uint8_t* __restrict__ out) {
 // at 65 536 envs (PCIe-bound, ~2.4 ms) although a step changes a few cells per screen. The mirror is
 // pinned host memory mapped into the device address space; these kernels compare the device block with
 // a device-resident shadow of what the host already holds and store only the 16-byte pieces that
-// differ - to the shadow and, over PCIe, straight into the host buffer.
+// differ - to the shadow and, over PCIe, straight into the host buffer (measured: ~70 us of a step's
+// ~135 us mirror cost is the ~55 k small PCIe writes themselves).
 struct MirrorArgs {
   uint8_t* h_screen;     // host [N][C] dense
   uint8_t* h_hist;       // host [N][HB] bit-packed visited map
@@ -887,60 +895,67 @@ struct MirrorArgs {
 
 RG_DEV bool differs(const uint4& a, const uint4& b) { return ((a.x ^ b.x) | (a.y ^ b.y) | (a.z ^ b.z) | (a.w ^ b.w)) != 0u; }
 
-__global__ void __launch_bounds__(256) k_mirror_planes(DevBatch b, MirrorArgs m) {
-  const int per_env = b.CP / 16 + b.HB / 16;  // 16-byte pieces of one env: screen first, then history bits
-  const int64_t total = b.n * per_env;
+// One warp per env (grid-stride). Lanes 0-12 first check the env's scalars (status, reward, message,
+// done | error) against the shadow; then, compose() having recorded which rows of the screen / visited
+// map it rewrote (scr_rows), only the 16-byte pieces that overlap those rows are compared at all.
+__global__ void __launch_bounds__(256) k_mirror(DevBatch b, MirrorArgs m) {
+  const int lane = threadIdx.x & 31;
+  const int n_scr = b.CP / 16, n_hist = b.HB / 16;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   uint32_t sent = 0;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t env = t / per_env;
-    const int piece = (int)(t - env * per_env);
-    const bool is_screen = piece < b.CP / 16;
-    const int off = (is_screen ? piece : piece - b.CP / 16) * 16;
-    const uint8_t* cur_p = is_screen ? b.screen + env * b.CP + off : b.hist + env * b.HB + off;
-    uint8_t* sh_p = is_screen ? m.s_screen + env * b.CP + off : m.s_hist + env * b.HB + off;
-    const uint4 cur = *reinterpret_cast<const uint4*>(cur_p);
-    if (!differs(cur, *reinterpret_cast<const uint4*>(sh_p))) continue;
-    *reinterpret_cast<uint4*>(sh_p) = cur;
-    if (!is_screen) {
-      *reinterpret_cast<uint4*>(m.h_hist + env * b.HB + off) = cur;
-      sent += 16;
-    } else if ((b.C & 15) == 0) {
-      *reinterpret_cast<uint4*>(m.h_screen + env * (int64_t)b.C + off) = cur;
-      sent += 16;
-    } else {  // odd screen sizes: the dense host rows are not 16-byte aligned
-      const uint8_t* cb = reinterpret_cast<const uint8_t*>(&cur);
-      for (int k = 0; k < 16 && off + k < b.C; ++k) m.h_screen[env * (int64_t)b.C + off + k] = cb[k];
-      sent += (uint32_t)min(16, b.C - off);
+  for (int64_t env = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; env < b.n; env += warps) {
+    const uint64_t rows = b.scr_rows[env];
+    if (lane < 13) {
+      uint32_t v;
+      if (lane < 10) v = b.status[env * 10 + lane];
+      else if (lane == 10) v = (uint32_t)b.reward[env];
+      else if (lane == 11) v = b.message[env];
+      else v = (uint32_t)b.done[env] | ((uint32_t)b.error[env] << 8);
+      uint32_t* sh = m.s_small + env * 16 + lane;
+      if (v != *sh) {
+        *sh = v;
+        if (lane < 10) m.h_status[env * 10 + lane] = v;
+        else if (lane == 10) m.h_reward[env] = (int32_t)v;
+        else if (lane == 11) m.h_message[env] = v;
+        else {
+          m.h_done[env] = (uint8_t)v;
+          m.h_error[env] = (uint8_t)(v >> 8);
+        }
+        sent += lane == 12 ? 2 : 4;
+      }
     }
+    if (!rows) continue;
+    for (int piece = lane; piece < n_scr + n_hist; piece += 32) {
+      const bool is_screen = piece < n_scr;
+      const int off = (is_screen ? piece : piece - n_scr) * 16;
+      // cells covered: 16 per screen piece, 128 per piece of the bit-packed visited map
+      const int c0 = is_screen ? off : off * 8, c1 = min((is_screen ? off + 15 : off * 8 + 127), b.C - 1);
+      if (c0 >= b.C) continue;
+      const int r0 = c0 / b.W, r1 = c1 / b.W;
+      if (!((rows >> r0) & ((2ull << (r1 - r0)) - 1ull))) continue;
+      const uint8_t* cur_p = is_screen ? b.screen + env * b.CP + off : b.hist + env * b.HB + off;
+      uint8_t* sh_p = is_screen ? m.s_screen + env * b.CP + off : m.s_hist + env * b.HB + off;
+      const uint4 cur = *reinterpret_cast<const uint4*>(cur_p);
+      if (!differs(cur, *reinterpret_cast<const uint4*>(sh_p))) continue;
+      *reinterpret_cast<uint4*>(sh_p) = cur;
+      if (!is_screen) {
+        *reinterpret_cast<uint4*>(m.h_hist + env * b.HB + off) = cur;
+        sent += 16;
+      } else if ((b.C & 15) == 0) {
+        *reinterpret_cast<uint4*>(m.h_screen + env * (int64_t)b.C + off) = cur;
+        sent += 16;
+      } else {  // odd screen sizes: the dense host rows are not 16-byte aligned
+        const uint8_t* cb = reinterpret_cast<const uint8_t*>(&cur);
+        for (int k = 0; k < 16 && off + k < b.C; ++k) m.h_screen[env * (int64_t)b.C + off + k] = cb[k];
+        sent += (uint32_t)min(16, b.C - off);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) b.scr_rows[env] = 0ull;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sent += __shfl_xor_sync(RG_FULL, sent, o);
-  if ((threadIdx.x & 31) == 0 && sent) atomicAdd(m.bytes, (unsigned long long)sent);
-}
-
-__global__ void __launch_bounds__(256) k_mirror_small(DevBatch b, MirrorArgs m) {
-  const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t sent = 0;
-  if (env < b.n) {
-    uint32_t* sh = m.s_small + env * 16;
-    for (int i = 0; i < 10; ++i) {
-      const uint32_t v = b.status[env * 10 + i];
-      if (v != sh[i]) { sh[i] = v; m.h_status[env * 10 + i] = v; sent += 4; }
-    }
-    const uint32_t r = (uint32_t)b.reward[env], msg = b.message[env];
-    const uint32_t de = (uint32_t)b.done[env] | ((uint32_t)b.error[env] << 8);
-    if (r != sh[10]) { sh[10] = r; m.h_reward[env] = (int32_t)r; sent += 4; }
-    if (msg != sh[11]) { sh[11] = msg; m.h_message[env] = msg; sent += 4; }
-    if (de != sh[12]) {
-      sh[12] = de;
-      m.h_done[env] = (uint8_t)de;
-      m.h_error[env] = (uint8_t)(de >> 8);
-      sent += 2;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sent += __shfl_xor_sync(RG_FULL, sent, o);
-  if ((threadIdx.x & 31) == 0 && sent) atomicAdd(m.bytes, (unsigned long long)sent);
+  if (lane == 0 && sent) atomicAdd(m.bytes, (unsigned long long)sent);
 }
 
 // ---------------------------------------------------------------- launchers
@@ -1045,12 +1060,8 @@ cudaError_t launch_mirror(const DevBatch& b, const rg_host_obs& host, uint8_t* h
   m.h_screen = host.screen; m.h_hist = host_hist_bits; m.h_status = host.status; m.h_reward = host.reward;
   m.h_done = host.done; m.h_message = host.message; m.h_error = host.error;
   m.s_screen = s_screen; m.s_hist = s_hist; m.s_small = s_small; m.bytes = bytes;
-  const int64_t total = b.n * (b.CP / 16 + b.HB / 16);
-  int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count * 16);  // grid-stride, 16 blocks of 256 per SM
-  k_mirror_planes<<<blocks, 256, 0, s>>>(b, m);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  k_mirror_small<<<(unsigned)((b.n + 255) / 256), 256, 0, s>>>(b, m);
+  int blocks = (int)std::min<int64_t>((b.n + 7) / 8, (int64_t)sm_count * 8);  // a warp per env, grid-stride, 64 warps per SM
+  k_mirror<<<blocks, 256, 0, s>>>(b, m);
   return cudaGetLastError();
 }
 cudaError_t launch_seed(const DevBatch& b, const uint64_t* lo, const uint64_t* hi, int seeded, cudaStream_t s) {

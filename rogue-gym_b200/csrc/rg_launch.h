@@ -17,7 +17,7 @@ cudaError_t launch_test_move_enemy(const DevBatch& b, int64_t env, int fx, int f
 cudaError_t launch_encode(const DevBatch& b, int mode, uint32_t flag, int with_hist, int channels, float* out_dev,
                           cudaStream_t s);
 cudaError_t launch_complete_maps(const DevBatch& b, int64_t env_lo, int64_t env_hi, cudaStream_t s);
-// delta write-back of the observation block into the mapped host mirror (two kernels)
+// delta write-back of the observation block into the mapped host mirror (k_mirror)
 cudaError_t launch_mirror(const DevBatch& b, const rg_host_obs& host_dev_ptrs, uint8_t* host_hist_bits, uint8_t* s_screen,
                           uint8_t* s_hist, uint32_t* s_small, unsigned long long* bytes, int sm_count, cudaStream_t s);
 cudaError_t launch_seed(const DevBatch& b, const uint64_t* lo_dev, const uint64_t* hi_dev, int seeded, cudaStream_t s);

@@ -114,6 +114,7 @@ struct DevBatch {
   uint32_t* message;
   uint8_t* error;
   uint32_t* errflag;  // OR of all errors raised since the last rg_sync
+  uint64_t* scr_rows; // [N] bit r: row r of screen / history was rewritten since the host mirror last looked
   uint32_t* defer_list;   // [N] env id | DEFER_* : work handed to the full-path kernel k_step_gen
   uint32_t* defer_count;  // [2] ping-pong by step parity
   uint8_t* full_path;     // [N] 1 = this step of the env runs in k_step_gen (written by k_step_scan every step)
