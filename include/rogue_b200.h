@@ -170,8 +170,10 @@ int rg_parse_config(const char* json, rg_params* out, char* err, size_t err_len)
 int rg_validate_params(const rg_params* p, char* err, size_t err_len);
 
 /* ---- lifetime */
-/* n_cfg == 1 broadcasts cfg_json[0] to all envs; n_cfg == n_envs gives every env its own
- * JSON, which may differ in "seed" only (heterogeneous configs: SURVEY §8f-4, not yet). */
+/* n_cfg == 1 broadcasts cfg_json[0] to all envs; n_cfg == n_envs gives every env its own JSON
+ * (python/src/lib.rs:270-280). The configs of one batch must agree on width, height, room_num_x,
+ * room_num_y and the symbol count (memory layout, observation shape) and must all set or all omit
+ * "seed"; everything else - monsters, rates, gold, player, hide_dungeon, seed - may differ per env. */
 int rg_create(const char* const* cfg_json, int64_t n_cfg, int64_t n_envs, int64_t max_steps, int device,
               rg_batch** out);
 int rg_create_from_params(const rg_params* p, int64_t n_envs, int64_t max_steps, int device, rg_batch** out);

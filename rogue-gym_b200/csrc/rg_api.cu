@@ -110,6 +110,11 @@ bool same_except_seed(rg_params a, rg_params b) {
   a.seed_lo = b.seed_lo = a.seed_hi = b.seed_hi = 0;
   return memcmp(&a, &b, sizeof(a)) == 0;
 }
+// What the HBM layout and the observation shape depend on: these must agree across one batch.
+bool same_geometry(const rg_params& a, const rg_params& b) {
+  return a.width == b.width && a.height == b.height && a.room_num_x == b.room_num_x && a.room_num_y == b.room_num_y &&
+         a.symbols == b.symbols;
+}
 
 int invalidate_prefetched(rg_batch* b);
 
@@ -169,9 +174,33 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
     d.mon_warps = prop.multiProcessorCount * 16;  // grid-stride warps of the monster kernel
     if (const char* e = getenv("RG_PLAYER_BLOCKS")) d.player_blocks = atoi(e);
   }
-  RG_TRY(dev_alloc(b, &b->dP, 1));
-  RG_TRY(cudaMemcpy(b->dP, &P, sizeof(P), cudaMemcpyHostToDevice));
-  d.P = b->dP;
+  {  // per-env configs (python/src/lib.rs:270-280 builds every worker from its own JSON): the distinct
+     // parameter sets go into a table, every env carries an index into it
+    std::vector<rg_params> table(1, P);
+    std::vector<uint16_t> idx;
+    if (per_env) {
+      idx.assign(N, 0);
+      for (size_t i = 0; i < N; ++i) {
+        const rg_params& q = (*per_env)[i];
+        size_t k = 0;
+        while (k < table.size() && !same_except_seed(table[k], q)) ++k;
+        if (k == table.size()) {
+          if (table.size() >= 65535) return fail(set_err(b, RG_ERR_SETTING, "too many distinct configs in one batch"));
+          table.push_back(q);
+        }
+        idx[i] = (uint16_t)k;
+      }
+    }
+    RG_TRY(dev_alloc(b, &b->dP, table.size()));
+    RG_TRY(cudaMemcpy(b->dP, table.data(), table.size() * sizeof(rg_params), cudaMemcpyHostToDevice));
+    d.P = b->dP;
+    if (table.size() > 1) {
+      uint16_t* di = nullptr;
+      RG_TRY(dev_alloc(b, &di, N));
+      RG_TRY(cudaMemcpy(di, idx.data(), N * sizeof(uint16_t), cudaMemcpyHostToDevice));
+      d.cfg_idx = di;
+    }
+  }
   {  // Floor::cd_to_room_id (floor.rs:194-200) as a table: the sector grid of rooms.rs:176,191-206
     uint8_t lut[208];
     memset(lut, 0xFF, sizeof(lut));
@@ -413,9 +442,14 @@ int rg_create(const char* const* cfg_json, int64_t n_cfg, int64_t n_envs, int64_
   for (int64_t i = 1; i < n_cfg; ++i) {
     rc = rg_parse_config(cfg_json[i], &all[(size_t)i], ebuf, sizeof(ebuf));
     if (rc != RG_OK) return set_err(nullptr, rc, ebuf);
-    if (!same_except_seed(P, all[(size_t)i]))
+    if (!same_geometry(P, all[(size_t)i]))
       return set_err(nullptr, RG_ERR_SETTING,
-                     "Error in rogue-gym: Invalid Setting: configs of one batch may differ in `seed` only");
+                     "Error in rogue-gym: Invalid Setting: the configs of one batch must agree on width, height, "
+                     "room_num_x / room_num_y and the number of symbols (they fix the memory layout and the "
+                     "observation shape); everything else may differ per env");
+    char vbuf[256];
+    rc = rg_validate_params(&all[(size_t)i], vbuf, sizeof(vbuf));
+    if (rc != RG_OK) return set_err(nullptr, rc, vbuf);
   }
   return create_impl(P, &all, n_envs, max_steps, device, out);
 }

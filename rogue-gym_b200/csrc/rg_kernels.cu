@@ -93,7 +93,7 @@ RG_DEV void fill_ctx(const DevBatch& b, Ctx& c, Stager& sg, unsigned char* base,
   c.st = reinterpret_cast<EnvState*>(base + 2 * (size_t)b.CP);
   c.col_room = b.room_lut;
   c.row_room = b.room_lut + 160;
-  c.P = b.P;
+  c.P = b.cfg_idx ? b.P + b.cfg_idx[env] : b.P;
   c.W = b.W; c.H = b.H; c.C = b.C; c.CP = b.CP; c.WW = b.WW;
   c.lane = threadIdx.x & 31;
   c.nx = b.nx; c.ny = b.ny;
@@ -599,6 +599,7 @@ __global__ void __launch_bounds__(PF_MAX_WPB * 32, 1) k_prefetch(DevBatch b, int
         bb.st = b.sp_st;  // basis = the previous prefetched game
         fill_ctx(bb, c, sg, base, prev, PL_NONE);
       }
+      c.P = b.cfg_idx ? b.P + b.cfg_idx[env] : b.P;  // fill_ctx was given a ring slot, not the env, for k > 1
       if (c.st->episode != e0 + k - 1) break;  // the basis moved on under us: next pass
       c.g_screen = b.sp_screen + sp * b.CP;
       c.g_rows = nullptr;  // a prefetched game's screen is not the live one (the swap-in marks every row)

@@ -96,7 +96,8 @@ struct DevBatch {
   int32_t nx, ny, rsx, rsy;  // room grid and sector size (rooms.rs:176)
   int32_t gen_warps;         // warps of the (grid-stride) generation kernel
   int64_t max_steps;
-  const rg_params* P;  // device copy
+  const rg_params* P;  // device copy: one entry, or the table of distinct configs of a heterogeneous batch
+  const uint16_t* cfg_idx;  // [N] env -> entry of P, or nullptr when every env uses P[0]
   const uint8_t* room_lut;  // [160] sector column of x, then [48] sector row of y (0xFF = no sector)
   uint8_t* surface;
   uint8_t* attr;

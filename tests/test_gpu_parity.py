@@ -301,7 +301,7 @@ def test_parallel_semantics(gpu, oracle):
     pg2 = gpu.ParallelGameState(10, [json.dumps(dict(cfg, seed=s)) for s in (1, 2, 3)])
     for s, st in zip((1, 2, 3), pg2.states()):
         assert st.dungeon == oracle.OracleEnv(dict(cfg, seed=s)).dungeon()
-    with pytest.raises(RuntimeError, match="seed"):
+    with pytest.raises(RuntimeError, match="must agree on width"):
         gpu.ParallelGameState(10, [json.dumps(cfg), json.dumps(dict(cfg, width=40))])
     pg.close()
     with pytest.raises(RuntimeError, match="closed"):
@@ -413,3 +413,67 @@ def test_host_mirror_equals_full_copy(gpu, cfg_name):
     b.fetch()
     assert np.array_equal(arr["screen"].reshape(n, -1), b.screen) and np.array_equal(arr["done"], b.done)
     pg.close()
+
+
+# ---------------------------------------------------------------- heterogeneous batches
+@pytest.mark.gpu
+def test_per_env_configs(gpu, oracle):
+    """Every worker of the reference's ParallelGameState is built from its own JSON (python/src/lib.rs:
+    270-280). One batch here: four different configs with the same geometry, interleaved; every env must
+    follow the oracle built from ITS config, step by step."""
+    import json
+
+    from helpers import KEYS19, diff_obs
+    variants = [
+        {},
+        {"enemies": {"enemies": [0, 3, 7, 12, 25]}, "hide_dungeon": False},
+        {"dungeon": {"style": "rogue", "dark_level": 1, "maze_rate_inv": 3, "locked_door_rate_inv": 2,
+                     "hidden_passage_rate_inv": 5},
+         "item": {"gold": {"rate_inv": 1, "base": 200, "per_level": 50, "minimum": 10}}},
+        {"player": {"init_hp": 40, "hunger_time": 60}, "enemies": {"enemies": list(range(26)), "appear_rate_gold": 100,
+                                                                  "appear_rate_nogold": 100}},
+    ]
+    n, steps = 128, 160
+    cfgs = [variants[i % 4] for i in range(n)]
+    seeds = list(range(11, n + 11))
+    pg = gpu.ParallelGameState(60, [json.dumps(c) for c in cfgs])
+    pg.seed(seeds)
+    pg.reset()
+    b = pg._batch
+    obs = [oracle.OracleBatch(variants[k], n // 4, max_steps=60, seeds=seeds[k::4]) for k in range(4)]
+    for ob in obs:
+        ob.reset()
+    rng = np.random.RandomState(5)
+
+    def gather():
+        parts = [ob.obs() for ob in obs]
+        out = {}
+        for key in parts[0]:
+            full = np.zeros((n,) + parts[0][key].shape[1:], parts[0][key].dtype)
+            for k in range(4):
+                full[k::4] = parts[k][key]
+            out[key] = full
+        rc = np.zeros(n, np.int32)
+        for k in range(4):
+            rc[k::4] = obs[k].rc
+        return out, rc
+
+    for t in range(steps):
+        keys = KEYS19[rng.randint(0, len(KEYS19), size=n)]
+        try:
+            b.step(keys, True)
+        except RuntimeError as e:
+            assert getattr(e, "code", None) == 3  # a reference-panic state somewhere: sticky, compared below
+        for k in range(4):
+            obs[k].step(keys[k::4], True)
+        want, rc = gather()
+        live = (rc == 0) & (b.error == 0)
+        assert np.array_equal(rc == 3, b.error == 3), "panic sets differ at step %d" % t
+        bad = diff_obs(b, want, t, b.W, live)
+        assert not bad, "\n".join(bad)
+    assert live.sum() > n // 2
+    # variants are really different games
+    assert len({bytes(b.screen[i]) for i in range(4)}) > 1
+    pg.close()
+    with pytest.raises(RuntimeError, match="must agree on width"):
+        gpu.ParallelGameState(60, [json.dumps({}), json.dumps({"width": 64})])
