@@ -1450,10 +1450,28 @@ __device__ void compose(Ctx& c) {
   }
   const uint64_t need = st->dirty_rows | st->ov_rows | rows_now;
   const int lo = W, hi = (H - 1) * W;  // rows 0 and H-1 are never written (python/src/lib.rs:44)
-  for (int ch = c.lane; ch < c.CP / 16; ch += 32) {  // PARALLEL, 128-bit in / 128-bit out, 4 cells per op
+  // PARALLEL, 128-bit in / 128-bit out, 4 cells per op. When rows are whole 16-cell pieces (W % 16 == 0,
+  // e.g. 80 = 5 pieces) the pieces of the needed rows are dealt to the lanes densely, so a typical
+  // redraw (4-7 rows = 20-35 pieces) is one or two trips for the warp instead of four; otherwise every
+  // lane walks its own pieces and skips the ones that lie in clean rows.
+  const bool dense = (W & 15) == 0;
+  const int cpr = W >> 4;
+  const uint32_t need_lo = (uint32_t)need & (H >= 32 ? 0xFFFFFFFFu : ((1u << H) - 1u));
+  const uint32_t need_hi = H > 32 ? (uint32_t)(need >> 32) & ((1u << (H - 32)) - 1u) : 0u;
+  const int n_lo = __popc(need_lo);
+  const int items = dense ? (n_lo + __popc(need_hi)) * cpr : c.CP / 16;
+  for (int it = c.lane; it < items; it += 32) {
+    int ch = it;
+    if (dense) {
+      const int ri = it / cpr;
+      const int row = ri < n_lo ? (int)__fns(need_lo, 0, ri + 1) : 32 + (int)__fns(need_hi, 0, ri - n_lo + 1);
+      ch = row * cpr + (it - ri * cpr);
+    }
     const int base = ch * 16;
-    const int r0 = base / W, r1 = min(base + 15, c.C - 1) / W;  // a 16-cell piece lies in one or two rows
-    if (!(((need >> r0) | (need >> r1)) & 1ull)) continue;
+    if (!dense) {
+      const int r0 = base / W, r1 = min(base + 15, c.C - 1) / W;  // a 16-cell piece lies in one or two rows
+      if (!(((need >> r0) | (need >> r1)) & 1ull)) continue;
+    }
     const uint4 s4 = *reinterpret_cast<const uint4*>(S + base);
     const uint4 a4 = *reinterpret_cast<const uint4*>(A + base);
     const uint32_t sv[4] = {s4.x, s4.y, s4.z, s4.w}, av[4] = {a4.x, a4.y, a4.z, a4.w};

@@ -19,6 +19,10 @@ namespace rg {
 // done, so a warp that runs a BFS does not pin three finished neighbours (measured: 4 warps/block
 // 0.668 ms per step, 1 warp/block 0.626 ms at 64 registers, 65 536 envs).
 constexpr int WARPS_PER_BLOCK = RG_WPB;
+#ifndef RG_PLAYER_WPB
+#define RG_PLAYER_WPB 1
+#endif
+constexpr int PLAYER_WPB = RG_PLAYER_WPB;  // warps (= envs) per block of k_step_player
 // The generator kernels are the opposite case: ~15 k instructions of divergent code run by a few
 // hundred warps beside the step kernels. Spread one warp per SM they evict the step kernels' code from
 // every SM's instruction caches (measured: the player kernel takes 216 us instead of 140 us while a
@@ -62,8 +66,8 @@ RG_DEV void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
 enum { PL_NONE = 0, PL_S = 1, PL_A = 2, PL_BOTH = 3 };
-// Loads EnvState (+ the requested planes) of `env` into the warp's region and waits for them.
-RG_DEV void stage_load(const DevBatch& b, Stager& s, unsigned char* base, int64_t env, int planes) {
+// Starts the bulk loads of EnvState (+ the requested planes) of `env` into the warp's region.
+RG_DEV void stage_issue(const DevBatch& b, Stager& s, unsigned char* base, int64_t env, int planes) {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic accesses to this region first
   __syncwarp();
   if ((threadIdx.x & 31) == 0) {
@@ -73,6 +77,9 @@ RG_DEV void stage_load(const DevBatch& b, Stager& s, unsigned char* base, int64_
     if (planes & PL_S) bulk_g2s(smem_u32(base), b.surface + env * b.CP, (uint32_t)b.CP, s.bar);
     if (planes & PL_A) bulk_g2s(smem_u32(base + b.CP), b.attr + env * b.CP, (uint32_t)b.CP, s.bar);
   }
+}
+// Waits for the loads started by stage_issue.
+RG_DEV void stage_wait(Stager& s) {
   uint32_t ok;
   do {
     asm volatile(
@@ -83,10 +90,15 @@ RG_DEV void stage_load(const DevBatch& b, Stager& s, unsigned char* base, int64_
   } while (!ok);
   s.phase ^= 1u;
 }
+RG_DEV void stage_load(const DevBatch& b, Stager& s, unsigned char* base, int64_t env, int planes) {
+  stage_issue(b, s, base, env, planes);
+  stage_wait(s);
+}
 
 // Stage one env into shared memory and fill the context.
-RG_DEV void fill_ctx(const DevBatch& b, Ctx& c, Stager& sg, unsigned char* base, int64_t env, int planes) {
-  stage_load(b, sg, base, env, planes);
+RG_DEV void fill_ctx(const DevBatch& b, Ctx& c, Stager& sg, unsigned char* base, int64_t env, int planes,
+                     bool already_staged = false) {
+  if (!already_staged) stage_load(b, sg, base, env, planes);
   c.soff = (uint32_t)(base - rg_smem);
   c.S = base;
   c.A = base + b.CP;
@@ -374,54 +386,69 @@ __global__ void __launch_bounds__(256) k_step_scan(DevBatch b, const uint8_t* __
   b.defer_list[atomicAdd(b.defer_count + parity, 1u)] = (uint32_t)env;
 }
 
-// Player phase of one env (see k_step_player).
+// Player phase of one env (see k_step_player). With SYNC the warps of a block move through the phases
+// together (a block barrier before the action and before the finish): the kernel's top stall is
+// instruction fetch - 4 100 instructions against a 6 KB L0 / 32 KB L1.5 instruction cache - and warps
+// that run the same few hundred instructions at the same time share the fetches.
+template <bool SYNC>
 RG_DEV void player_env(const DevBatch& b, Stager& sg, unsigned char* base, int64_t env, const uint8_t* __restrict__ actions,
                        int auto_reset, int parity) {
-  if (b.full_path[env]) return;  // on k_step_scan's list: the whole step runs in k_step_gen, concurrently
+  // The env's state and both planes are requested first; the two small global reads that decide what
+  // to do with them (is the env on the full path? which key?) overlap with the bulk loads instead of
+  // preceding them. k_step_gen may be rewriting a full-path env right now: its data is loaded but never
+  // looked at.
+  const bool present = env < b.n;
+  uint8_t on_full_path = 1, key = 0;
+  if (present) {
+    stage_issue(b, sg, base, env, PL_BOTH);
+    on_full_path = b.full_path[env];
+    key = actions[env];
+    stage_wait(sg);
+  }
+  if (SYNC) __syncthreads();
   Ctx c;
-  const uint8_t key = actions[env];
-  int d;
-  const int act = map_key(key, d);
-  // NoOp and DownStair-without-a-stair (descents went to k_step_gen) never look at the tile planes and
-  // never redraw: only the state is staged for them. Everything else gets state and both planes in
-  // flight together.
-  fill_ctx(b, c, sg, base, env, (act == 3 || act == 4) ? PL_NONE : PL_BOTH);
-  EnvState* st = c.st;
-  if (st->error == RG_ERR_PANIC || st->error == RG_ERR_SETTING) {  // the reference's worker is gone
-    emit_obs(b, c, env, 0, st->error);
-    return;
+  int d = 0, act = 4;
+  // what is left to do for this env: 0 nothing, 1 report `err` only, 2 the normal path
+  int todo = 0;
+  uint8_t err = 0;
+  if (!on_full_path) {  // otherwise on k_step_scan's list: the whole step runs in k_step_gen, concurrently
+    act = map_key(key, d);
+    fill_ctx(b, c, sg, base, env, PL_BOTH, true);
+    EnvState* st = c.st;
+    todo = 1;
+    if (st->error == RG_ERR_PANIC || st->error == RG_ERR_SETTING) err = st->error;  // the reference's worker is gone
+    else if ((int64_t)st->steps > b.max_steps) err = 0;                           // state_impls.rs:52-54
+    else if (act < 0) err = RG_ERR_INVALID_INPUT;  // ErrorKind::InvalidInput: nothing changes (core/src/lib.rs:322-327)
+    else if (st->ui_dead) err = RG_ERR_IGNORED_INPUT;  // UiState::Mordal(Grave) + Act => IgnoredInput (core/src/lib.rs:314)
+    else todo = 2;
+    if (todo == 2) {
+      st->f_gold_before = st->status[1];
+      if (act == 0 || act == 2) {
+        process_action<true>(c, act, d);
+      } else if (act == 3) {
+        process_action<true>(c, act, d);  // NoDownStair: a turn passes, the grid is not consulted
+      }
+    }
   }
-  if ((int64_t)st->steps > b.max_steps) {  // state_impls.rs:52-54
-    emit_obs(b, c, env, 0, 0);
-    return;
+  if (SYNC) __syncthreads();
+  if (todo == 1) {
+    emit_obs(b, c, env, 0, err);
+  } else if (todo == 2) {
+    EnvState* st = c.st;
+    if (act != 4 && !c.panic && has_active_monster(c)) {
+      // hand over to the monster kernel: it runs the monster phase and then finishes the step
+      st->f_msg = c.msg;
+      st->f_flags = (uint8_t)((c.redraw ? SF_REDRAW : 0) | (c.status_upd ? SF_STATUS : 0));
+      if (c.lane == 0) b.mon_list[atomicAdd(b.mon_count + parity, 1u)] = (uint32_t)env;
+      count_event(b, c, RGS_MONSTER_ENVS);
+      close_env(b, c, env);
+    } else {
+      finish_env(b, c, env, auto_reset, parity);  // no monster moves this turn: the step ends here
+    }
   }
-  if (act < 0) {  // ErrorKind::InvalidInput: nothing changes (core/src/lib.rs:322-327)
-    emit_obs(b, c, env, 0, RG_ERR_INVALID_INPUT);
-    return;
-  }
-  if (st->ui_dead) {  // UiState::Mordal(Grave) + Act => IgnoredInput (core/src/lib.rs:314)
-    emit_obs(b, c, env, 0, RG_ERR_IGNORED_INPUT);
-    return;
-  }
-  st->f_gold_before = st->status[1];
-  if (act == 0 || act == 2) {
-    process_action<true>(c, act, d);
-  } else if (act == 3) {
-    process_action<true>(c, act, d);  // NoDownStair: a turn passes, the grid is not consulted
-  }
-  if (act != 4 && !c.panic && has_active_monster(c)) {
-    // hand over to the monster kernel: it runs the monster phase and then finishes the step
-    st->f_msg = c.msg;
-    st->f_flags = (uint8_t)((c.redraw ? SF_REDRAW : 0) | (c.status_upd ? SF_STATUS : 0));
-    if (c.lane == 0) b.mon_list[atomicAdd(b.mon_count + parity, 1u)] = (uint32_t)env;
-    count_event(b, c, RGS_MONSTER_ENVS);
-    close_env(b, c, env);
-    return;
-  }
-  finish_env(b, c, env, auto_reset, parity);  // no monster moves this turn: the step ends here
 }
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_HOT_MIN_BLOCKS)
+__global__ void __launch_bounds__(PLAYER_WPB * 32, RG_HOT_MIN_BLOCKS / PLAYER_WPB)
 k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset) {
   unsigned char* const smem = rg_smem;
   const int parity = (int)(*b.dstep & 1u);
@@ -429,8 +456,9 @@ k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset) {
   const int warp = threadIdx.x >> 5;
   unsigned char* const base = smem + (size_t)warp * warp_smem(b);
   Stager sg = stager_init(b, base);
-  for (int64_t env = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp; env < b.n; env += (int64_t)gridDim.x * WARPS_PER_BLOCK) {
-    player_env(b, sg, base, env, actions, auto_reset, parity);
+  // the trip count is the same for every warp of a block (the block barriers need that)
+  for (int64_t env0 = (int64_t)blockIdx.x * PLAYER_WPB; env0 < b.n; env0 += (int64_t)gridDim.x * PLAYER_WPB) {
+    player_env<(PLAYER_WPB > 1)>(b, sg, base, env0 + warp, actions, auto_reset, parity);
     __syncwarp();
   }
 }
@@ -974,7 +1002,7 @@ cudaError_t configure_kernels(const DevBatch& b) {
   size_t sm = block_smem(b);
   cudaError_t e = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_step_player, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  e = cudaFuncSetAttribute(k_step_player, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PLAYER_WPB * one_warp_smem(b)));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_step_monsters, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return e;
@@ -1011,7 +1039,11 @@ cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_rese
   k_step_gen<<<gen_blocks, GEN_WPB * 32, gen_sm, side>>>(b, actions, auto_reset, 0);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if ((e = cudaEventRecord(ev_join, side)) != cudaSuccess) return e;
-  k_step_player<<<b.player_blocks > 0 ? std::min(blocks, b.player_blocks) : blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, actions, auto_reset);
+  {
+    const int pblocks = (int)((b.n + PLAYER_WPB - 1) / PLAYER_WPB);
+    k_step_player<<<b.player_blocks > 0 ? std::min(pblocks, b.player_blocks) : pblocks, PLAYER_WPB * 32,
+                    PLAYER_WPB * one_warp_smem(b), s>>>(b, actions, auto_reset);
+  }
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   int mon_blocks = b.mon_warps / WARPS_PER_BLOCK;
   if (mon_blocks > blocks) mon_blocks = blocks;
