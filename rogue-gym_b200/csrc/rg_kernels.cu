@@ -372,8 +372,10 @@ __global__ void __launch_bounds__(256) k_step_scan(DevBatch b, const uint8_t* __
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // next step's counters
     b.defer_count[parity ^ 1] = 0;
     b.reset_count[parity ^ 1] = 0;
-    b.mon_count[parity ^ 1] = 0;
-    b.mon_count[2 + (parity ^ 1)] = 0;  // the monster kernel's work cursor
+    for (int k = 0; k < MAX_CHUNKS; ++k) {
+      b.mon_count[(parity ^ 1) * MAX_CHUNKS + k] = 0;
+      b.mon_count[(2 + (parity ^ 1)) * MAX_CHUNKS + k] = 0;  // the monster kernel's work cursor
+    }
   }
   const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= b.n) return;
@@ -392,12 +394,12 @@ __global__ void __launch_bounds__(256) k_step_scan(DevBatch b, const uint8_t* __
 // that run the same few hundred instructions at the same time share the fetches.
 template <bool SYNC>
 RG_DEV void player_env(const DevBatch& b, Stager& sg, unsigned char* base, int64_t env, const uint8_t* __restrict__ actions,
-                       int auto_reset, int parity) {
+                       int auto_reset, int parity, int chunk, int64_t lo, int64_t hi) {
   // The env's state and both planes are requested first; the two small global reads that decide what
   // to do with them (is the env on the full path? which key?) overlap with the bulk loads instead of
   // preceding them. k_step_gen may be rewriting a full-path env right now: its data is loaded but never
   // looked at.
-  const bool present = env < b.n;
+  const bool present = env < hi;
   uint8_t on_full_path = 1, key = 0;
   if (present) {
     stage_issue(b, sg, base, env, PL_BOTH);
@@ -439,7 +441,7 @@ RG_DEV void player_env(const DevBatch& b, Stager& sg, unsigned char* base, int64
       // hand over to the monster kernel: it runs the monster phase and then finishes the step
       st->f_msg = c.msg;
       st->f_flags = (uint8_t)((c.redraw ? SF_REDRAW : 0) | (c.status_upd ? SF_STATUS : 0));
-      if (c.lane == 0) b.mon_list[atomicAdd(b.mon_count + parity, 1u)] = (uint32_t)env;
+      if (c.lane == 0) b.mon_list[lo + atomicAdd(b.mon_count + parity * MAX_CHUNKS + chunk, 1u)] = (uint32_t)env;
       count_event(b, c, RGS_MONSTER_ENVS);
       close_env(b, c, env);
     } else {
@@ -449,27 +451,29 @@ RG_DEV void player_env(const DevBatch& b, Stager& sg, unsigned char* base, int64
 }
 
 __global__ void __launch_bounds__(PLAYER_WPB * 32, RG_HOT_MIN_BLOCKS / PLAYER_WPB)
-k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset) {
+k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset, int chunk) {
   unsigned char* const smem = rg_smem;
   const int parity = (int)(*b.dstep & 1u);
   TraceScope trace(b, TK_PLAYER);
   const int warp = threadIdx.x >> 5;
   unsigned char* const base = smem + (size_t)warp * warp_smem(b);
   Stager sg = stager_init(b, base);
+  const int64_t lo = b.n * chunk / b.chunks, hi = b.n * (chunk + 1) / b.chunks;  // this launch's piece of the env range
   // the trip count is the same for every warp of a block (the block barriers need that)
-  for (int64_t env0 = (int64_t)blockIdx.x * PLAYER_WPB; env0 < b.n; env0 += (int64_t)gridDim.x * PLAYER_WPB) {
-    player_env<(PLAYER_WPB > 1)>(b, sg, base, env0 + warp, actions, auto_reset, parity);
+  for (int64_t env0 = lo + (int64_t)blockIdx.x * PLAYER_WPB; env0 < hi; env0 += (int64_t)gridDim.x * PLAYER_WPB) {
+    player_env<(PLAYER_WPB > 1)>(b, sg, base, env0 + warp, actions, auto_reset, parity, chunk, lo, hi);
     __syncwarp();
   }
 }
 
 // actions::move_active_enemies (actions.rs:82-119) for the envs that have an active monster
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 16)
-k_step_monsters(DevBatch b, int auto_reset) {
+k_step_monsters(DevBatch b, int auto_reset, int chunk) {
   unsigned char* const smem = rg_smem;
   const int parity = (int)(*b.dstep & 1u);
   TraceScope trace(b, TK_MONSTERS);
-  const uint32_t count = b.mon_count[parity];
+  const int64_t lo = b.n * chunk / b.chunks;
+  const uint32_t count = b.mon_count[parity * MAX_CHUNKS + chunk];
   const int warp = threadIdx.x >> 5;
   unsigned char* const base = smem + (size_t)warp * warp_smem(b);
   Stager sg = stager_init(b, base);
@@ -477,10 +481,10 @@ k_step_monsters(DevBatch b, int auto_reset) {
   // and warps on SMs that also host a background generator block run slower
   for (;;) {
     uint32_t i = 0;
-    if ((threadIdx.x & 31) == 0) i = atomicAdd(b.mon_count + 2 + parity, 1u);
+    if ((threadIdx.x & 31) == 0) i = atomicAdd(b.mon_count + (2 + parity) * MAX_CHUNKS + chunk, 1u);
     i = __shfl_sync(RG_FULL, i, 0);
     if (i >= count) break;
-    const int64_t env = (int64_t)b.mon_list[i];
+    const int64_t env = (int64_t)b.mon_list[lo + i];
     Ctx c;
     fill_ctx(b, c, sg, base, env, PL_BOTH);  // surface for the moves, both planes if the step ends with a compose
     EnvState* st = c.st;
@@ -1023,8 +1027,8 @@ cudaError_t launch_reset(const DevBatch& b, cudaStream_t s) {
 // kernels, the synchronous-reset pass, the join, and the step counter. No per-step
 // arguments (the step parity lives on the device, the actions are read from a fixed buffer), so
 // the whole sequence is captured once into a CUDA graph and replayed with one launch per step.
-cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_reset, cudaStream_t s, cudaStream_t side,
-                        cudaEvent_t ev_fork, cudaEvent_t ev_join) {
+cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_reset, const StepStreams& q) {
+  cudaStream_t s = q.main;
   const int blocks = (int)((b.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
   const size_t sm = block_smem(b);
   int gen_blocks = (int)std::min<int64_t>(b.gen_warps / GEN_WPB, (b.n + GEN_WPB - 1) / GEN_WPB);
@@ -1034,26 +1038,40 @@ cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_rese
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   // full-path steps (descents, MoveUntil) are a few long serial chains: they start first, on the
   // high-priority side stream, and run beside the player and monster kernels
-  if ((e = cudaEventRecord(ev_fork, s)) != cudaSuccess) return e;
-  if ((e = cudaStreamWaitEvent(side, ev_fork, 0)) != cudaSuccess) return e;
-  k_step_gen<<<gen_blocks, GEN_WPB * 32, gen_sm, side>>>(b, actions, auto_reset, 0);
+  if ((e = cudaEventRecord(q.ev_fork, s)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(q.side, q.ev_fork, 0)) != cudaSuccess) return e;
+  k_step_gen<<<gen_blocks, GEN_WPB * 32, gen_sm, q.side>>>(b, actions, auto_reset, 0);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  if ((e = cudaEventRecord(ev_join, side)) != cudaSuccess) return e;
-  {
-    const int pblocks = (int)((b.n + PLAYER_WPB - 1) / PLAYER_WPB);
+  if ((e = cudaEventRecord(q.ev_join, q.side)) != cudaSuccess) return e;
+  // The env range goes through in `chunks` pieces: the monster kernel of piece k (a few thousand
+  // latency-bound warps) runs on its own high-priority stream beside the player kernel of piece k+1
+  // (a throughput kernel), so only the last piece's monster phase is exposed.
+  for (int k = 0; k < b.chunks; ++k) {
+    const int64_t lo = b.n * k / b.chunks, hi = b.n * (k + 1) / b.chunks;
+    const int pblocks = (int)((hi - lo + PLAYER_WPB - 1) / PLAYER_WPB);
+    if (pblocks <= 0) continue;
     k_step_player<<<b.player_blocks > 0 ? std::min(pblocks, b.player_blocks) : pblocks, PLAYER_WPB * 32,
-                    PLAYER_WPB * one_warp_smem(b), s>>>(b, actions, auto_reset);
+                    PLAYER_WPB * one_warp_smem(b), s>>>(b, actions, auto_reset, k);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    cudaStream_t ms = b.chunks > 1 ? q.mon : s;
+    if (b.chunks > 1) {
+      if ((e = cudaEventRecord(q.ev_chunk[k], s)) != cudaSuccess) return e;
+      if ((e = cudaStreamWaitEvent(q.mon, q.ev_chunk[k], 0)) != cudaSuccess) return e;
+    }
+    int mon_blocks = (int)std::min<int64_t>(b.mon_warps / WARPS_PER_BLOCK, (hi - lo + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    k_step_monsters<<<mon_blocks, WARPS_PER_BLOCK * 32, sm, ms>>>(b, auto_reset, k);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
-  if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  int mon_blocks = b.mon_warps / WARPS_PER_BLOCK;
-  if (mon_blocks > blocks) mon_blocks = blocks;
-  k_step_monsters<<<mon_blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, auto_reset);
-  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (b.chunks > 1) {
+    if ((e = cudaEventRecord(q.ev_mon, q.mon)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(s, q.ev_mon, 0)) != cudaSuccess) return e;
+  }
+  (void)blocks;
   if (auto_reset) {  // episode ends whose next game was not prefetched in time (normally none)
     k_step_gen<<<gen_blocks, GEN_WPB * 32, gen_sm, s>>>(b, actions, auto_reset, 1);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
-  if ((e = cudaStreamWaitEvent(s, ev_join, 0)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(s, q.ev_join, 0)) != cudaSuccess) return e;
   k_step_end<<<1, 32, 0, s>>>(b, auto_reset);
   return cudaGetLastError();
 }

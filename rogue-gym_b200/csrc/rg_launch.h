@@ -7,9 +7,16 @@
 namespace rg {
 cudaError_t configure_kernels(const DevBatch& b);
 cudaError_t launch_reset(const DevBatch& b, cudaStream_t s);
-// one env-step = player, monster, finish and full-path kernels (4 launches)
-cudaError_t launch_step(const DevBatch& b, const uint8_t* actions_dev, int auto_reset, cudaStream_t s, cudaStream_t side,
-                        cudaEvent_t ev_fork, cudaEvent_t ev_join);
+// streams and events one env-step is enqueued on (all owned by the batch)
+struct StepStreams {
+  cudaStream_t main;   // the batch's stream
+  cudaStream_t side;   // high priority: the full-path kernel
+  cudaStream_t mon;    // high priority: monster kernels when the env range is stepped in pieces
+  cudaEvent_t ev_fork, ev_join, ev_mon;
+  cudaEvent_t ev_chunk[MAX_CHUNKS];
+};
+// one env-step = scan, full-path kernel beside {player, monster} kernels per piece, reset pass, end
+cudaError_t launch_step(const DevBatch& b, const uint8_t* actions_dev, int auto_reset, const StepStreams& q);
 // background generation of next-episode games into the sp_* buffers; serves window `slot` of refill_win
 cudaError_t launch_prefetch(const DevBatch& b, int warps, int slot, cudaStream_t s);
 cudaError_t launch_test_move_enemy(const DevBatch& b, int64_t env, int fx, int fy, int tx, int ty, int* out3_dev,

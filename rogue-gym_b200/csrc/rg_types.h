@@ -21,6 +21,7 @@ namespace rg {
 constexpr int MAX_ROOMS = RG_MAX_ROOMS;
 constexpr int NCACHE = RG_DIST_CACHE;
 constexpr int SP_DEPTH = 2;  // prefetched next-episode games kept per env
+constexpr int MAX_CHUNKS = 8;  // pieces of the env range in one step (see launch_step)
 
 // Surface codes follow the reference's declaration order (rogue/mod.rs:137-146).
 enum : uint8_t { S_PASSAGE = 0, S_FLOOR = 1, S_WALLX = 2, S_WALLY = 3, S_STAIR = 4, S_DOOR = 5, S_TRAP = 6, S_NONE = 7 };
@@ -143,8 +144,9 @@ struct DevBatch {
   int32_t prefetch_every; // a background pass is kicked every k-th auto-reset step
   int32_t pf_wpb;         // warps per block of k_prefetch (0 = default)
   int32_t prefetch;       // 0 = off (every reset is generated synchronously by k_step_gen)
-  uint32_t* mon_list;     // [N] envs with an active monster this step (player kernel -> monster kernel)
-  uint32_t* mon_count;    // [0..1] list length by step parity, [2..3] the monster kernel's work cursor
+  uint32_t* mon_list;     // [N] envs with an active monster this step (player kernel -> monster kernel); chunk k's list starts at its first env id
+  uint32_t* mon_count;    // [2][MAX_CHUNKS] list lengths by step parity and chunk, then [2][MAX_CHUNKS] work cursors
+  int32_t chunks;         // the env range is stepped in this many pieces (player kernel k+1 beside monster kernel k)
   int32_t mon_warps;      // warps of the (grid-stride) monster kernel
   int32_t player_blocks;  // > 0: the player kernel runs as that many persistent blocks (grid-stride); 0: one block per env
 };
