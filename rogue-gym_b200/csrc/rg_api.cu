@@ -552,7 +552,7 @@ int rg_step(rg_batch* b, const uint8_t* actions_dev, int auto_reset) {
   } else {
     RG_CUDA(b, rg::launch_step(b->d, b->d_actions, auto_reset, b->step_streams()));
   }
-  b->launches += (auto_reset ? 4 : 3) + 2 * b->d.chunks;
+  b->launches += 3 + 2 * b->d.chunks;
   if (auto_reset && (b->auto_steps++ % b->prefetch_every) == 0)
     return kick_prefetch(b);  // refill the next-episode buffers consumed so far
   return RG_OK;

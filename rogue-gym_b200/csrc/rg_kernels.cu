@@ -547,10 +547,10 @@ RG_DEV void step_env_full(const DevBatch& b, Ctx& c, int64_t env, const uint8_t*
   close_env(b, c, env);
 }
 
-// Last kernel of a step: advances the step counter and, on the steps that kick a background pass,
-// fixes the window of refill requests that pass serves: [end of the previous window, current tail).
-__global__ void k_step_end(DevBatch b, int auto_reset) {
-  if (threadIdx.x != 0) return;
+// End of a step: advances the step counter and, on the steps that kick a background pass, fixes the
+// window of refill requests that pass serves: [end of the previous window, current tail). Runs in one
+// thread after every kernel of the step has finished.
+RG_DEV void step_end(const DevBatch& b, int auto_reset) {
   b.dstep[0] += 1u;
   if (!auto_reset || !b.prefetch) return;
   const uint32_t k = b.dstep[1]++;
@@ -559,10 +559,14 @@ __global__ void k_step_end(DevBatch b, int auto_reset) {
   win[0] = b.refill_ctl[2];
   win[1] = b.refill_ctl[2] = *reinterpret_cast<volatile uint32_t*>(b.refill_ctl);
 }
+__global__ void k_step_end(DevBatch b, int auto_reset) {
+  if (threadIdx.x == 0) step_end(b, auto_reset);
+}
 
 // Grid-stride over the full-path list; exits at once when the list is empty.
+// With `finalize` the last block to finish also does the end-of-step bookkeeping (one kernel boundary less).
 __global__ void __launch_bounds__(GEN_WPB * 32) k_step_gen(DevBatch b, const uint8_t* __restrict__ actions,
-                                                                  int auto_reset, int resets) {
+                                                                  int auto_reset, int resets, int finalize) {
   unsigned char* const smem = rg_smem;
   const int parity = (int)(*b.dstep & 1u);
   TraceScope trace(b, resets ? TK_RESETS : TK_FULL);
@@ -578,6 +582,17 @@ __global__ void __launch_bounds__(GEN_WPB * 32) k_step_gen(DevBatch b, const uin
     fill_ctx(b, c, sg, base, env, (item & DEFER_RESET) ? PL_NONE : PL_BOTH);
     step_env_full(b, c, env, actions, auto_reset, (item & DEFER_RESET) != 0);
     __syncwarp();
+  }
+  if (finalize) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(b.dstep + 2, 1u) == gridDim.x - 1) {  // every other block has finished (and read the parity)
+        b.dstep[2] = 0;
+        __threadfence();
+        step_end(b, auto_reset);
+      }
+    }
   }
 }
 
@@ -1040,7 +1055,7 @@ cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_rese
   // high-priority side stream, and run beside the player and monster kernels
   if ((e = cudaEventRecord(q.ev_fork, s)) != cudaSuccess) return e;
   if ((e = cudaStreamWaitEvent(q.side, q.ev_fork, 0)) != cudaSuccess) return e;
-  k_step_gen<<<gen_blocks, GEN_WPB * 32, gen_sm, q.side>>>(b, actions, auto_reset, 0);
+  k_step_gen<<<gen_blocks, GEN_WPB * 32, gen_sm, q.side>>>(b, actions, auto_reset, 0, 0);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if ((e = cudaEventRecord(q.ev_join, q.side)) != cudaSuccess) return e;
   // The env range goes through in `chunks` pieces: the monster kernel of piece k (a few thousand
@@ -1067,12 +1082,15 @@ cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_rese
     if ((e = cudaStreamWaitEvent(s, q.ev_mon, 0)) != cudaSuccess) return e;
   }
   (void)blocks;
-  if (auto_reset) {  // episode ends whose next game was not prefetched in time (normally none)
-    k_step_gen<<<gen_blocks, GEN_WPB * 32, gen_sm, s>>>(b, actions, auto_reset, 1);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  }
   if ((e = cudaStreamWaitEvent(s, q.ev_join, 0)) != cudaSuccess) return e;
-  k_step_end<<<1, 32, 0, s>>>(b, auto_reset);
+  if (auto_reset) {
+    // episode ends whose next game was not prefetched in time (normally none; with prefetching on, a
+    // small grid is enough), and the end-of-step bookkeeping in the last block to finish
+    const int rblocks = b.prefetch ? std::min(gen_blocks, 296) : gen_blocks;
+    k_step_gen<<<rblocks, GEN_WPB * 32, gen_sm, s>>>(b, actions, auto_reset, 1, 1);
+  } else {
+    k_step_end<<<1, 32, 0, s>>>(b, auto_reset);
+  }
   return cudaGetLastError();
 }
 cudaError_t launch_prefetch(const DevBatch& b, int warps, int slot, cudaStream_t s) {
