@@ -34,7 +34,7 @@ CONFIG = {}  # config-default: every field at its default ("{}" => default, core
 BYTES_PER_ENV_STEP = 7858
 # dram__bytes_read.sum + dram__bytes_write.sum of one steady-state step (scan + player + monsters + full-path
 # kernels) at 65 536 envs, from the ncu --set full capture summarised in profiles/r1_ncu_summary.md
-NCU_DRAM_BYTES_PER_STEP = 453.3e6
+NCU_DRAM_BYTES_PER_STEP = 403.9e6
 WORKLOAD = "65536 envs/GPU, config-default 80x24 (3x3 rooms, monsters, gold, visibility), random 11-action rollout, max_steps 1000, auto-reset"
 
 
@@ -314,7 +314,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_BYTES_PER_STEP if (n == ENVS_PER_GPU and not args.config_json) else None,
                          "kernel": "one step = CUDA graph of rg::k_step_scan -> k_step_player -> k_step_monsters (+ k_step_gen beside them); "
-                                   "k_step_player is the dominant kernel (ncu: 137 us of the ~195 us serial chain, 423 MB of the step's DRAM traffic)",
+                                   "k_step_player is the dominant kernel (ncu: 121 us of the ~173 us serial chain, 382 MB of the step's DRAM traffic)",
                          "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_source": peak_src,
                          "note": "achieved = algorithmic bytes of one step (7858 B x envs) / average step duration over the timed region "
                                  "(CUDA events on the batch's stream); traffic = dram read+write of the step's kernels from ncu --set full "
