@@ -30,12 +30,13 @@ struct rg_batch {
   cudaStream_t bg[2] = {nullptr, nullptr};  // background streams: k_prefetch passes alternate, so two can be in flight
   cudaStream_t side = nullptr;    // full-path steps, forked after the player kernel and joined at the end of the step
   cudaStream_t mon = nullptr;     // monster kernels of piece k beside the player kernel of piece k+1
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mon = nullptr;
+  cudaStream_t mir = nullptr;     // first host-mirror pass of a step
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mon = nullptr, ev_player = nullptr, ev_mir = nullptr;
   cudaEvent_t ev_chunk[rg::MAX_CHUNKS] = {};
   rg::StepStreams step_streams() const {
     rg::StepStreams q;
-    q.main = stream; q.side = side; q.mon = mon;
-    q.ev_fork = ev_fork; q.ev_join = ev_join; q.ev_mon = ev_mon;
+    q.main = stream; q.side = side; q.mon = mon; q.mir = mir;
+    q.ev_fork = ev_fork; q.ev_join = ev_join; q.ev_mon = ev_mon; q.ev_player = ev_player; q.ev_mir = ev_mir;
     for (int i = 0; i < rg::MAX_CHUNKS; ++i) q.ev_chunk[i] = ev_chunk[i];
     return q;
   }
@@ -48,7 +49,10 @@ struct rg_batch {
   int64_t auto_steps = 0;
   int64_t steps_launched = 0;
   bool use_graph = true;
-  cudaGraphExec_t graph[2] = {nullptr, nullptr};  // [auto_reset]
+  cudaGraphExec_t graph[2] = {nullptr, nullptr};    // [auto_reset]
+  cudaGraphExec_t graph_m[2] = {nullptr, nullptr};  // the same step with the two host-mirror passes
+  rg::MirrorArgs margs{};
+  int mirror_chunks = 1;  // pieces of the env range in a step that carries the host-mirror passes
   DevBatch d{};
   rg_params* dP = nullptr;
   uint8_t* d_actions = nullptr;
@@ -312,6 +316,9 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
     RG_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     RG_TRY(cudaStreamCreateWithPriority(&b->side, cudaStreamNonBlocking, hi));
     RG_TRY(cudaStreamCreateWithPriority(&b->mon, cudaStreamNonBlocking, hi));
+    RG_TRY(cudaStreamCreateWithFlags(&b->mir, cudaStreamNonBlocking));
+    RG_TRY(cudaEventCreateWithFlags(&b->ev_player, cudaEventDisableTiming));
+    RG_TRY(cudaEventCreateWithFlags(&b->ev_mir, cudaEventDisableTiming));
     RG_TRY(cudaEventCreateWithFlags(&b->ev_mon, cudaEventDisableTiming));
     for (int i = 0; i < rg::MAX_CHUNKS; ++i) RG_TRY(cudaEventCreateWithFlags(&b->ev_chunk[i], cudaEventDisableTiming));
     // measured at 65 536 envs: 1 piece 0.245 ms per step, 2 pieces 0.255, 4 pieces 0.278, 8 pieces 0.330 - every extra
@@ -319,6 +326,9 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
     d.chunks = 1;
     if (const char* e = getenv("RG_CHUNKS")) d.chunks = std::min(rg::MAX_CHUNKS, std::max(1, atoi(e)));
     if ((int64_t)d.chunks > b->n) d.chunks = 1;
+    b->mirror_chunks = b->n >= 8192 ? 2 : 1;
+    if (const char* e = getenv("RG_MIRROR_CHUNKS")) b->mirror_chunks = std::min(rg::MAX_CHUNKS, std::max(1, atoi(e)));
+    if ((int64_t)b->mirror_chunks > b->n) b->mirror_chunks = 1;
   }
   RG_TRY(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
   RG_TRY(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
@@ -479,8 +489,14 @@ void rg_destroy(rg_batch* b) {
     if (b->bg[i]) cudaStreamSynchronize(b->bg[i]);
   if (b->side) cudaStreamSynchronize(b->side);
   if (b->mon) cudaStreamSynchronize(b->mon);
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 2; ++i) {
     if (b->graph[i]) cudaGraphExecDestroy(b->graph[i]);
+    if (b->graph_m[i]) cudaGraphExecDestroy(b->graph_m[i]);
+  }
+  if (b->mir) cudaStreamSynchronize(b->mir);
+  if (b->mir) cudaStreamDestroy(b->mir);
+  if (b->ev_player) cudaEventDestroy(b->ev_player);
+  if (b->ev_mir) cudaEventDestroy(b->ev_mir);
   if (b->ev_fork) cudaEventDestroy(b->ev_fork);
   if (b->ev_join) cudaEventDestroy(b->ev_join);
   if (b->side) cudaStreamDestroy(b->side);
@@ -528,34 +544,52 @@ int rg_reset(rg_batch* b) {
   return RG_OK;
 }
 
-int rg_step(rg_batch* b, const uint8_t* actions_dev, int auto_reset) {
-  if (!b || !actions_dev) return set_err(b, RG_ERR_ARG, "rg_step: null argument");
+}  // extern "C"
+
+namespace {
+// One env-step on the batch's stream; with_mirror adds the host-mirror passes (rg_step_mirror).
+int step_impl(rg_batch* b, const uint8_t* actions_dev, int auto_reset, bool with_mirror) {
   RG_CUDA(b, cudaSetDevice(b->device));
   auto_reset = auto_reset ? 1 : 0;
+  const rg::MirrorArgs* mirror = with_mirror ? &b->margs : nullptr;
+  cudaGraphExec_t* graphs = with_mirror ? b->graph_m : b->graph;
+  // With the mirror the env range goes through in two pieces: the second piece's player kernel hides the
+  // first piece's mirror pass (measured at 65 536 envs: 348 us per synced step in one piece, 335 us in two,
+  // 341 us in three or four); without it one piece is fastest (see create_impl).
+  DevBatch d = b->d;
+  if (with_mirror) d.chunks = b->mirror_chunks;
   // the step kernels read the batch's own action buffer, so that the launch sequence has no
   // per-step argument and can be replayed as a graph
   if (actions_dev != b->d_actions)
     RG_CUDA(b, cudaMemcpyAsync(b->d_actions, actions_dev, (size_t)b->n, cudaMemcpyDeviceToDevice, b->stream));
   b->d.trace_step = (int32_t)(b->steps_launched++ % 512);
   if (b->use_graph) {
-    if (!b->graph[auto_reset]) {
+    if (!graphs[auto_reset]) {
       cudaGraph_t g = nullptr;
       RG_CUDA(b, cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
-      cudaError_t le = rg::launch_step(b->d, b->d_actions, auto_reset, b->step_streams());
+      cudaError_t le = rg::launch_step(d, b->d_actions, auto_reset, b->step_streams(), mirror, b->sm_count);
       cudaError_t ce = cudaStreamEndCapture(b->stream, &g);
       if (le != cudaSuccess) return cuda_fail(b, le, "launch_step (capture)");
       if (ce != cudaSuccess) return cuda_fail(b, ce, "cudaStreamEndCapture");
-      RG_CUDA(b, cudaGraphInstantiate(&b->graph[auto_reset], g, 0));
+      RG_CUDA(b, cudaGraphInstantiate(&graphs[auto_reset], g, 0));
       cudaGraphDestroy(g);
     }
-    RG_CUDA(b, cudaGraphLaunch(b->graph[auto_reset], b->stream));
+    RG_CUDA(b, cudaGraphLaunch(graphs[auto_reset], b->stream));
   } else {
-    RG_CUDA(b, rg::launch_step(b->d, b->d_actions, auto_reset, b->step_streams()));
+    RG_CUDA(b, rg::launch_step(d, b->d_actions, auto_reset, b->step_streams(), mirror, b->sm_count));
   }
-  b->launches += 3 + 2 * b->d.chunks;
+  b->launches += 3 + 2 * d.chunks + (with_mirror ? 1 + d.chunks : 0);
   if (auto_reset && (b->auto_steps++ % b->prefetch_every) == 0)
     return kick_prefetch(b);  // refill the next-episode buffers consumed so far
   return RG_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int rg_step(rg_batch* b, const uint8_t* actions_dev, int auto_reset) {
+  if (!b || !actions_dev) return set_err(b, RG_ERR_ARG, "rg_step: null argument");
+  return step_impl(b, actions_dev, auto_reset, false);
 }
 
 int rg_stats(rg_batch* b, uint64_t* out8) {
@@ -689,6 +723,10 @@ int rg_mirror_get(rg_batch* b, rg_host_obs* out, uint8_t** history_bits) {
     RG_CUDA(b, cudaMemsetAsync(b->m_count, 0, 8, b->stream));
     b->m_host = hp;
     b->m_bytes = total;
+    rg::MirrorArgs& m = b->margs;
+    m.h_screen = b->m_dev.screen; m.h_hist = b->m_hist_dev; m.h_status = b->m_dev.status; m.h_reward = b->m_dev.reward;
+    m.h_done = b->m_dev.done; m.h_message = b->m_dev.message; m.h_error = b->m_dev.error;
+    m.s_screen = b->ms_screen; m.s_hist = b->ms_hist; m.s_small = b->ms_small; m.bytes = b->m_count;
     int rc = rg_mirror_sync(b, nullptr);  // the mirror starts out current
     if (rc != RG_OK && rc != RG_ERR_PANIC && rc != RG_ERR_INVALID_INPUT && rc != RG_ERR_IGNORED_INPUT) return rc;
   }
@@ -702,8 +740,7 @@ int rg_mirror_sync(rg_batch* b, uint64_t* bytes_to_host) {
   if (!b->m_host) return set_err(b, RG_ERR_ARG, "rg_mirror_sync: call rg_mirror_get first");
   RG_CUDA(b, cudaSetDevice(b->device));
   RG_CUDA(b, cudaMemsetAsync(b->m_count, 0, 8, b->stream));
-  RG_CUDA(b, rg::launch_mirror(b->d, b->m_dev, b->m_hist_dev, b->ms_screen, b->ms_hist, b->ms_small, b->m_count,
-                               b->sm_count, b->stream));
+  RG_CUDA(b, rg::launch_mirror(b->d, b->margs, b->sm_count, b->stream));
   b->launches += 1;
   RG_CUDA(b, cudaMemcpyAsync(b->h_count, b->m_count, 8, cudaMemcpyDeviceToHost, b->stream));
   int rc = rg_sync(b);  // drains the stream: the mirror is readable now
@@ -716,9 +753,15 @@ int rg_step_mirror(rg_batch* b, const uint8_t* actions_host, int auto_reset, uin
   if (!b->m_host) return set_err(b, RG_ERR_ARG, "rg_step_mirror: call rg_mirror_get first");
   RG_CUDA(b, cudaSetDevice(b->device));
   RG_CUDA(b, cudaMemcpyAsync(b->d_actions, actions_host, (size_t)b->n, cudaMemcpyHostToDevice, b->stream));
-  int rc = rg_step(b, b->d_actions, auto_reset);
+  RG_CUDA(b, cudaMemsetAsync(b->m_count, 0, 8, b->stream));
+  // the step with its two mirror passes: most envs are written back beside the monster / full-path
+  // kernels, the rest after the step's last kernel
+  int rc = step_impl(b, b->d_actions, auto_reset, true);
   if (rc != RG_OK) return rc;
-  return rg_mirror_sync(b, bytes_to_host);
+  RG_CUDA(b, cudaMemcpyAsync(b->h_count, b->m_count, 8, cudaMemcpyDeviceToHost, b->stream));
+  rc = rg_sync(b);  // drains the stream: the mirror is readable now
+  if (bytes_to_host) *bytes_to_host = *b->h_count;
+  return rc;
 }
 
 void* rg_stream(rg_batch* b) { return b ? (void*)b->stream : nullptr; }

@@ -190,6 +190,7 @@ RG_DEV void defer(const DevBatch& b, Ctx& c, int64_t env, uint32_t code, int par
     atomicAdd(b.stats + (code ? RGS_SYNC_RESET : RGS_FULL_STEP), 1ull);
     // two lists: full-path steps are known after the player kernel (their kernel overlaps the monster
     // and finish kernels on a side stream), synchronous resets only after the finish kernel
+    if (code) b.full_path[env] = 3;  // finished by the reset pass: not yet final for the host mirror
     uint32_t* cnt = (code ? b.reset_count : b.defer_count) + parity;
     uint32_t* list = code ? b.reset_list : b.defer_list;
     list[atomicAdd(cnt, 1u)] = (uint32_t)env | code;
@@ -441,7 +442,10 @@ RG_DEV void player_env(const DevBatch& b, Stager& sg, unsigned char* base, int64
       // hand over to the monster kernel: it runs the monster phase and then finishes the step
       st->f_msg = c.msg;
       st->f_flags = (uint8_t)((c.redraw ? SF_REDRAW : 0) | (c.status_upd ? SF_STATUS : 0));
-      if (c.lane == 0) b.mon_list[lo + atomicAdd(b.mon_count + parity * MAX_CHUNKS + chunk, 1u)] = (uint32_t)env;
+      if (c.lane == 0) {
+        b.mon_list[lo + atomicAdd(b.mon_count + parity * MAX_CHUNKS + chunk, 1u)] = (uint32_t)env;
+        b.full_path[env] = 2;  // finished by the monster kernel
+      }
       count_event(b, c, RGS_MONSTER_ENVS);
       close_env(b, c, env);
     } else {
@@ -927,31 +931,24 @@ __global__ void k_unpack_hist(DevBatch b, uint8_t* __restrict__ out) {
 // a device-resident shadow of what the host already holds and store only the 16-byte pieces that
 // differ - to the shadow and, over PCIe, straight into the host buffer (measured: ~70 us of a step's
 // ~135 us mirror cost is the ~55 k small PCIe writes themselves).
-struct MirrorArgs {
-  uint8_t* h_screen;     // host [N][C] dense
-  uint8_t* h_hist;       // host [N][HB] bit-packed visited map
-  uint32_t* h_status;    // host [N][10]
-  int32_t* h_reward;     // host [N]
-  uint8_t* h_done;       // host [N]
-  uint32_t* h_message;   // host [N]
-  uint8_t* h_error;      // host [N]
-  uint8_t* s_screen;     // shadows, device: [N][CP]
-  uint8_t* s_hist;       // [N][HB]
-  uint32_t* s_small;     // [N][16]: status[10], reward, message, done | error << 8, 3 spare
-  unsigned long long* bytes;  // [1] bytes stored to the host since the counter was last cleared
-};
 
 RG_DEV bool differs(const uint4& a, const uint4& b) { return ((a.x ^ b.x) | (a.y ^ b.y) | (a.z ^ b.z) | (a.w ^ b.w)) != 0u; }
 
 // One warp per env (grid-stride). Lanes 0-12 first check the env's scalars (status, reward, message,
 // done | error) against the shadow; then, compose() having recorded which rows of the screen / visited
 // map it rewrote (scr_rows), only the 16-byte pieces that overlap those rows are compared at all.
-__global__ void __launch_bounds__(256) k_mirror(DevBatch b, MirrorArgs m) {
+// `pass`: 0 every env; 1 only the envs whose step was finished by the player kernel (full_path[] == 0) -
+// this pass runs beside the monster, full-path and reset kernels, which own the other envs; 2 only those others.
+__global__ void __launch_bounds__(256) k_mirror(DevBatch b, MirrorArgs m, int pass, int64_t env_lo, int64_t env_hi) {
   const int lane = threadIdx.x & 31;
   const int n_scr = b.CP / 16, n_hist = b.HB / 16;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   uint32_t sent = 0;
-  for (int64_t env = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; env < b.n; env += warps) {
+  for (int64_t env = env_lo + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); env < env_hi; env += warps) {
+    if (pass) {
+      const bool early = b.full_path[env] == 0;
+      if (early != (pass == 1)) continue;
+    }
     const uint64_t rows = b.scr_rows[env];
     if (lane < 13) {
       uint32_t v;
@@ -1007,6 +1004,9 @@ __global__ void __launch_bounds__(256) k_mirror(DevBatch b, MirrorArgs m) {
 }
 
 // ---------------------------------------------------------------- launchers
+static int mirror_blocks(const DevBatch& b, int sm_count) {
+  return (int)std::min<int64_t>((b.n + 7) / 8, (int64_t)sm_count * 8);  // a warp per env, grid-stride, 64 warps per SM
+}
 static size_t one_warp_smem(const DevBatch& b) { return 2 * (size_t)b.CP + sizeof(EnvState) + 16; }
 static size_t block_smem(const DevBatch& b) { return (size_t)WARPS_PER_BLOCK * one_warp_smem(b); }
 static int pf_warps_per_block(const DevBatch& b) {
@@ -1042,7 +1042,8 @@ cudaError_t launch_reset(const DevBatch& b, cudaStream_t s) {
 // kernels, the synchronous-reset pass, the join, and the step counter. No per-step
 // arguments (the step parity lives on the device, the actions are read from a fixed buffer), so
 // the whole sequence is captured once into a CUDA graph and replayed with one launch per step.
-cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_reset, const StepStreams& q) {
+cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_reset, const StepStreams& q,
+                        const MirrorArgs* mirror, int sm_count) {
   cudaStream_t s = q.main;
   const int blocks = (int)((b.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
   const size_t sm = block_smem(b);
@@ -1069,13 +1070,26 @@ cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_rese
                     PLAYER_WPB * one_warp_smem(b), s>>>(b, actions, auto_reset, k);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     cudaStream_t ms = b.chunks > 1 ? q.mon : s;
+    if (b.chunks > 1 || mirror) {
+      if ((e = cudaEventRecord(q.ev_chunk[k], s)) != cudaSuccess) return e;  // this piece's player kernel is done
+    }
     if (b.chunks > 1) {
-      if ((e = cudaEventRecord(q.ev_chunk[k], s)) != cudaSuccess) return e;
       if ((e = cudaStreamWaitEvent(q.mon, q.ev_chunk[k], 0)) != cudaSuccess) return e;
     }
     int mon_blocks = (int)std::min<int64_t>(b.mon_warps / WARPS_PER_BLOCK, (hi - lo + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
     k_step_monsters<<<mon_blocks, WARPS_PER_BLOCK * 32, sm, ms>>>(b, auto_reset, k);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (mirror) {
+      // host mirror, first pass: the envs of this piece that the player kernel finished (most of them),
+      // beside the monster, full-path and reset kernels (and the next piece's player kernel) - the pass
+      // is dominated by small PCIe writes, not by SM work
+      if ((e = cudaStreamWaitEvent(q.mir, q.ev_chunk[k], 0)) != cudaSuccess) return e;
+      k_mirror<<<mirror_blocks(b, sm_count), 256, 0, q.mir>>>(b, *mirror, 1, lo, hi);
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+  }
+  if (mirror) {
+    if ((e = cudaEventRecord(q.ev_mir, q.mir)) != cudaSuccess) return e;
   }
   if (b.chunks > 1) {
     if ((e = cudaEventRecord(q.ev_mon, q.mon)) != cudaSuccess) return e;
@@ -1090,6 +1104,11 @@ cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_rese
     k_step_gen<<<rblocks, GEN_WPB * 32, gen_sm, s>>>(b, actions, auto_reset, 1, 1);
   } else {
     k_step_end<<<1, 32, 0, s>>>(b, auto_reset);
+  }
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (mirror) {  // second pass: the envs that were finished by the monster, full-path and reset kernels
+    if ((e = cudaStreamWaitEvent(s, q.ev_mir, 0)) != cudaSuccess) return e;
+    k_mirror<<<mirror_blocks(b, sm_count), 256, 0, s>>>(b, *mirror, 2, 0, b.n);
   }
   return cudaGetLastError();
 }
@@ -1123,14 +1142,8 @@ cudaError_t launch_complete_maps(const DevBatch& b, int64_t env_lo, int64_t env_
   k_complete_maps<<<(unsigned)(env_hi - env_lo), 32, one_warp_smem(b), s>>>(b, env_lo, env_hi);
   return cudaGetLastError();
 }
-cudaError_t launch_mirror(const DevBatch& b, const rg_host_obs& host, uint8_t* host_hist_bits, uint8_t* s_screen,
-                          uint8_t* s_hist, uint32_t* s_small, unsigned long long* bytes, int sm_count, cudaStream_t s) {
-  MirrorArgs m;
-  m.h_screen = host.screen; m.h_hist = host_hist_bits; m.h_status = host.status; m.h_reward = host.reward;
-  m.h_done = host.done; m.h_message = host.message; m.h_error = host.error;
-  m.s_screen = s_screen; m.s_hist = s_hist; m.s_small = s_small; m.bytes = bytes;
-  int blocks = (int)std::min<int64_t>((b.n + 7) / 8, (int64_t)sm_count * 8);  // a warp per env, grid-stride, 64 warps per SM
-  k_mirror<<<blocks, 256, 0, s>>>(b, m);
+cudaError_t launch_mirror(const DevBatch& b, const MirrorArgs& m, int sm_count, cudaStream_t s) {
+  k_mirror<<<mirror_blocks(b, sm_count), 256, 0, s>>>(b, m, 0, 0, b.n);
   return cudaGetLastError();
 }
 cudaError_t launch_seed(const DevBatch& b, const uint64_t* lo, const uint64_t* hi, int seeded, cudaStream_t s) {

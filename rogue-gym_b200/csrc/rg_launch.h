@@ -7,16 +7,34 @@
 namespace rg {
 cudaError_t configure_kernels(const DevBatch& b);
 cudaError_t launch_reset(const DevBatch& b, cudaStream_t s);
+// host mirror of the observation block (rg_mirror_get): where k_mirror reads shadows and writes the host
+struct MirrorArgs {
+  uint8_t* h_screen;     // host [N][C] dense
+  uint8_t* h_hist;       // host [N][HB] bit-packed visited map
+  uint32_t* h_status;    // host [N][10]
+  int32_t* h_reward;     // host [N]
+  uint8_t* h_done;       // host [N]
+  uint32_t* h_message;   // host [N]
+  uint8_t* h_error;      // host [N]
+  uint8_t* s_screen;     // shadows, device: [N][CP]
+  uint8_t* s_hist;       // [N][HB]
+  uint32_t* s_small;     // [N][16]: status[10], reward, message, done | error << 8, 3 spare
+  unsigned long long* bytes;  // [1] bytes stored to the host since the counter was last cleared
+};
+
 // streams and events one env-step is enqueued on (all owned by the batch)
 struct StepStreams {
   cudaStream_t main;   // the batch's stream
   cudaStream_t side;   // high priority: the full-path kernel
   cudaStream_t mon;    // high priority: monster kernels when the env range is stepped in pieces
-  cudaEvent_t ev_fork, ev_join, ev_mon;
+  cudaStream_t mir;    // first host-mirror pass, beside the monster / full-path / reset kernels
+  cudaEvent_t ev_fork, ev_join, ev_mon, ev_player, ev_mir;
   cudaEvent_t ev_chunk[MAX_CHUNKS];
 };
 // one env-step = scan, full-path kernel beside {player, monster} kernels per piece, reset pass, end
-cudaError_t launch_step(const DevBatch& b, const uint8_t* actions_dev, int auto_reset, const StepStreams& q);
+// `mirror` != nullptr adds the two host-mirror passes to the step (rg_step_mirror)
+cudaError_t launch_step(const DevBatch& b, const uint8_t* actions_dev, int auto_reset, const StepStreams& q,
+                        const MirrorArgs* mirror, int sm_count);
 // background generation of next-episode games into the sp_* buffers; serves window `slot` of refill_win
 cudaError_t launch_prefetch(const DevBatch& b, int warps, int slot, cudaStream_t s);
 cudaError_t launch_test_move_enemy(const DevBatch& b, int64_t env, int fx, int fy, int tx, int ty, int* out3_dev,
@@ -24,9 +42,8 @@ cudaError_t launch_test_move_enemy(const DevBatch& b, int64_t env, int fx, int f
 cudaError_t launch_encode(const DevBatch& b, int mode, uint32_t flag, int with_hist, int channels, float* out_dev,
                           cudaStream_t s);
 cudaError_t launch_complete_maps(const DevBatch& b, int64_t env_lo, int64_t env_hi, cudaStream_t s);
-// delta write-back of the observation block into the mapped host mirror (k_mirror)
-cudaError_t launch_mirror(const DevBatch& b, const rg_host_obs& host_dev_ptrs, uint8_t* host_hist_bits, uint8_t* s_screen,
-                          uint8_t* s_hist, uint32_t* s_small, unsigned long long* bytes, int sm_count, cudaStream_t s);
+// delta write-back of the whole observation block into the mapped host mirror (k_mirror, every env)
+cudaError_t launch_mirror(const DevBatch& b, const MirrorArgs& m, int sm_count, cudaStream_t s);
 cudaError_t launch_seed(const DevBatch& b, const uint64_t* lo_dev, const uint64_t* hi_dev, int seeded, cudaStream_t s);
 cudaError_t launch_unpack_hist(const DevBatch& b, uint8_t* out_dev, cudaStream_t s);
 cudaError_t launch_state_hash(const DevBatch& b, uint64_t* out_dev, cudaStream_t s);
