@@ -285,6 +285,7 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
       RG_TRY(dev_alloc(b, &d.sp_cancel, NS));
       d.prefetch_every = b->prefetch_every;
       if (const char* e = getenv("RG_PF_WPB")) d.pf_wpb = std::max(1, atoi(e));
+      if (const char* e = getenv("RG_PF_EXCLUSIVE")) d.pf_exclusive = atoi(e) != 0;
       {
         // a pass is a few hundred one-warp chains: at high priority it starts at once and costs the
         // step kernels next to nothing; at low priority it only runs in their gaps and falls behind

@@ -30,6 +30,7 @@ constexpr int PLAYER_WPB = RG_PLAYER_WPB;  // warps (= envs) per block of k_step
 // k_prefetch takes its warps per block from the launch (DevBatch::pf_wpb, at most PF_MAX_WPB and as many
 // as fit in shared memory). The full-path kernel handles ~10 envs per step: one warp per block, spread.
 constexpr int PF_MAX_WPB = 16;
+constexpr int PF_EXCLUSIVE_SMEM = 227 * 1024 - 4608;  // leaves less than one step-kernel block's worth (4.4 KB + 1 KB reserved)
 #ifndef RG_GEN_WPB
 #define RG_GEN_WPB 1
 #endif
@@ -170,7 +171,8 @@ struct TraceScope {
   unsigned long long* slot;
   RG_DEV TraceScope(const DevBatch& b, int kernel) {
     slot = nullptr;
-    if (b.trace && (blockIdx.x & 63) == 0 && threadIdx.x == 0) {
+    // the generator kernels are sampled in full: their few working blocks have consecutive indices and the slowest one matters
+    if (b.trace && ((blockIdx.x & 63) == 0 || kernel == TK_FULL || kernel == TK_RESETS) && threadIdx.x == 0) {
       slot = b.trace + ((size_t)(kernel == TK_PREFETCH ? b.trace_step : (int)(*b.dstep % 512u)) * 8 + kernel) * 2;
       atomicMin(slot, gtime());
     }
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_reset(DevBatch b) {
   unsigned char* const base = smem + (size_t)warp * warp_smem(b);
   Stager sg = stager_init(b, base);
   fill_ctx(b, c, sg, base, env, PL_NONE);
-  reset_env(c);
+  reset_env<true>(c);
   uint8_t err = 0;
   if (c.panic) {
     c.st->error = RG_ERR_PANIC;
@@ -508,7 +510,7 @@ RG_DEV void step_env_full(const DevBatch& b, Ctx& c, int64_t env, const uint8_t*
   EnvState* st = c.st;
   if (reset_only) {  // second half of a terminal step: finish_env left gold_before in reward[]
     const uint32_t gold_before = (uint32_t)b.reward[env];
-    reset_env(c);
+    reset_env<false>(c);
     uint8_t err = 0;
     if (c.panic) {
       st->error = RG_ERR_PANIC;
@@ -536,7 +538,7 @@ RG_DEV void step_env_full(const DevBatch& b, Ctx& c, int64_t env, const uint8_t*
     st->steps += 1;
     st->is_terminal = (c.dead || (int64_t)st->steps >= b.max_steps) ? 1 : 0;
     if (st->is_terminal && auto_reset) {
-      reset_env(c);
+      reset_env<false>(c);
       if (c.panic) {
         st->error = RG_ERR_PANIC;
         err = RG_ERR_PANIC;
@@ -656,7 +658,7 @@ __global__ void __launch_bounds__(PF_MAX_WPB * 32, 1) k_prefetch(DevBatch b, int
       c.g_rows = nullptr;  // a prefetched game's screen is not the live one (the swap-in marks every row)
       c.g_hist = b.sp_hist + sp * b.HB;
       c.g_walk = b.sp_walk + sp * (int64_t)(b.H * b.WW);
-      reset_env(c);
+      reset_env<true>(c);
       if (c.panic) c.st->error = RG_ERR_PANIC;
       compose(c);
       write_back(b, c, sp, true, true, b.sp_st, b.sp_surface, b.sp_attr);
@@ -1027,7 +1029,8 @@ cudaError_t configure_kernels(const DevBatch& b) {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_step_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GEN_WPB * one_warp_smem(b)));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_prefetch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pf_warps_per_block(b) * one_warp_smem(b)));
+  e = cudaFuncSetAttribute(k_prefetch, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           b.pf_exclusive ? PF_EXCLUSIVE_SMEM : (int)(pf_warps_per_block(b) * one_warp_smem(b)));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_complete_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one_warp_smem(b));
   if (e != cudaSuccess) return e;
@@ -1118,7 +1121,9 @@ cudaError_t launch_prefetch(const DevBatch& b, int warps, int slot, cudaStream_t
   int blocks = (warps > 0 ? warps : b.gen_warps) / PF_WPB;
   if (blocks > blocks_all) blocks = (int)blocks_all;
   if (blocks < 1) blocks = 1;
-  k_prefetch<<<blocks, PF_WPB * 32, PF_WPB * one_warp_smem(b), s>>>(b, slot);
+  // pf_exclusive: the block asks for (nearly) all of an SM's shared memory, so no step-kernel block shares
+  // the SM with it - the generator's code and the step kernels' code stop evicting each other
+  k_prefetch<<<blocks, PF_WPB * 32, b.pf_exclusive ? (size_t)PF_EXCLUSIVE_SMEM : PF_WPB * one_warp_smem(b), s>>>(b, slot);
   return cudaGetLastError();
 }
 cudaError_t launch_test_move_enemy(const DevBatch& b, int64_t env, int fx, int fy, int tx, int ty, int* out3,

@@ -143,6 +143,7 @@ struct DevBatch {
   uint32_t* sp_cancel;    // [N][SP_DEPTH] episode whose game must not be published: it was built synchronously
   int32_t prefetch_every; // a background pass is kicked every k-th auto-reset step
   int32_t pf_wpb;         // warps per block of k_prefetch (0 = default)
+  int32_t pf_exclusive;   // k_prefetch blocks take a whole SM each (see launch_prefetch)
   int32_t prefetch;       // 0 = off (every reset is generated synchronously by k_step_gen)
   uint32_t* mon_list;     // [N] envs with an active monster this step (player kernel -> monster kernel); chunk k's list starts at its first env id
   uint32_t* mon_count;    // [2][MAX_CHUNKS] list lengths by step parity and chunk, then [2][MAX_CHUNKS] work cursors
