@@ -60,6 +60,7 @@ struct rg_batch {
   uint64_t* d_u64 = nullptr;        // [2N] scratch: seeds / hashes
   int* d_out3 = nullptr;
   uint32_t* h_errflag = nullptr;    // pinned
+  uint8_t* h_actions = nullptr;     // pinned [N]: staging for rg_step_mirror's graph
   uint8_t* h_error = nullptr;       // pinned [N]
   // host mirror (rg_mirror_get): pinned + mapped host block, its device alias, and the shadows
   void* m_host = nullptr;
@@ -340,6 +341,7 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
   RG_TRY(dev_alloc(b, &b->d_u64, 2 * N));
   RG_TRY(dev_alloc(b, &b->d_out3, 4));
   RG_TRY(cudaMallocHost(&b->h_errflag, sizeof(uint32_t)));
+  RG_TRY(cudaMallocHost(&b->h_actions, N));
   RG_TRY(cudaMallocHost(&b->h_error, N));
   RG_TRY(cudaMemsetAsync(d.st, 0, N * sizeof(EnvState), b->stream));
   RG_TRY(cudaMemsetAsync(d.screen, ' ', N * d.CP, b->stream));
@@ -514,6 +516,7 @@ void rg_destroy(rg_batch* b) {
   if (b->m_host) cudaFreeHost(b->m_host);
   if (b->h_count) cudaFreeHost(b->h_count);
   if (b->h_errflag) cudaFreeHost(b->h_errflag);
+  if (b->h_actions) cudaFreeHost(b->h_actions);
   if (b->h_error) cudaFreeHost(b->h_error);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
@@ -568,7 +571,19 @@ int step_impl(rg_batch* b, const uint8_t* actions_dev, int auto_reset, bool with
     if (!graphs[auto_reset]) {
       cudaGraph_t g = nullptr;
       RG_CUDA(b, cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
-      cudaError_t le = rg::launch_step(d, b->d_actions, auto_reset, b->step_streams(), mirror, b->sm_count);
+      cudaError_t le = cudaSuccess;
+      if (with_mirror) {
+        // the host-facing step is one graph launch: actions from the pinned staging buffer, the counter
+        // cleared, the step with its mirror passes, the counter and the error flag back to the host
+        le = cudaMemcpyAsync(b->d_actions, b->h_actions, (size_t)b->n, cudaMemcpyHostToDevice, b->stream);
+        if (le == cudaSuccess) le = cudaMemsetAsync(b->m_count, 0, 8, b->stream);
+      }
+      if (le == cudaSuccess) le = rg::launch_step(d, b->d_actions, auto_reset, b->step_streams(), mirror, b->sm_count);
+      if (with_mirror && le == cudaSuccess) {
+        le = cudaMemcpyAsync(b->h_count, b->m_count, 8, cudaMemcpyDeviceToHost, b->stream);
+        if (le == cudaSuccess)
+          le = cudaMemcpyAsync(b->h_errflag, b->d.errflag, sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream);
+      }
       cudaError_t ce = cudaStreamEndCapture(b->stream, &g);
       if (le != cudaSuccess) return cuda_fail(b, le, "launch_step (capture)");
       if (ce != cudaSuccess) return cuda_fail(b, ce, "cudaStreamEndCapture");
@@ -577,7 +592,15 @@ int step_impl(rg_batch* b, const uint8_t* actions_dev, int auto_reset, bool with
     }
     RG_CUDA(b, cudaGraphLaunch(graphs[auto_reset], b->stream));
   } else {
+    if (with_mirror) {
+      RG_CUDA(b, cudaMemcpyAsync(b->d_actions, b->h_actions, (size_t)b->n, cudaMemcpyHostToDevice, b->stream));
+      RG_CUDA(b, cudaMemsetAsync(b->m_count, 0, 8, b->stream));
+    }
     RG_CUDA(b, rg::launch_step(d, b->d_actions, auto_reset, b->step_streams(), mirror, b->sm_count));
+    if (with_mirror) {
+      RG_CUDA(b, cudaMemcpyAsync(b->h_count, b->m_count, 8, cudaMemcpyDeviceToHost, b->stream));
+      RG_CUDA(b, cudaMemcpyAsync(b->h_errflag, b->d.errflag, sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
+    }
   }
   b->launches += 3 + 2 * d.chunks + (with_mirror ? 1 + d.chunks : 0);
   if (auto_reset && (b->auto_steps++ % b->prefetch_every) == 0)
@@ -753,16 +776,17 @@ int rg_step_mirror(rg_batch* b, const uint8_t* actions_host, int auto_reset, uin
   if (!b || !actions_host) return set_err(b, RG_ERR_ARG, "rg_step_mirror: null argument");
   if (!b->m_host) return set_err(b, RG_ERR_ARG, "rg_step_mirror: call rg_mirror_get first");
   RG_CUDA(b, cudaSetDevice(b->device));
-  RG_CUDA(b, cudaMemcpyAsync(b->d_actions, actions_host, (size_t)b->n, cudaMemcpyHostToDevice, b->stream));
-  RG_CUDA(b, cudaMemsetAsync(b->m_count, 0, 8, b->stream));
-  // the step with its two mirror passes: most envs are written back beside the monster / full-path
-  // kernels, the rest after the step's last kernel
+  // One graph launch: the actions go through a pinned staging buffer (the caller's array may be pageable
+  // and changes from call to call, a graph node needs a fixed source), then H2D, the step with its mirror
+  // passes - most envs are written back beside the monster / full-path kernels, the rest after the step's
+  // last kernel - and the byte counter and error flag back to the host.
+  memcpy(b->h_actions, actions_host, (size_t)b->n);
   int rc = step_impl(b, b->d_actions, auto_reset, true);
   if (rc != RG_OK) return rc;
-  RG_CUDA(b, cudaMemcpyAsync(b->h_count, b->m_count, 8, cudaMemcpyDeviceToHost, b->stream));
-  rc = rg_sync(b);  // drains the stream: the mirror is readable now
+  RG_CUDA(b, cudaStreamSynchronize(b->stream));  // the mirror is readable now
   if (bytes_to_host) *bytes_to_host = *b->h_count;
-  return rc;
+  if (*b->h_errflag == 0) return RG_OK;
+  return rg_sync(b);  // some env raised an error: report it like every other call
 }
 
 void* rg_stream(rg_batch* b) { return b ? (void*)b->stream : nullptr; }
