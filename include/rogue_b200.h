@@ -200,6 +200,20 @@ int rg_trace(rg_batch* b, uint64_t* out, int64_t* steps_launched);
 int rg_sync(rg_batch* b);          /* waits for the stream and raises per-env errors like the reference */
 int rg_views_get(rg_batch* b, rg_views* out);
 int rg_fetch(rg_batch* b, rg_host_obs* out);
+/* ---- trainer-facing step: everything a policy loop needs from one call, all on the device and on the
+ * batch's stream (what ParallelRogueEnv.step + StairRewardParallel + ImageSetting.expand per state do in
+ * Python: python/rogue_gym/envs/parallel.py:44-66, wrappers.py:44-64, rogue_env.py:84-98).
+ * action_idx_dev: [N] indices into the gym action table ". h j k l n b u y > s", index_bytes = 1, 4 or 8
+ * (uint8 / int32 / int64), or index_bytes = 0 for uint8 ASCII keys as rg_step takes them (capitals = move
+ * until blocked); an index outside 0..10 gives that env RG_ERR_INVALID_INPUT. obs_out_dev: f32
+ * [N][channels][H][W] image of the new state (mode / status_flag / with_hist as rg_encode; NULL = no image);
+ * reward_out_dev: f32 [N] = gold gained, plus stair_reward on the step an env gets deeper than the level
+ * last seen for it (NULL = skip). Steps with auto-reset; done / status / screen are in rg_views. */
+int rg_step_train(rg_batch* b, const void* action_idx_dev, int index_bytes, int mode, uint32_t status_flag, int with_hist,
+                  float* obs_out_dev, float* reward_out_dev, float stair_reward);
+/* Forget the levels rg_step_train has seen (call after rg_reset). */
+int rg_train_reset(rg_batch* b);
+
 /* ---- host mirror: the observation block kept current in HOST memory without copying it whole.
  * rg_mirror_get allocates (once) pinned host buffers that the device can write, owned by the batch and
  * valid until rg_destroy: out->screen [N][W*H], status, reward, done, message, error as in rg_host_obs;

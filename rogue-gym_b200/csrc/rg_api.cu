@@ -61,6 +61,7 @@ struct rg_batch {
   int* d_out3 = nullptr;
   uint32_t* h_errflag = nullptr;    // pinned
   uint8_t* h_actions = nullptr;     // pinned [N]: staging for rg_step_mirror's graph
+  int32_t* d_level_seen = nullptr;  // [N] deepest level rg_step_train has seen per env (lazily allocated)
   uint8_t* h_error = nullptr;       // pinned [N]
   // host mirror (rg_mirror_get): pinned + mapped host block, its device alias, and the shadows
   void* m_host = nullptr;
@@ -701,6 +702,49 @@ int rg_views_get(rg_batch* b, rg_views* out) {
   out->done = b->d.done;
   out->message = b->d.message;
   out->error = b->d.error;
+  return RG_OK;
+}
+
+static int ensure_level_seen(rg_batch* b) {
+  if (b->d_level_seen) return RG_OK;
+  RG_CUDA(b, dev_alloc(b, &b->d_level_seen, (size_t)b->n));
+  std::vector<int32_t> ones((size_t)b->n, 1);
+  RG_CUDA(b, cudaMemcpyAsync(b->d_level_seen, ones.data(), ones.size() * 4, cudaMemcpyHostToDevice, b->stream));
+  RG_CUDA(b, cudaStreamSynchronize(b->stream));
+  return RG_OK;
+}
+
+int rg_train_reset(rg_batch* b) {
+  if (!b) return set_err(b, RG_ERR_ARG, "rg_train_reset: null batch");
+  RG_CUDA(b, cudaSetDevice(b->device));
+  if (b->d_level_seen) {
+    std::vector<int32_t> ones((size_t)b->n, 1);
+    RG_CUDA(b, cudaMemcpyAsync(b->d_level_seen, ones.data(), ones.size() * 4, cudaMemcpyHostToDevice, b->stream));
+    RG_CUDA(b, cudaStreamSynchronize(b->stream));
+  }
+  return RG_OK;
+}
+
+int rg_step_train(rg_batch* b, const void* action_idx_dev, int index_bytes, int mode, uint32_t status_flag, int with_hist,
+                  float* obs_out_dev, float* reward_out_dev, float stair_reward) {
+  if (!b || !action_idx_dev) return set_err(b, RG_ERR_ARG, "rg_step_train: null argument");
+  if (index_bytes != 0 && index_bytes != 1 && index_bytes != 4 && index_bytes != 8)
+    return set_err(b, RG_ERR_ARG, "rg_step_train: index_bytes must be 0 (ASCII keys), 1, 4 or 8");
+  RG_CUDA(b, cudaSetDevice(b->device));
+  RG_CUDA(b, rg::launch_keys_from_index(b->d, action_idx_dev, index_bytes, b->d_actions, b->stream));
+  b->launches += 1;
+  int rc = step_impl(b, b->d_actions, 1, false);
+  if (rc != RG_OK) return rc;
+  if (obs_out_dev) {
+    rc = rg_encode(b, mode, status_flag, with_hist, obs_out_dev, nullptr);
+    if (rc != RG_OK) return rc;
+  }
+  if (reward_out_dev) {
+    rc = ensure_level_seen(b);
+    if (rc != RG_OK) return rc;
+    RG_CUDA(b, rg::launch_train_reward(b->d, stair_reward, b->d_level_seen, reward_out_dev, b->stream));
+    b->launches += 1;
+  }
   return RG_OK;
 }
 

@@ -885,6 +885,37 @@ __global__ void __launch_bounds__(256) k_encode_gray(DevBatch b, uint32_t flag, 
   }
 }
 
+// ---------------------------------------------------------------- trainer-facing step (rg_step_train)
+// Before the step: gym action index -> ASCII key (RogueEnv.ACTIONS, python/rogue_gym/envs/rogue_env.py:159-172).
+__global__ void __launch_bounds__(256) k_keys_from_index(DevBatch b, const void* __restrict__ idx, int index_bytes,
+                                                         uint8_t* __restrict__ keys) {
+  const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= b.n) return;
+  if (index_bytes == 0) {  // already ASCII keys
+    keys[env] = reinterpret_cast<const uint8_t*>(idx)[env];
+    return;
+  }
+  long long a = index_bytes == 8 ? reinterpret_cast<const long long*>(idx)[env]
+              : index_bytes == 4 ? (long long)reinterpret_cast<const int*>(idx)[env]
+                                 : (long long)reinterpret_cast<const uint8_t*>(idx)[env];
+  // an index outside the table becomes a key outside the key map: the env reports InvalidInput, as
+  // ParallelRogueEnv.step raises for it
+  keys[env] = (a >= 0 && a < 11) ? (uint8_t)".hjklnbuy>s"[a] : (uint8_t)'?';
+}
+// After the step: float reward = gold gained (+ stair bonus when the env is deeper than the level remembered
+// for it; the remembered level follows the env, so it is 1 again after an auto-reset:
+// StairRewardParallel, python/rogue_gym/envs/wrappers.py:44-64).
+__global__ void __launch_bounds__(256) k_train_reward(DevBatch b, float stair_reward, int32_t* __restrict__ level_seen,
+                                                      float* __restrict__ reward_out) {
+  const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= b.n) return;
+  float r = (float)b.reward[env];
+  const int32_t level = (int32_t)b.status[env * 10];
+  if (level > level_seen[env]) r += stair_reward;
+  level_seen[env] = level;
+  reward_out[env] = r;
+}
+
 // per-env state hash for large-N parity checks (matches oracle orc_state_hash)
 __global__ void k_state_hash(DevBatch b, uint64_t* out) {
   const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1149,6 +1180,14 @@ cudaError_t launch_complete_maps(const DevBatch& b, int64_t env_lo, int64_t env_
 }
 cudaError_t launch_mirror(const DevBatch& b, const MirrorArgs& m, int sm_count, cudaStream_t s) {
   k_mirror<<<mirror_blocks(b, sm_count), 256, 0, s>>>(b, m, 0, 0, b.n);
+  return cudaGetLastError();
+}
+cudaError_t launch_keys_from_index(const DevBatch& b, const void* idx, int index_bytes, uint8_t* keys, cudaStream_t s) {
+  k_keys_from_index<<<(unsigned)((b.n + 255) / 256), 256, 0, s>>>(b, idx, index_bytes, keys);
+  return cudaGetLastError();
+}
+cudaError_t launch_train_reward(const DevBatch& b, float stair_reward, int32_t* level_seen, float* reward_out, cudaStream_t s) {
+  k_train_reward<<<(unsigned)((b.n + 255) / 256), 256, 0, s>>>(b, stair_reward, level_seen, reward_out);
   return cudaGetLastError();
 }
 cudaError_t launch_seed(const DevBatch& b, const uint64_t* lo, const uint64_t* hi, int seeded, cudaStream_t s) {

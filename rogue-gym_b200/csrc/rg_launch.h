@@ -44,6 +44,10 @@ cudaError_t launch_encode(const DevBatch& b, int mode, uint32_t flag, int with_h
 cudaError_t launch_complete_maps(const DevBatch& b, int64_t env_lo, int64_t env_hi, cudaStream_t s);
 // delta write-back of the whole observation block into the mapped host mirror (k_mirror, every env)
 cudaError_t launch_mirror(const DevBatch& b, const MirrorArgs& m, int sm_count, cudaStream_t s);
+// trainer-facing step: action index -> key before the step, float reward (+ stair bonus) after it
+cudaError_t launch_keys_from_index(const DevBatch& b, const void* idx_dev, int index_bytes, uint8_t* keys_dev, cudaStream_t s);
+cudaError_t launch_train_reward(const DevBatch& b, float stair_reward, int32_t* level_seen_dev, float* reward_out_dev,
+                                cudaStream_t s);
 cudaError_t launch_seed(const DevBatch& b, const uint64_t* lo_dev, const uint64_t* hi_dev, int seeded, cudaStream_t s);
 cudaError_t launch_unpack_hist(const DevBatch& b, uint8_t* out_dev, cudaStream_t s);
 cudaError_t launch_state_hash(const DevBatch& b, uint64_t* out_dev, cudaStream_t s);

@@ -88,8 +88,6 @@ class DeviceRogueEnv:
         self.channels = int(self._L.rg_encode_channels(h, *self._enc))
         self.obs = torch.empty((n, self.channels, v.height, v.width), dtype=torch.float32, device=self.device)
         self.reward = torch.zeros(n, dtype=torch.float32, device=self.device)
-        self._levels = torch.ones(n, dtype=torch.int32, device=self.device)
-        self._keys = torch.tensor([ord(a) for a in self.ACTIONS], dtype=torch.uint8, device=self.device)
         self._stream = torch.cuda.ExternalStream(int(self._L.rg_stream(h)), device=self.device)
         if seeds is not None:
             self.seed(seeds)
@@ -128,24 +126,26 @@ class DeviceRogueEnv:
         self._alive()
         cur = self._enter()
         _cabi.check(self._L.rg_reset(self._h), self._h)
+        _cabi.check(self._L.rg_train_reset(self._h), self._h)
         self._observe()
         with self._torch.cuda.stream(self._stream):
-            self._levels.fill_(1)
             self.reward.zero_()
         cur.wait_stream(self._stream)
         return self.obs
 
     def step(self, actions):
-        """actions: integer tensor / array [N] of indices into ACTIONS."""
+        """actions: integer tensor / array [N] of indices into ACTIONS (uint8, int32 or int64 on the device
+        are used as they are). One C-ABI call (`rg_step_train`): index -> key, the step kernels, the image
+        encoder into `obs`, the float reward with the stair bonus - all on the batch's stream. An index
+        outside 0..10 leaves that env untouched and marks it in `error` (the reference raises ValueError)."""
         torch = self._torch
         self._alive()
         a = torch.as_tensor(actions, device=self.device)
         if a.shape != (self.num_envs,):
             raise ValueError("Invalid action: expected shape (%d,), got %s" % (self.num_envs, tuple(a.shape)))
-        cur = self._enter()
-        with torch.cuda.stream(self._stream):
-            keys = self._keys[a.long().clamp(0, self.ACTION_LEN - 1)]
-        return self._step_keys(keys, cur)
+        if a.dtype not in (torch.uint8, torch.int32, torch.int64):
+            a = a.long()
+        return self._step(a.contiguous(), a.element_size())
 
     def step_keys(self, keys):
         """keys: uint8 tensor / array [N] of ASCII keys (capitals = move until blocked)."""
@@ -154,18 +154,17 @@ class DeviceRogueEnv:
         k = torch.as_tensor(keys, device=self.device).to(torch.uint8).contiguous()
         if k.shape != (self.num_envs,):
             raise ValueError("Invalid action: expected shape (%d,), got %s" % (self.num_envs, tuple(k.shape)))
-        return self._step_keys(k, self._enter())
+        return self._step(k, 0)
 
-    def _step_keys(self, keys, cur):
-        torch = self._torch
-        with torch.cuda.stream(self._stream):
-            _cabi.check(self._L.rg_step(self._h, keys.data_ptr(), 1), self._h)
-            self._observe()
-            self.reward.copy_(self.gold_reward)
-            if self.stair_reward:
-                level = self.status[:, 0]
-                self.reward.add_((level > self._levels).to(torch.float32), alpha=self.stair_reward)
-                self._levels.copy_(level)  # follows the env, so it is 1 again after an auto-reset
+    def _step(self, a, index_bytes):
+        cur = self._enter()
+        # the kernels read `a` on the batch's stream: keep it alive until the next step instead of
+        # record_stream() (the batch owns that stream and destroys it in close(), which the caching
+        # allocator's bookkeeping for recorded streams does not survive at interpreter exit)
+        self._last_actions = a
+        _cabi.check(self._L.rg_step_train(self._h, a.data_ptr(), index_bytes, self._enc[0], self._enc[1],
+                                          self._enc[2], self.obs.data_ptr(), self.reward.data_ptr(),
+                                          C.c_float(self.stair_reward)), self._h)
         cur.wait_stream(self._stream)
         return self.obs, self.reward, self.done, {}
 
@@ -185,6 +184,7 @@ class DeviceRogueEnv:
         return self.error.cpu().numpy()
 
     def close(self) -> None:
+        self._last_actions = None
         if self._h:
             self._torch.cuda.synchronize(self.device)
             self._L.rg_destroy(self._h)

@@ -106,6 +106,8 @@ SYMBOLS = {
     "rg_trace": (_i, [_vp, _vp, _vp]),
     "rg_views_get": (_i, [_vp, C.POINTER(Views)]),
     "rg_fetch": (_i, [_vp, C.POINTER(HostObs)]),
+    "rg_step_train": (_i, [_vp, _vp, _i, _i, _u32, _i, _vp, _vp, C.c_float]),
+    "rg_train_reset": (_i, [_vp]),
     "rg_mirror_get": (_i, [_vp, C.POINTER(HostObs), C.POINTER(_vp)]),
     "rg_mirror_sync": (_i, [_vp, C.POINTER(C.c_uint64)]),
     "rg_step_mirror": (_i, [_vp, _vp, _i, C.POINTER(C.c_uint64)]),

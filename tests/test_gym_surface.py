@@ -302,6 +302,19 @@ def test_device_env_matches_list_api(envs, oracle, setting_args):
         assert np.array_equal(got_r, np.asarray(rewards, np.float32)), "reward differs at step %d" % t
         assert np.array_equal(got_d.astype(bool), np.asarray(dones)), "done differs at step %d" % t
     assert not dev.errors().any()
+    # ASCII keys (capitals = MoveUntil) go through the same fused call; an index outside the table only marks the env
+    keys = np.frombuffer(b"HJKLhjkl.s>", np.uint8)[np.arange(n) % 11]
+    states, rewards, dones, _ = ref.step("".join(chr(k) for k in keys))
+    obs, reward, done, _ = dev.step_keys(keys)
+    assert np.array_equal(obs.cpu().numpy(), ref.game.encode_states(states, *setting.encoder_args()))
+    assert np.array_equal(reward.cpu().numpy(), np.asarray(rewards, np.float32))
+    before = dev.screen.cpu().numpy().copy()
+    bad = np.zeros(n, np.int64)
+    bad[0] = 99
+    dev.step(bad)
+    assert dev.errors()[0] == 1 and np.array_equal(dev.screen.cpu().numpy()[0], before[0])
+    ref.step([0] * n)
+    states = ref.states
     scr = dev.screen.cpu().numpy()
     assert scr.shape == (n, 24, 80) and (scr == ord("@")).sum(axis=(1, 2)).max() == 1
     hist = dev.history().cpu().numpy()
