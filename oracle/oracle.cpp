@@ -1762,6 +1762,38 @@ double orc_batch_rollout(void** envs, int64_t n, int64_t first_env_id, int64_t t
   return std::chrono::duration<double>(t_end - t_start).count();
 }
 
+// ---- hooks for the reference's own unit-test known answers (fenwick.rs:262-305, passages.rs:272-296)
+// A set over [0, cap) holding `members`; returns nth(k) or -1. ops (nullable): per member 1 = insert, 2 = remove,
+// applied in order, with each call's bool result written back to ops_result.
+int64_t orc_test_ordset(uint64_t cap, const uint64_t* members, const uint8_t* ops, uint8_t* ops_result, int64_t n,
+                        int64_t k, uint64_t* len_out) {
+  OrdSet s((size_t)cap);
+  for (int64_t i = 0; i < n; ++i) {
+    bool r = (ops && ops[i] == 2) ? s.remove((size_t)members[i]) : s.insert((size_t)members[i]);
+    if (ops_result) ops_result[i] = r ? 1 : 0;
+  }
+  if (len_out) *len_out = s.len();
+  auto v = s.nth((size_t)k);
+  return v ? (int64_t)*v : -1;
+}
+int orc_test_ordset_from_range_contains(uint64_t lo, uint64_t hi, uint64_t e) {
+  return OrdSet::from_range((size_t)lo, (size_t)hi).contains((size_t)e) ? 1 : 0;
+}
+// passages::edges of the half-open rect x0..x1 x y0..y1; direction in enum-iterator order (Up 0, Down 1, Left 2,
+// Right 3); writes (x, y) pairs, returns how many.
+int orc_test_edges(int x0, int x1, int y0, int y1, int direction, int inclusive, int32_t* out_xy, int cap) {
+  Rect r{x0, y0, x1, y1};
+  auto v = edges(r, direction, inclusive != 0);
+  int n = 0;
+  for (Coord c : v) {
+    if (n >= cap) break;
+    out_xy[2 * n] = c.x;
+    out_xy[2 * n + 1] = c.y;
+    ++n;
+  }
+  return (int)v.size();
+}
+
 // ---- batch helpers for lock-step parity tests (no reference counterpart)
 void orc_batch_step(void** envs, int64_t n, const uint8_t* keys, int auto_reset, int threads, int32_t* rc_out) {
   if (threads < 1) threads = 1;

@@ -134,6 +134,11 @@ int orc_test_move_enemy(void* env, int fx, int fy, int tx, int ty, int* nx, int*
 double orc_batch_rollout(void** envs, int64_t n, int64_t first_env_id, int64_t t0, int64_t steps,
                          int threads, int compose_only_on_redraw, uint64_t* digest);
 uint64_t orc_state_hash(void* env);
+/* hooks for the reference's own unit tests (fenwick.rs:262-305, passages.rs:272-296) */
+int64_t orc_test_ordset(uint64_t cap, const uint64_t* members, const uint8_t* ops, uint8_t* ops_result, int64_t n,
+                        int64_t k, uint64_t* len_out);
+int orc_test_ordset_from_range_contains(uint64_t lo, uint64_t hi, uint64_t e);
+int orc_test_edges(int x0, int x1, int y0, int y1, int direction, int inclusive, int32_t* out_xy, int cap);
 
 /* Lock-step helpers for the parity tests: one call steps / resets / reads n envs. */
 void orc_batch_step(void** envs, int64_t n, const uint8_t* keys, int auto_reset, int threads, int32_t* rc_out);

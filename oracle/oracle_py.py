@@ -289,8 +289,29 @@ def lib():
         L.orc_batch_reset.argtypes = [C.POINTER(vp), C.c_int64, C.c_int, vp]
         L.orc_batch_get_obs.argtypes = [C.POINTER(vp), C.c_int64, vp, vp, vp, vp, vp]
         L.orc_batch_hash.argtypes = [C.POINTER(vp), C.c_int64, vp]
+        L.orc_test_ordset.restype = C.c_int64
+        L.orc_test_ordset.argtypes = [C.c_uint64, vp, vp, vp, C.c_int64, C.c_int64, C.POINTER(C.c_uint64)]
+        L.orc_test_ordset_from_range_contains.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
+        L.orc_test_edges.argtypes = [C.c_int] * 6 + [vp, C.c_int]
         _lib = L
     return _lib
+
+
+def ordset_nth(cap, members, k, ops=None):
+    """FenwickSet restatement: apply insert (1) / remove (2) ops for `members`, return (nth(k) or None, len, results)."""
+    m = np.asarray(members, np.uint64)
+    o = np.ones(len(m), np.uint8) if ops is None else np.asarray(ops, np.uint8)
+    res = np.zeros(len(m), np.uint8)
+    n_out = C.c_uint64()
+    v = lib().orc_test_ordset(cap, m.ctypes.data, o.ctypes.data, res.ctypes.data, len(m), k, C.byref(n_out))
+    return (None if v < 0 else int(v)), int(n_out.value), res.astype(bool)
+
+
+def edges(x0, x1, y0, y1, direction, inclusive):
+    """passages::edges of a half-open rect; direction 0 Up, 1 Down, 2 Left, 3 Right. List of (x, y)."""
+    out = np.zeros((512, 2), np.int32)
+    n = lib().orc_test_edges(x0, x1, y0, y1, direction, int(inclusive), out.ctypes.data, 512)
+    return [tuple(int(v) for v in p) for p in out[:n]]
 
 
 class OracleError(RuntimeError):

@@ -104,3 +104,36 @@ def test_batch_rollout_is_deterministic(oracle):
             b.step(oracle.synthetic_actions(t, ids))
         digests.append(b.hashes())
     assert np.array_equal(digests[0], digests[1])
+
+
+# ---------------------------------------------------------------- the reference's own unit-test known answers
+def test_fenwick_set_known_answers(oracle):
+    """core/src/fenwick.rs:262-305 (tests `nth`, `invalid_value`, `from_range`) restated on the oracle's set."""
+    cap = 1_000_000
+    odd = [i for i in range(1000) if i % 2 == 1]
+    assert oracle.ordset_nth(cap, odd, 9)[0] == 19
+    assert oracle.ordset_nth(cap, odd, 499)[0] == 999
+    v, n, _ = oracle.ordset_nth(cap, odd, 500)
+    assert v is None and n == 500
+    # out-of-range members are refused by insert and by remove
+    bad = list(range(cap, cap + 10))
+    _, n, res = oracle.ordset_nth(cap, bad + bad, 0, ops=[1] * 10 + [2] * 10)
+    assert n == 0 and not res.any()
+    # a second insert of the same member is refused, a remove of a present one succeeds
+    _, n, res = oracle.ordset_nth(100, [5, 5, 7, 5, 5], 0, ops=[1, 1, 1, 2, 2])
+    assert res.tolist() == [True, False, True, True, False] and n == 1
+    L = oracle.lib()
+    for i in range(0, 1000, 7):
+        assert bool(L.orc_test_ordset_from_range_contains(40, 500, i)) == (40 <= i < 500)
+
+
+def test_inclusive_edges_known_answer(oracle):
+    """core/src/dungeon/rogue/passages.rs:272-296 `test_inclusive_edges`: rect x 5..10, y 6..9."""
+    UP, DOWN, LEFT, RIGHT = 0, 1, 2, 3
+    assert oracle.edges(5, 10, 6, 9, DOWN, True) == [(x, 8) for x in range(6, 9)]
+    assert oracle.edges(5, 10, 6, 9, UP, True) == [(x, 6) for x in range(6, 9)]
+    assert oracle.edges(5, 10, 6, 9, LEFT, True) == [(5, y) for y in range(7, 8)]
+    assert oracle.edges(5, 10, 6, 9, RIGHT, True) == [(9, y) for y in range(7, 8)]
+    # the non-inclusive form (maze exits, passages.rs:160-176) keeps the corners
+    assert oracle.edges(5, 10, 6, 9, DOWN, False) == [(x, 8) for x in range(5, 10)]
+    assert oracle.edges(5, 10, 6, 9, LEFT, False) == [(5, y) for y in range(6, 9)]
