@@ -190,8 +190,8 @@ RG_DEV void count_event(const DevBatch& b, const Ctx& c, int which) {
 RG_DEV void defer(const DevBatch& b, Ctx& c, int64_t env, uint32_t code, int parity) {
   if (c.lane == 0) {
     atomicAdd(b.stats + (code ? RGS_SYNC_RESET : RGS_FULL_STEP), 1ull);
-    // two lists: full-path steps are known after the player kernel (their kernel overlaps the monster
-    // and finish kernels on a side stream), synchronous resets only after the finish kernel
+    // two lists: full-path steps come from k_step_scan (their kernel runs beside the player and monster
+    // kernels on a side stream), synchronous resets are known only when finish_env has run
     if (code) b.full_path[env] = 3;  // finished by the reset pass: not yet final for the host mirror
     uint32_t* cnt = (code ? b.reset_count : b.defer_count) + parity;
     uint32_t* list = code ? b.reset_list : b.defer_list;
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(GEN_WPB * 32) k_step_gen(DevBatch b, const uin
 
 // Background generation of every env's NEXT episode (GameConfig::build for the seed its next reset
 // will use - fixed, or already derived for `seed: null` - core/src/lib.rs:157-165,193-228). Runs on
-// a second, low-priority stream concurrently with the step kernels, so the ~1000 dependent RNG
+// two alternating high-priority background streams concurrently with the step kernels, so the ~1000 dependent RNG
 // draws of a floor are off the step's critical path; finish_env moves the finished game in
 // when the episode ends. Ownership of a buffer is handed over through sp_state (0: this kernel
 // may write it, 1: the step kernels may read it), with a fence on each side.

@@ -120,9 +120,9 @@ struct DevBatch {
   uint32_t* defer_list;   // [N] env id | DEFER_* : work handed to the full-path kernel k_step_gen
   uint32_t* defer_count;  // [2] ping-pong by step parity
   uint8_t* full_path;     // [N] 1 = this step of the env runs in k_step_gen (written by k_step_scan every step)
-  uint32_t* reset_list;   // [N] terminal envs whose next game was not prefetched in time (k_step_finish -> k_step_gen)
+  uint32_t* reset_list;   // [N] terminal envs whose next game was not prefetched in time (finish_env -> reset pass of k_step_gen)
   uint32_t* reset_count;  // [2]
-  // "next episode" buffers, filled in the background by k_prefetch and swapped in by k_step_finish
+  // "next episode" buffers, filled in the background by k_prefetch and swapped in by finish_env
   // when an env's episode ends (sp_state: 0 = empty / being built, 1 = ready)
   uint8_t* sp_surface;    // [N][SP_DEPTH][CP]
   uint8_t* sp_attr;       // [N][SP_DEPTH][CP]
