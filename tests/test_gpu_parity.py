@@ -477,3 +477,25 @@ def test_per_env_configs(gpu, oracle):
     pg.close()
     with pytest.raises(RuntimeError, match="must agree on width"):
         gpu.ParallelGameState(60, [json.dumps({}), json.dumps({"width": 64})])
+
+
+# ---------------------------------------------------------------- sharding invariance
+@pytest.mark.gpu
+def test_shards_reproduce_the_single_batch(gpu):
+    """An env's trajectory depends only on its id (seed, action stream), never on which shard or batch
+    size it is stepped in: two shards of 160 envs give the state hashes of one batch of 320."""
+    from rogue_gym_python.rollout import Shard, synthetic_actions
+    n, steps = 320, 120
+    whole = Shard("{}", 0, n, max_steps=50)
+    parts = [Shard("{}", 0, n // 2, max_steps=50), Shard("{}", n // 2, n, max_steps=50)]
+    import torch
+    for t in range(steps):
+        for sh in [whole] + parts:
+            keys = torch.from_numpy(synthetic_actions(t, sh.env_ids)).cuda()
+            sh.step_device(keys.data_ptr())
+            sh.sync()
+    h = whole.hashes()
+    assert np.array_equal(h[: n // 2], parts[0].hashes()) and np.array_equal(h[n // 2:], parts[1].hashes())
+    assert np.array_equal(whole.errors()[n // 2:], parts[1].errors())
+    for sh in [whole] + parts:
+        sh.close()
