@@ -780,15 +780,23 @@ int rg_mirror_get(rg_batch* b, rg_host_obs* out, uint8_t** history_bits) {
     };
     fill(b->m_obs, b->m_hist_host, hp);
     fill(b->m_dev, b->m_hist_dev, dp);
-    RG_CUDA(b, dev_alloc(b, &b->ms_screen, N * d.CP));
-    RG_CUDA(b, dev_alloc(b, &b->ms_hist, N * d.HB));
-    RG_CUDA(b, dev_alloc(b, &b->ms_small, N * 16));
-    RG_CUDA(b, dev_alloc(b, &b->m_count, 1));
-    RG_CUDA(b, cudaMallocHost(&b->h_count, sizeof(uint64_t)));
-    RG_CUDA(b, cudaMemsetAsync(b->ms_screen, 0, N * d.CP, b->stream));
-    RG_CUDA(b, cudaMemsetAsync(b->ms_hist, 0, N * d.HB, b->stream));
-    RG_CUDA(b, cudaMemsetAsync(b->ms_small, 0, N * 64, b->stream));
-    RG_CUDA(b, cudaMemsetAsync(b->m_count, 0, 8, b->stream));
+    auto setup = [&]() -> cudaError_t {  // the shadows start zeroed, like the host block
+      cudaError_t e2;
+      if ((e2 = dev_alloc(b, &b->ms_screen, N * d.CP)) != cudaSuccess) return e2;
+      if ((e2 = dev_alloc(b, &b->ms_hist, N * d.HB)) != cudaSuccess) return e2;
+      if ((e2 = dev_alloc(b, &b->ms_small, N * 16)) != cudaSuccess) return e2;
+      if ((e2 = dev_alloc(b, &b->m_count, 1)) != cudaSuccess) return e2;
+      if (!b->h_count && (e2 = cudaMallocHost(&b->h_count, sizeof(uint64_t))) != cudaSuccess) return e2;
+      if ((e2 = cudaMemsetAsync(b->ms_screen, 0, N * d.CP, b->stream)) != cudaSuccess) return e2;
+      if ((e2 = cudaMemsetAsync(b->ms_hist, 0, N * d.HB, b->stream)) != cudaSuccess) return e2;
+      if ((e2 = cudaMemsetAsync(b->ms_small, 0, N * 64, b->stream)) != cudaSuccess) return e2;
+      return cudaMemsetAsync(b->m_count, 0, 8, b->stream);
+    };
+    e = setup();
+    if (e != cudaSuccess) {  // nothing half-built stays behind (the device pieces are freed with the batch)
+      cudaFreeHost(hp);
+      return cuda_fail(b, e, "rg_mirror_get: allocating the shadows");
+    }
     b->m_host = hp;
     b->m_bytes = total;
     rg::MirrorArgs& m = b->margs;
