@@ -125,15 +125,23 @@ __device__ void lay_rooms(Ctx& c, Rng& r, uint32_t level) {
       }
       __syncwarp();
     } else if (rm.kind == K_MAZE) {  // UNIFORM: each passage cell rolls gen_attr in index order
-      for (int y = rm.y0; y < rm.y1; ++y)
-        for (int x = rm.x0; x < rm.x1; ++x) {
-          int idx = y * W + x;
-          if (!(A[idx] & A_MARK)) continue;
+      // the marked cells are found 32 at a time (ballot); the draws stay serial, in ascending cell order
+      const int w = rm.x1 - rm.x0, total = w * (rm.y1 - rm.y0);
+      for (int base = 0; base < total; base += 32) {
+        const int k = base + c.lane;
+        int idx = -1;
+        if (k < total) idx = (rm.y0 + k / w) * W + rm.x0 + k % w;
+        uint32_t bal = __ballot_sync(RG_FULL, idx >= 0 && (A[idx] & A_MARK));
+        while (bal) {
+          const int cell = __shfl_sync(RG_FULL, idx, __ffs(bal) - 1);
+          bal &= bal - 1;
           uint8_t attr = 0;
           if (r.range32G(0, P.dark_level) < level && r.does_happenG(P.hidden_passage_rate_inv)) attr = A_HIDDEN;
-          S[idx] = S_PASSAGE;
-          A[idx] = A_MARK | attr;
+          S[cell] = S_PASSAGE;
+          A[cell] = A_MARK | attr;
         }
+        __syncwarp();
+      }
     }
   }
 }
@@ -189,24 +197,28 @@ __device__ void select_start_or_end(Ctx& c, Rng& r, int room, int d, int& ox, in
     bool horiz = (d == D_DOWN || d == D_UP);
     int fix = (d == D_DOWN) ? y1 - 1 : (d == D_UP) ? y0 : (d == D_RIGHT) ? x1 - 1 : x0;
     int lo = horiz ? x0 : y0, hi = horiz ? x1 : y1;
+    // PARALLEL: the passage cells on the line, 32 positions per ballot (a line is at most 160 cells long)
+    uint32_t bal[5] = {0, 0, 0, 0, 0};
     int cnt = 0;
-    for (int t = lo; t < hi; ++t) {
-      int x = horiz ? t : fix, y = horiz ? fix : t;
+    for (int q = 0; q < 5 && lo + 32 * q < hi; ++q) {
+      const int t = lo + 32 * q + c.lane;
+      const int x = horiz ? t : fix, y = horiz ? fix : t;
       // Maze::has_cd tests membership in the ORIGINAL range (maze.rs:25-31)
-      if (in_rect(rm, x, y) && (A[y * W + x] & A_MARK)) ++cnt;
+      const bool member = t < hi && in_rect(rm, x, y) && (A[y * W + x] & A_MARK);
+      bal[q] = __ballot_sync(RG_FULL, member);
+      cnt += __popc(bal[q]);
     }
     if (cnt) {
       int n = (int)r.range64G(0, (uint64_t)cnt);
-      for (int t = lo; t < hi; ++t) {
-        int x = horiz ? t : fix, y = horiz ? fix : t;
-        if (in_rect(rm, x, y) && (A[y * W + x] & A_MARK)) {
-          if (n == 0) {
-            ox = x;
-            oy = y;
-            return;
-          }
-          --n;
+      for (int q = 0; q < 5; ++q) {
+        const int pc = __popc(bal[q]);
+        if (n < pc) {
+          const int t = lo + 32 * q + nth_set_bit(bal[q], (uint32_t)n);
+          ox = horiz ? t : fix;
+          oy = horiz ? fix : t;
+          return;
         }
+        n -= pc;
       }
     }
     if (d == D_DOWN) --y1;
@@ -355,13 +367,22 @@ __device__ int select_in_room(Ctx& c, Rng& r, int room, int excl) {
   int cnt = (int)rm.ncells - (excl >= 0 ? 1 : 0);
   if (cnt <= 0) return -1;
   int n = (int)r.range64G(0, (uint64_t)cnt);
-  for (int y = rm.y0; y < rm.y1; ++y)
-    for (int x = rm.x0; x < rm.x1; ++x) {
-      int idx = y * W + x;
-      if (!(A[idx] & A_MARK) || idx == excl) continue;
-      if (n == 0) return idx;
-      --n;
+  // PARALLEL: the n-th marked cell in row-major order, 32 cells of the maze's rect per trip (one ballot,
+  // one popcount) instead of one cell per trip
+  const int w = rm.x1 - rm.x0, total = w * (rm.y1 - rm.y0);
+  for (int base = 0; base < total; base += 32) {
+    const int k = base + c.lane;
+    int idx = -1;
+    bool member = false;
+    if (k < total) {
+      idx = (rm.y0 + k / w) * W + rm.x0 + k % w;
+      member = (A[idx] & A_MARK) && idx != excl;
     }
+    const uint32_t bal = __ballot_sync(RG_FULL, member);
+    const int pc = __popc(bal);
+    if (n < pc) return __shfl_sync(RG_FULL, idx, nth_set_bit(bal, (uint32_t)n));
+    n -= pc;
+  }
   set_panic(c);
   return -1;
 }
