@@ -274,17 +274,21 @@ __device__ void connect_2rooms(Ctx& c, Rng& rd, Rng& ra, int r1, int r2, int d, 
 
 // Node::candidates (passages.rs:252-262) of room `a` in ascending room id - the order in which
 // select_candidate (passages.rs:69-82) meets them: Up (a-nx) < Left (a-1) < Right (a+1) < Down (a+nx).
+// Fixed slots (0 Up, 1 Left, 2 Right, 3 Down) with a validity flag instead of a packed list: every index is a
+// compile-time constant after unrolling, so the struct lives in registers (a packed list is indexed
+// dynamically while it is built and ends up in local memory).
 struct Neigh {
-  int id[4], dir[4], n;
+  int id[4];
+  bool ok[4];
 };
+RG_DEV int neigh_dir(int slot) { return slot == 0 ? D_UP : slot == 1 ? D_LEFT : slot == 2 ? D_RIGHT : D_DOWN; }
 RG_DEV Neigh neighbours(const Ctx& c, int a) {
   Neigh r;
-  r.n = 0;
   const int ay = a / c.nx, ax = a - ay * c.nx;
-  if (ay > 0) { r.id[r.n] = a - c.nx; r.dir[r.n++] = D_UP; }
-  if (ax > 0) { r.id[r.n] = a - 1; r.dir[r.n++] = D_LEFT; }
-  if (ax < c.nx - 1) { r.id[r.n] = a + 1; r.dir[r.n++] = D_RIGHT; }
-  if (ay < c.ny - 1) { r.id[r.n] = a + c.nx; r.dir[r.n++] = D_DOWN; }
+  r.ok[0] = ay > 0;          r.id[0] = a - c.nx;
+  r.ok[1] = ax > 0;          r.id[1] = a - 1;
+  r.ok[2] = ax < c.nx - 1;   r.id[2] = a + 1;
+  r.ok[3] = ay < c.ny - 1;   r.id[3] = a + c.nx;
   return r;
 }
 
@@ -307,8 +311,8 @@ __device__ void dig_passages(Ctx& c, Rng& rd, Rng& ra, uint32_t level) {
     const Neigh nb = neighbours(c, cur);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {  // select_candidate passages.rs:69-82
-      if (q >= nb.n || ((selected >> nb.id[q]) & 1u)) continue;
-      if (rd.does_happenG(k + 1)) { pick = nb.id[q]; pdir = nb.dir[q]; }
+      if (!nb.ok[q] || ((selected >> nb.id[q]) & 1u)) continue;
+      if (rd.does_happenG(k + 1)) { pick = nb.id[q]; pdir = neigh_dir(q); }
       ++k;
     }
     if (pick >= 0) {
@@ -331,8 +335,8 @@ __device__ void dig_passages(Ctx& c, Rng& rd, Rng& ra, uint32_t level) {
     const Neigh nb = neighbours(c, room1);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      if (q >= nb.n || ((conn >> (room1 * 4 + nb.dir[q])) & 1ull)) continue;
-      if (rd.does_happenG(k + 1)) { pick = nb.id[q]; pdir = nb.dir[q]; }
+      if (!nb.ok[q] || ((conn >> (room1 * 4 + neigh_dir(q))) & 1ull)) continue;
+      if (rd.does_happenG(k + 1)) { pick = nb.id[q]; pdir = neigh_dir(q); }
       ++k;
     }
     if (pick >= 0) {

@@ -200,7 +200,7 @@ RG_DEV void defer(const DevBatch& b, Ctx& c, int64_t env, uint32_t code, int par
 }
 
 // ThreadWorker::run Instruction::Reset for every env (python/src/thread_impls.rs:117-124)
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_reset(DevBatch b) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_HOT_MIN_BLOCKS) k_reset(DevBatch b) {
   unsigned char* const smem = rg_smem;
   Ctx c;
   const int warp = threadIdx.x >> 5;
