@@ -301,6 +301,7 @@ __device__ void snapshot_suspended_maps(Ctx& c);  // lazy DistCache, defined wit
 
 #define RG_GEN_SECOND_HALF
 namespace gen_inl {
+#define RG_GEN_NEW_LEVEL_ATTR __device__ __forceinline__
 #define range32G range32
 #define range64G range64
 #define range_i32G range_i32
@@ -312,8 +313,10 @@ namespace gen_inl {
 #undef range_i32G
 #undef does_happenG
 #undef parcentG
+#undef RG_GEN_NEW_LEVEL_ATTR
 }  // namespace gen_inl
 namespace gen_call {
+#define RG_GEN_NEW_LEVEL_ATTR __device__ __noinline__
 #define range32G range32g
 #define range64G range64g
 #define range_i32G range_i32g
@@ -325,6 +328,7 @@ namespace gen_call {
 #undef range_i32G
 #undef does_happenG
 #undef parcentG
+#undef RG_GEN_NEW_LEVEL_ATTR
 }  // namespace gen_call
 #undef RG_GEN_SECOND_HALF
 

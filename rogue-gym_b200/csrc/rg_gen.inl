@@ -444,7 +444,7 @@ __device__ bool gen_enemy(Ctx& c, Rng& re, uint32_t rmin, uint32_t rmax, bool ha
 // rogue::Dungeon::new_level_ rogue/mod.rs:434-481 + Floor::gen_floor floor.rs:50-104
 // + setup_items :132-153 + setup_stair :156-167 + place_enemies :106-130,
 // then actions::new_level's player placement (actions.rs:134-137).
-__device__ __noinline__ void new_level(Ctx* cp, bool is_initial) {
+RG_GEN_NEW_LEVEL_ATTR void new_level(Ctx* cp, bool is_initial) {
   Ctx& c = *cp;
   RG_PLANES(c);
   const rg_params& P = *c.P;
