@@ -19,10 +19,18 @@ __device__ int dig_maze(Ctx& c, Rng& r, int x0, int y0, int x1, int y1) {
   for (;;) {
     int pick = -1;
     uint32_t k = 0;
+    // the four membership reads are issued together (one shared-memory latency instead of four on this
+    // serial chain); an out-of-range neighbour reads the current cell, which is marked
+    bool open[4];
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
-      int tx = cx + 2 * ddx(d), ty = cy + 2 * ddy(d);
-      if (tx >= x0 && tx < x1 && ty >= y0 && ty < y1 && !(A[ty * W + tx] & A_MARK)) {
+      const int tx = cx + 2 * ddx(d), ty = cy + 2 * ddy(d);
+      const bool inside = tx >= x0 && tx < x1 && ty >= y0 && ty < y1;
+      open[d] = !(A[inside ? ty * W + tx : cy * W + cx] & A_MARK);
+    }
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      if (open[d]) {
         if (r.does_happenG(k + 1)) pick = d;  // reservoir pick: every candidate draws (maze.rs:64-75)
         ++k;
       }
