@@ -98,9 +98,20 @@ struct Rng {
   RG_DEV bool parcentg(uint32_t p) { return range32g(1, 101) <= p; }
 };
 
+// Position of the n-th (0-based) set bit of m, which must exist: five popcount halvings instead of
+// clearing n bits one after the other (n reaches 31 in the ballot-based cell selects, and this sits on
+// the serial chain of a floor).
 RG_DEV int nth_set_bit(uint32_t m, uint32_t n) {
-  for (uint32_t i = 0; i < n; ++i) m &= m - 1;
-  return __ffs(m) - 1;
+  int pos = 0;
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const uint32_t c = (uint32_t)__popc(m & (((1u << w) - 1u) << pos));
+    if (n >= c) {
+      n -= c;
+      pos += w;
+    }
+  }
+  return pos;
 }
 
 // ------------------------------------------------------------------ per-warp context

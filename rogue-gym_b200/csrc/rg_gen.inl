@@ -134,6 +134,7 @@ __device__ void lay_rooms(Ctx& c, Rng& r, uint32_t level) {
       __syncwarp();
     } else if (rm.kind == K_MAZE) {  // UNIFORM: each passage cell rolls gen_attr in index order
       // the marked cells are found 32 at a time (ballot); the draws stay serial, in ascending cell order
+      const uint32_t dark_level = P.dark_level, hidden_inv = P.hidden_passage_rate_inv;  // not re-read per cell
       const int w = rm.x1 - rm.x0, total = w * (rm.y1 - rm.y0);
       for (int base = 0; base < total; base += 32) {
         const int k = base + c.lane;
@@ -144,7 +145,7 @@ __device__ void lay_rooms(Ctx& c, Rng& r, uint32_t level) {
           const int cell = __shfl_sync(RG_FULL, idx, __ffs(bal) - 1);
           bal &= bal - 1;
           uint8_t attr = 0;
-          if (r.range32G(0, P.dark_level) < level && r.does_happenG(P.hidden_passage_rate_inv)) attr = A_HIDDEN;
+          if (r.range32G(0, dark_level) < level && r.does_happenG(hidden_inv)) attr = A_HIDDEN;
           S[cell] = S_PASSAGE;
           A[cell] = A_MARK | attr;
         }
@@ -155,9 +156,11 @@ __device__ void lay_rooms(Ctx& c, Rng& r, uint32_t level) {
 }
 
 // floor.rs:85-102: one registered passage cell; `ra` is the attribute stream of the replay
-RG_DEV void apply_passage_cell(Ctx& c, Rng& ra, int x, int y, uint8_t surface, uint32_t level) {
+struct PassageRates {  // read once per connection, not once per cell (the sampler calls in between are opaque)
+  uint32_t dark_level, locked_inv, hidden_inv;
+};
+RG_DEV void apply_passage_cell(Ctx& c, Rng& ra, int x, int y, uint8_t surface, uint32_t level, const PassageRates& pr) {
   RG_PLANES(c);
-  const rg_params& P = *c.P;
   int idx = y * c.W + x;
   if (!inb(c, x, y)) {
     set_panic(c);
@@ -167,9 +170,9 @@ RG_DEV void apply_passage_cell(Ctx& c, Rng& ra, int x, int y, uint8_t surface, u
   uint8_t attr = 0;
   if (surface == S_DOOR) {
     keep |= A_DOOR;
-    if (ra.range32G(0, P.dark_level) < level && ra.does_happenG(P.locked_door_rate_inv)) attr = A_LOCKED;
+    if (ra.range32G(0, pr.dark_level) < level && ra.does_happenG(pr.locked_inv)) attr = A_LOCKED;
   } else {
-    if (ra.range32G(0, P.dark_level) < level && ra.does_happenG(P.hidden_passage_rate_inv)) attr = A_HIDDEN;
+    if (ra.range32G(0, pr.dark_level) < level && ra.does_happenG(pr.hidden_inv)) attr = A_HIDDEN;
   }
   A[idx] = keep | attr;
   if (!attr) S[idx] = surface;
@@ -248,12 +251,13 @@ __device__ void connect_2rooms(Ctx& c, Rng& rd, Rng& ra, int r1, int r2, int d, 
     int t = r1; r1 = r2; r2 = t;
     d = reverse_dir(d);
   }
+  const PassageRates pr = {c.P->dark_level, c.P->locked_door_rate_inv, c.P->hidden_passage_rate_inv};
   int sx, sy, ex, ey;
   select_start_or_end(c, rd, r1, d, sx, sy);
   select_start_or_end(c, rd, r2, reverse_dir(d), ex, ey);
   if (APPLY) {
-    apply_passage_cell(c, ra, sx, sy, st->rooms[r1].kind == K_NORMAL ? S_DOOR : S_PASSAGE, level);
-    apply_passage_cell(c, ra, ex, ey, st->rooms[r2].kind == K_NORMAL ? S_DOOR : S_PASSAGE, level);
+    apply_passage_cell(c, ra, sx, sy, st->rooms[r1].kind == K_NORMAL ? S_DOOR : S_PASSAGE, level, pr);
+    apply_passage_cell(c, ra, ex, ey, st->rooms[r2].kind == K_NORMAL ? S_DOOR : S_PASSAGE, level, pr);
   }
   int tsx, tsy, tex, tey, tdir;
   if (d == D_DOWN) {
@@ -271,11 +275,11 @@ __device__ void connect_2rooms(Ctx& c, Rng& rd, Rng& ra, int r1, int r2, int d, 
     int guard = c.W + c.H + 4;
     int x = sx + ddx(d), y = sy + ddy(d);  // .skip(1)
     for (; (x != tsx || y != tsy) && guard > 0; x += ddx(d), y += ddy(d), --guard)
-      apply_passage_cell(c, ra, x, y, S_PASSAGE, level);
+      apply_passage_cell(c, ra, x, y, S_PASSAGE, level, pr);
     for (x = tsx, y = tsy; (x != tex || y != tey) && guard > 0; x += ddx(tdir), y += ddy(tdir), --guard)
-      apply_passage_cell(c, ra, x, y, S_PASSAGE, level);
+      apply_passage_cell(c, ra, x, y, S_PASSAGE, level, pr);
     for (x = tex, y = tey; (x != ex || y != ey) && guard > 0; x += ddx(d), y += ddy(d), --guard)
-      apply_passage_cell(c, ra, x, y, S_PASSAGE, level);
+      apply_passage_cell(c, ra, x, y, S_PASSAGE, level, pr);
     if (guard <= 0) set_panic(c);
   }
 }
