@@ -243,35 +243,56 @@ __device__ void select_start_or_end(Ctx& c, Rng& r, int room, int d, int& ox, in
   oy = rm.y0;
 }
 
-// passages::connect_2rooms passages.rs:84-133
-template <bool APPLY>
-__device__ void connect_2rooms(Ctx& c, Rng& rd, Rng& ra, int r1, int r2, int d, uint32_t level) {
+// passages::connect_2rooms passages.rs:84-133, first half: where the passage starts, ends and turns (three
+// draws on the dungeon stream). Which cells it covers follows from that alone, so the connection is only
+// RECORDED here; the cells are laid - and their attributes rolled on the second stream - afterwards, in the
+// same order (apply_connections), exactly as the reference registers cells while digging and rolls
+// gen_attr when the digging is done (floor.rs:73-102). A pair of adjacent rooms is connected at most once,
+// so there are at most 2*nx*ny - nx - ny <= 24 records.
+struct ConnList {
+  uint64_t rec[32];
+  int n;
+};
+__device__ void connect_2rooms(Ctx& c, Rng& rd, ConnList& cl, int r1, int r2, int d) {
   RG_PLANES(c);
   if (d == D_UP || d == D_LEFT) {
     int t = r1; r1 = r2; r2 = t;
     d = reverse_dir(d);
   }
-  const PassageRates pr = {c.P->dark_level, c.P->locked_door_rate_inv, c.P->hidden_passage_rate_inv};
   int sx, sy, ex, ey;
   select_start_or_end(c, rd, r1, d, sx, sy);
   select_start_or_end(c, rd, r2, reverse_dir(d), ex, ey);
-  if (APPLY) {
-    apply_passage_cell(c, ra, sx, sy, st->rooms[r1].kind == K_NORMAL ? S_DOOR : S_PASSAGE, level, pr);
-    apply_passage_cell(c, ra, ex, ey, st->rooms[r2].kind == K_NORMAL ? S_DOOR : S_PASSAGE, level, pr);
-  }
-  int tsx, tsy, tex, tey, tdir;
+  int turn;
   if (d == D_DOWN) {
     if (!(sy + 1 < ey)) { set_panic(c); return; }
-    int y = rd.range_i32G(sy + 1, ey);
-    tdir = (sx < ex) ? D_RIGHT : D_LEFT;
-    tsx = sx; tsy = y; tex = ex; tey = y;
+    turn = rd.range_i32G(sy + 1, ey);
   } else {
     if (!(sx + 1 < ex)) { set_panic(c); return; }
-    int x = rd.range_i32G(sx + 1, ex);
-    tdir = (sy < ey) ? D_DOWN : D_UP;
-    tsx = x; tsy = sy; tex = x; tey = ey;
+    turn = rd.range_i32G(sx + 1, ex);
   }
-  if (APPLY) {
+  if (cl.n >= 32) { set_panic(c); return; }
+  const uint64_t doors = (st->rooms[r1].kind == K_NORMAL ? 1ull : 0ull) | (st->rooms[r2].kind == K_NORMAL ? 2ull : 0ull);
+  cl.rec[cl.n++] = (uint64_t)sx | ((uint64_t)sy << 8) | ((uint64_t)ex << 16) | ((uint64_t)ey << 24) |
+                   ((uint64_t)turn << 32) | ((uint64_t)(d == D_DOWN ? 1 : 0) << 40) | (doors << 41);
+}
+// passages.rs:98-133, second half, for every recorded connection in order: the two ends, then the three legs.
+__device__ void apply_connections(Ctx& c, Rng& ra, const ConnList& cl, uint32_t level) {
+  const PassageRates pr = {c.P->dark_level, c.P->locked_door_rate_inv, c.P->hidden_passage_rate_inv};
+  for (int i = 0; i < cl.n && !c.panic; ++i) {
+    const uint64_t r = cl.rec[i];
+    const int sx = (int)(r & 0xFF), sy = (int)((r >> 8) & 0xFF), ex = (int)((r >> 16) & 0xFF), ey = (int)((r >> 24) & 0xFF);
+    const int turn = (int)((r >> 32) & 0xFF);
+    const int d = ((r >> 40) & 1) ? D_DOWN : D_RIGHT;
+    apply_passage_cell(c, ra, sx, sy, ((r >> 41) & 1) ? S_DOOR : S_PASSAGE, level, pr);
+    apply_passage_cell(c, ra, ex, ey, ((r >> 42) & 1) ? S_DOOR : S_PASSAGE, level, pr);
+    int tsx, tsy, tex, tey, tdir;
+    if (d == D_DOWN) {
+      tdir = (sx < ex) ? D_RIGHT : D_LEFT;
+      tsx = sx; tsy = turn; tex = ex; tey = turn;
+    } else {
+      tdir = (sy < ey) ? D_DOWN : D_UP;
+      tsx = turn; tsy = sy; tex = turn; tey = ey;
+    }
     int guard = c.W + c.H + 4;
     int x = sx + ddx(d), y = sy + ddy(d);  // .skip(1)
     for (; (x != tsx || y != tsy) && guard > 0; x += ddx(d), y += ddy(d), --guard)
@@ -304,13 +325,8 @@ RG_DEV Neigh neighbours(const Ctx& c, int a) {
   return r;
 }
 
-// passages::dig_passges passages.rs:16-67. The reference collects every registered cell and
-// rolls their attributes afterwards (floor.rs:73-102); here the dig runs twice from the same
-// RNG snapshot: a dry run that only advances the stream, then a replay that lays tiles while a
-// second stream (starting where the dry run ended) rolls the attributes. Same draws, same
-// order, no cell list.
-template <bool APPLY>
-__device__ void dig_passages(Ctx& c, Rng& rd, Rng& ra, uint32_t level) {
+// passages::dig_passges passages.rs:16-67: which rooms get connected, in which order (dungeon stream only).
+__device__ void dig_passages(Ctx& c, Rng& rd, ConnList& cl) {
   const int n = c.nrooms;
   uint64_t conn = 0;  // bit room*4+dir : connected to the neighbour in that direction
   uint32_t selected;
@@ -331,7 +347,7 @@ __device__ void dig_passages(Ctx& c, Rng& rd, Rng& ra, uint32_t level) {
       selected |= 1u << pick;
       conn |= 1ull << (cur * 4 + pdir);
       conn |= 1ull << (pick * 4 + reverse_dir(pdir));
-      connect_2rooms<APPLY>(c, rd, ra, cur, pick, pdir, level);
+      connect_2rooms(c, rd, cl, cur, pick, pdir);
     } else {
       uint32_t cnt = __popc(selected);
       cur = nth_set_bit(selected, (uint32_t)rd.range64G(0, cnt));
@@ -354,7 +370,7 @@ __device__ void dig_passages(Ctx& c, Rng& rd, Rng& ra, uint32_t level) {
     if (pick >= 0) {
       conn |= 1ull << (room1 * 4 + pdir);
       conn |= 1ull << (pick * 4 + reverse_dir(pdir));
-      connect_2rooms<APPLY>(c, rd, ra, room1, pick, pdir, level);
+      connect_2rooms(c, rd, cl, room1, pick, pdir);
     }
     if (c.panic) return;
   }
@@ -489,11 +505,13 @@ RG_GEN_NEW_LEVEL_ATTR void new_level(Ctx* cp, bool is_initial) {
   Rng rd = c.rd;
   gen_rooms(c, rd, level);
   lay_rooms(c, rd, level);
-  {  // two-pass passage dig (see dig_passages)
-    Rng dry = rd, none = rd;
-    dig_passages<false>(c, dry, none, level);
-    Rng ra = dry;
-    dig_passages<true>(c, rd, ra, level);
+  {  // dig (dungeon stream), then lay the recorded passages while a second stream, which starts where the
+     // dig ended, rolls the cell attributes (connect_2rooms / apply_connections)
+    ConnList cl;
+    cl.n = 0;
+    dig_passages(c, rd, cl);
+    Rng ra = rd;
+    apply_connections(c, ra, cl, level);
     rd = ra;
   }
   // Floor::setup_items: cell from the dungeon stream, amount from the item stream (gold.rs:18-24)
