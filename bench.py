@@ -34,7 +34,7 @@ CONFIG = {}  # config-default: every field at its default ("{}" => default, core
 BYTES_PER_ENV_STEP = 7858
 # dram__bytes_read.sum + dram__bytes_write.sum of one steady-state step (scan + player + monsters + full-path
 # kernels) at 65 536 envs, from the ncu --set full capture summarised in profiles/r1_ncu_summary.md
-NCU_DRAM_BYTES_PER_STEP = 403.4e6
+NCU_DRAM_BYTES_PER_STEP = 404.9e6
 WORKLOAD = "65536 envs/GPU, config-default 80x24 (3x3 rooms, monsters, gold, visibility), random 11-action rollout, max_steps 1000, auto-reset"
 
 
