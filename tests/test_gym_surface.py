@@ -25,6 +25,35 @@ def test_gym_api_resolves_and_spaces_compare_by_value():
     assert gym.spaces.discrete.Discrete(3) == sp.discrete.Discrete(3)
 
 
+def test_gym_shim_wrapper_semantics_and_optional_adapter():
+    from rogue_gym import _gymapi
+    import rogue_gym  # the package imports without `rainy`
+
+    class Dummy(_gymapi.Env):
+        action_space = _gymapi.spaces.discrete.Discrete(3)
+        observation_space = _gymapi.spaces.box.Box(low=0, high=1, shape=(2, 2), dtype=np.float32)
+        extra = 41
+
+        def step(self, a):
+            return a, 1.0, False, {}
+
+        def reset(self):
+            return 0
+
+    w = _gymapi.Wrapper(Dummy())
+    assert w.unwrapped is w.env and w.action_space == Dummy.action_space and w.extra == 41
+    assert w.step(2) == (2, 1.0, False, {}) and w.reset() == 0
+    if _gymapi.IS_SHIM:
+        assert w.action_space.contains(2) and not w.action_space.contains(3)
+        assert w.observation_space.sample().shape == (2, 2)
+    try:
+        import rainy  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="install rainy"):
+            import rogue_gym.rainy_impls  # noqa: F401
+    assert rogue_gym.__version__.startswith("0.0.2")
+
+
 def test_status_flag_and_image_setting_dims():
     from rogue_gym.envs import DungeonType, ImageSetting, StatusFlag
     assert StatusFlag.FULL.value == 0b111111111 and StatusFlag.FULL.count_one() == 9
