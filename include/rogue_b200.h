@@ -247,6 +247,12 @@ int rg_state_hash(rg_batch* b, uint64_t* out_host /* [N] */);
 /* Dungeon::move_enemy with an always-false skip, for the known-answer test
  * (core/src/dungeon/rogue/mod.rs:566-578): 0 CantMove, 1 CanMove, 2 Reach. */
 int rg_test_move_enemy(rg_batch* b, int64_t env, int fx, int fy, int tx, int ty, int* kind, int* nx, int* ny);
+/* The tile planes and room tables of every env, into caller-owned DEVICE buffers (any may be NULL), on the
+ * batch's stream: surface_dev / attr_dev u8 [N][W*H] dense (codes as in rg_dump), rooms_dev i16
+ * [N][RG_MAX_ROOMS][8] = kind (0 normal, 1 maze, 2 empty), is_dark, x0, y0, x1, y1 (half-open, walls
+ * included), player x, player y. For the reference's generator property tests restated on whole batches
+ * (passages.rs:343-379 connectivity, rooms.rs:308-340 pos_check, floor.rs:466-488 secret_door). */
+int rg_export_floors(rg_batch* b, uint8_t* surface_dev, uint8_t* attr_dev, int16_t* rooms_dev);
 
 #ifdef __cplusplus
 }

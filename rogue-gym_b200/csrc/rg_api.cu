@@ -870,6 +870,21 @@ int rg_state_hash(rg_batch* b, uint64_t* out_host) {
   return RG_OK;
 }
 
+int rg_export_floors(rg_batch* b, uint8_t* surface_dev, uint8_t* attr_dev, int16_t* rooms_dev) {
+  if (!b) return set_err(b, RG_ERR_ARG, "rg_export_floors: null batch");
+  RG_CUDA(b, cudaSetDevice(b->device));
+  const DevBatch& d = b->d;
+  const size_t N = (size_t)b->n;
+  if (surface_dev)
+    RG_CUDA(b, cudaMemcpy2DAsync(surface_dev, d.C, d.surface, d.CP, d.C, N, cudaMemcpyDeviceToDevice, b->stream));
+  if (attr_dev) RG_CUDA(b, cudaMemcpy2DAsync(attr_dev, d.C, d.attr, d.CP, d.C, N, cudaMemcpyDeviceToDevice, b->stream));
+  if (rooms_dev) {
+    RG_CUDA(b, rg::launch_export_rooms(d, rooms_dev, b->stream));
+    b->launches += 1;
+  }
+  return RG_OK;
+}
+
 int rg_test_move_enemy(rg_batch* b, int64_t env, int fx, int fy, int tx, int ty, int* kind, int* nx, int* ny) {
   if (!b || env < 0 || env >= b->n) return set_err(b, RG_ERR_ARG, "rg_test_move_enemy: bad env");
   if (fx < 0 || fy < 0 || fx >= b->d.W || fy >= b->d.H || tx < 0 || ty < 0 || tx >= b->d.W || ty >= b->d.H)

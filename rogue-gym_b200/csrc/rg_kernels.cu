@@ -556,19 +556,22 @@ RG_DEV void step_env_full(const DevBatch& b, Ctx& c, int64_t env, const uint8_t*
 // End of a step: advances the step counter and, on the steps that kick a background pass, fixes the
 // window of refill requests that pass serves: [end of the previous window, current tail). Runs in one
 // thread after every kernel of the step has finished.
+RG_DEV void fix_window(const DevBatch& b) {  // window of background pass number dstep[3] (host: rg_batch::passes)
+  const uint32_t p = b.dstep[3]++;
+  uint32_t* win = b.refill_win + 2 * (p % 8u);
+  win[0] = b.refill_ctl[2];
+  win[1] = b.refill_ctl[2] = *reinterpret_cast<volatile uint32_t*>(b.refill_ctl);
+}
 RG_DEV void step_end(const DevBatch& b, int auto_reset) {
   b.dstep[0] += 1u;
   if (!auto_reset || !b.prefetch) return;
   const uint32_t k = b.dstep[1]++;
   if (k % (uint32_t)b.prefetch_every) return;
-  uint32_t* win = b.refill_win + 2 * ((k / (uint32_t)b.prefetch_every) % 8u);
-  win[0] = b.refill_ctl[2];
-  win[1] = b.refill_ctl[2] = *reinterpret_cast<volatile uint32_t*>(b.refill_ctl);
+  fix_window(b);
 }
 __global__ void k_step_end(DevBatch b, int auto_reset) {
   if (threadIdx.x == 0) step_end(b, auto_reset);
 }
-
 // Grid-stride over the full-path list; exits at once when the list is empty.
 // With `finalize` the last block to finish also does the end-of-step bookkeeping (one kernel boundary less).
 __global__ void __launch_bounds__(GEN_WPB * 32) k_step_gen(DevBatch b, const uint8_t* __restrict__ actions,
@@ -935,6 +938,26 @@ __global__ void k_state_hash(DevBatch b, uint64_t* out) {
   out[env] = h;
 }
 
+// parity harness (rg_export_floors): room table + player position of every env
+__global__ void k_export_rooms(DevBatch b, int16_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b.n * MAX_ROOMS) return;
+  const int64_t env = i / MAX_ROOMS;
+  const int r = (int)(i % MAX_ROOMS);
+  const EnvState* st = b.st + env;
+  int16_t* o = out + i * 8;
+  const bool live = r < b.nx * b.ny;
+  const RoomD rm = st->rooms[live ? r : 0];
+  o[0] = live ? rm.kind : -1;
+  o[1] = live && (rm.flags & RF_DARK) ? 1 : 0;
+  o[2] = live ? rm.x0 : 0;
+  o[3] = live ? rm.y0 : 0;
+  o[4] = live ? rm.x1 : 0;
+  o[5] = live ? rm.y1 : 0;
+  o[6] = st->px;
+  o[7] = st->py;
+}
+
 // Instruction::Seed for every env (python/src/thread_impls.rs:125-128): stored, used by the next reset
 __global__ void k_seed(DevBatch b, const uint64_t* __restrict__ lo, const uint64_t* __restrict__ hi, int seeded) {
   const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1196,6 +1219,10 @@ cudaError_t launch_seed(const DevBatch& b, const uint64_t* lo, const uint64_t* h
 }
 cudaError_t launch_unpack_hist(const DevBatch& b, uint8_t* out, cudaStream_t s) {
   k_unpack_hist<<<(unsigned)b.n, 128, 0, s>>>(b, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_export_rooms(const DevBatch& b, int16_t* rooms, cudaStream_t s) {
+  k_export_rooms<<<(unsigned)((b.n * MAX_ROOMS + 255) / 256), 256, 0, s>>>(b, rooms);
   return cudaGetLastError();
 }
 cudaError_t launch_state_hash(const DevBatch& b, uint64_t* out, cudaStream_t s) {

@@ -51,4 +51,5 @@ cudaError_t launch_train_reward(const DevBatch& b, float stair_reward, int32_t* 
 cudaError_t launch_seed(const DevBatch& b, const uint64_t* lo_dev, const uint64_t* hi_dev, int seeded, cudaStream_t s);
 cudaError_t launch_unpack_hist(const DevBatch& b, uint8_t* out_dev, cudaStream_t s);
 cudaError_t launch_state_hash(const DevBatch& b, uint64_t* out_dev, cudaStream_t s);
+cudaError_t launch_export_rooms(const DevBatch& b, int16_t* rooms_dev, cudaStream_t s);
 }  // namespace rg

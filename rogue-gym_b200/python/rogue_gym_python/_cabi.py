@@ -118,6 +118,7 @@ SYMBOLS = {
     "rg_encode_states": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _u32, _i, _vp, C.POINTER(_i)]),
     "rg_dump_env": (_i, [_vp, _i64, C.POINTER(Dump)]),
     "rg_state_hash": (_i, [_vp, _vp]),
+    "rg_export_floors": (_i, [_vp, _vp, _vp, _vp]),
     "rg_test_move_enemy": (_i, [_vp, _i64, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
 }
 
