@@ -191,7 +191,8 @@ int rg_step_host(rg_batch* b, const uint8_t* actions_host, int auto_reset, rg_ho
 int rg_quiesce(rg_batch* b);
 /* Event counters since creation: [0] episode ends served by a prefetched game, [1] episode ends
  * generated synchronously, [2] steps taken on the full path (descents, MoveUntil), [3] games built in
- * the background, [4] prefetched games found stale, [5] env-steps with an active monster, [6..7] spare. */
+ * the background, [4] prefetched games found stale, [5] env-steps with an active monster, [6] spare,
+ * [7] env-steps finished by the thread-per-env kernel (k_step_fast). */
 int rg_stats(rg_batch* b, uint64_t* out8);
 /* Timeline of the last 512 steps (only when the batch was created with RG_TRACE=1 in the environment):
  * out[512][8][2] = first start / last end (globaltimer ns) of kernel k of step slot s; k = 0 player,

@@ -29,15 +29,12 @@ struct rg_batch {
   cudaStream_t stream = nullptr;
   cudaStream_t bg[2] = {nullptr, nullptr};  // background streams: k_prefetch passes alternate, so two can be in flight
   cudaStream_t side = nullptr;    // full-path steps, forked after the player kernel and joined at the end of the step
-  cudaStream_t mon = nullptr;     // monster kernels of piece k beside the player kernel of piece k+1
   cudaStream_t mir = nullptr;     // first host-mirror pass of a step
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mon = nullptr, ev_player = nullptr, ev_mir = nullptr;
-  cudaEvent_t ev_chunk[rg::MAX_CHUNKS] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mir = nullptr;
   rg::StepStreams step_streams() const {
     rg::StepStreams q;
-    q.main = stream; q.side = side; q.mon = mon; q.mir = mir;
-    q.ev_fork = ev_fork; q.ev_join = ev_join; q.ev_mon = ev_mon; q.ev_player = ev_player; q.ev_mir = ev_mir;
-    for (int i = 0; i < rg::MAX_CHUNKS; ++i) q.ev_chunk[i] = ev_chunk[i];
+    q.main = stream; q.side = side; q.mir = mir;
+    q.ev_fork = ev_fork; q.ev_join = ev_join; q.ev_mir = ev_mir;
     return q;
   }
   cudaEvent_t ev_main = nullptr;  // "this step's kernels are queued up to here"
@@ -52,7 +49,6 @@ struct rg_batch {
   cudaGraphExec_t graph[2] = {nullptr, nullptr};    // [auto_reset]
   cudaGraphExec_t graph_m[2] = {nullptr, nullptr};  // the same step with the two host-mirror passes
   rg::MirrorArgs margs{};
-  int mirror_chunks = 1;  // pieces of the env range in a step that carries the host-mirror passes
   DevBatch d{};
   rg_params* dP = nullptr;
   uint8_t* d_actions = nullptr;
@@ -318,26 +314,19 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
     int lo = 0, hi = 0;
     RG_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     RG_TRY(cudaStreamCreateWithPriority(&b->side, cudaStreamNonBlocking, hi));
-    RG_TRY(cudaStreamCreateWithPriority(&b->mon, cudaStreamNonBlocking, hi));
     RG_TRY(cudaStreamCreateWithFlags(&b->mir, cudaStreamNonBlocking));
-    RG_TRY(cudaEventCreateWithFlags(&b->ev_player, cudaEventDisableTiming));
     RG_TRY(cudaEventCreateWithFlags(&b->ev_mir, cudaEventDisableTiming));
-    RG_TRY(cudaEventCreateWithFlags(&b->ev_mon, cudaEventDisableTiming));
-    for (int i = 0; i < rg::MAX_CHUNKS; ++i) RG_TRY(cudaEventCreateWithFlags(&b->ev_chunk[i], cudaEventDisableTiming));
-    // measured at 65 536 envs: 1 piece 0.245 ms per step, 2 pieces 0.255, 4 pieces 0.278, 8 pieces 0.330 - every extra
-    // kernel boundary (tail of one player kernel, ramp of the next) costs more than the hidden monster phase saves
-    d.chunks = 1;
-    if (const char* e = getenv("RG_CHUNKS")) d.chunks = std::min(rg::MAX_CHUNKS, std::max(1, atoi(e)));
-    if ((int64_t)d.chunks > b->n) d.chunks = 1;
-    b->mirror_chunks = b->n >= 8192 ? 2 : 1;
-    if (const char* e = getenv("RG_MIRROR_CHUNKS")) b->mirror_chunks = std::min(rg::MAX_CHUNKS, std::max(1, atoi(e)));
-    if ((int64_t)b->mirror_chunks > b->n) b->mirror_chunks = 1;
   }
   RG_TRY(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
   RG_TRY(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
   RG_TRY(dev_alloc(b, &d.mon_list, N));
-  RG_TRY(dev_alloc(b, &d.mon_count, 4 * rg::MAX_CHUNKS));
-  RG_TRY(cudaMemsetAsync(d.mon_count, 0, 16 * rg::MAX_CHUNKS, b->stream));
+  RG_TRY(dev_alloc(b, &d.mon_count, 4));
+  RG_TRY(cudaMemsetAsync(d.mon_count, 0, 16, b->stream));
+  RG_TRY(dev_alloc(b, &d.slow_list, N));
+  RG_TRY(dev_alloc(b, &d.slow_count, 4));
+  RG_TRY(cudaMemsetAsync(d.slow_count, 0, 16, b->stream));
+  d.fast = 1;
+  if (const char* e = getenv("RG_FAST")) d.fast = e[0] != '0';
   RG_TRY(dev_alloc(b, &b->d_actions, N));
   RG_TRY(dev_alloc(b, &b->d_u64, 2 * N));
   RG_TRY(dev_alloc(b, &b->d_out3, 4));
@@ -492,22 +481,16 @@ void rg_destroy(rg_batch* b) {
   for (int i = 0; i < 2; ++i)
     if (b->bg[i]) cudaStreamSynchronize(b->bg[i]);
   if (b->side) cudaStreamSynchronize(b->side);
-  if (b->mon) cudaStreamSynchronize(b->mon);
   for (int i = 0; i < 2; ++i) {
     if (b->graph[i]) cudaGraphExecDestroy(b->graph[i]);
     if (b->graph_m[i]) cudaGraphExecDestroy(b->graph_m[i]);
   }
   if (b->mir) cudaStreamSynchronize(b->mir);
   if (b->mir) cudaStreamDestroy(b->mir);
-  if (b->ev_player) cudaEventDestroy(b->ev_player);
   if (b->ev_mir) cudaEventDestroy(b->ev_mir);
   if (b->ev_fork) cudaEventDestroy(b->ev_fork);
   if (b->ev_join) cudaEventDestroy(b->ev_join);
   if (b->side) cudaStreamDestroy(b->side);
-  if (b->mon) cudaStreamDestroy(b->mon);
-  if (b->ev_mon) cudaEventDestroy(b->ev_mon);
-  for (int i = 0; i < rg::MAX_CHUNKS; ++i)
-    if (b->ev_chunk[i]) cudaEventDestroy(b->ev_chunk[i]);
   if (b->ev_main) cudaEventDestroy(b->ev_main);
   for (int i = 0; i < 2; ++i) {
     if (b->ev_bg[i]) cudaEventDestroy(b->ev_bg[i]);
@@ -558,11 +541,7 @@ int step_impl(rg_batch* b, const uint8_t* actions_dev, int auto_reset, bool with
   auto_reset = auto_reset ? 1 : 0;
   const rg::MirrorArgs* mirror = with_mirror ? &b->margs : nullptr;
   cudaGraphExec_t* graphs = with_mirror ? b->graph_m : b->graph;
-  // With the mirror the env range goes through in two pieces: the second piece's player kernel hides the
-  // first piece's mirror pass (measured at 65 536 envs: 348 us per synced step in one piece, 335 us in two,
-  // 341 us in three or four); without it one piece is fastest (see create_impl).
-  DevBatch d = b->d;
-  if (with_mirror) d.chunks = b->mirror_chunks;
+  const DevBatch& d = b->d;
   // the step kernels read the batch's own action buffer, so that the launch sequence has no
   // per-step argument and can be replayed as a graph
   if (actions_dev != b->d_actions)
@@ -603,7 +582,7 @@ int step_impl(rg_batch* b, const uint8_t* actions_dev, int auto_reset, bool with
       RG_CUDA(b, cudaMemcpyAsync(b->h_errflag, b->d.errflag, sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
     }
   }
-  b->launches += 3 + 2 * d.chunks + (with_mirror ? 1 + d.chunks : 0);
+  b->launches += 5 + (with_mirror ? 2 : 0);
   if (auto_reset && (b->auto_steps++ % b->prefetch_every) == 0)
     return kick_prefetch(b);  // refill the next-episode buffers consumed so far
   return RG_OK;

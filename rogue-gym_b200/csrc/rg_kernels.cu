@@ -19,10 +19,6 @@ namespace rg {
 // done, so a warp that runs a BFS does not pin three finished neighbours (measured: 4 warps/block
 // 0.668 ms per step, 1 warp/block 0.626 ms at 64 registers, 65 536 envs).
 constexpr int WARPS_PER_BLOCK = RG_WPB;
-#ifndef RG_PLAYER_WPB
-#define RG_PLAYER_WPB 1
-#endif
-constexpr int PLAYER_WPB = RG_PLAYER_WPB;  // warps (= envs) per block of k_step_player
 // The generator kernels are the opposite case: ~15 k instructions of divergent code run by a few
 // hundred warps beside the step kernels. Spread one warp per SM they evict the step kernels' code from
 // every SM's instruction caches (measured: the player kernel takes 216 us instead of 140 us while a
@@ -129,10 +125,22 @@ RG_DEV void fill_ctx(const DevBatch& b, Ctx& c, Stager& sg, unsigned char* base,
 RG_DEV void write_back(const DevBatch& b, Ctx& c, int64_t env, bool with_s, bool with_a, EnvState* st_dst, uint8_t* s_dst,
                        uint8_t* a_dst) {
   __syncwarp();
-  if (c.lane == 0) {
-    c.rd.store(c.st->rng);
-    c.ri.store(c.st->rng + 4);
-    c.re.store(c.st->rng + 8);
+  {  // what k_step_fast needs to know about the monsters, recomputed wherever the state is written back
+    uint32_t present = 0, active = 0;
+    if (c.lane < MAX_ROOMS) {
+      const MonD m = c.st->mon[c.lane];
+      present = (m.flags & MF_PRESENT) ? 1u : 0u;
+      active = (present && (m.flags & MF_ACTIVE)) ? 1u : 0u;
+      c.st->mon_xy[c.lane] = (uint16_t)(m.x | (m.y << 8));
+    }
+    const uint32_t pm = __ballot_sync(RG_FULL, present), am = __ballot_sync(RG_FULL, active);
+    if (c.lane == 0) {
+      c.st->mon_present = (uint16_t)pm;
+      c.st->mon_active = (uint16_t)am;
+      c.rd.store(c.st->rng);
+      c.ri.store(c.st->rng + 4);
+      c.re.store(c.st->rng + 8);
+    }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncwarp();
@@ -192,7 +200,7 @@ RG_DEV void defer(const DevBatch& b, Ctx& c, int64_t env, uint32_t code, int par
     atomicAdd(b.stats + (code ? RGS_SYNC_RESET : RGS_FULL_STEP), 1ull);
     // two lists: full-path steps come from k_step_scan (their kernel runs beside the player and monster
     // kernels on a side stream), synchronous resets are known only when finish_env has run
-    if (code) b.full_path[env] = 3;  // finished by the reset pass: not yet final for the host mirror
+    if (code) b.full_path[env] = FP_RESET;  // finished by the reset pass: not yet final for the host mirror
     uint32_t* cnt = (code ? b.reset_count : b.defer_count) + parity;
     uint32_t* list = code ? b.reset_list : b.defer_list;
     list[atomicAdd(cnt, 1u)] = (uint32_t)env | code;
@@ -240,13 +248,14 @@ RG_DEV bool has_active_monster(const Ctx& c) {
 // resident in the instruction caches (the single-kernel version spent most of its stall samples
 // on instruction fetch: 17-30 k SASS instructions executed divergently by independent warps):
 //
-//   k_step_scan     one thread per env, looks at the key (and, for '>' / capitals, at the position):
-//                   descents and MoveUntil go to the full-path list and are flagged in full_path[].
+//   k_step_fast     one THREAD per env: classifies the env from its key and a few state words and finishes the
+//                   cheap common steps itself (see there); descents and MoveUntil go to the full-path list,
+//                   everything else that needs warp-wide work to the slow list. full_path[] says who ends the step.
 //   k_step_gen      full-path list, high-priority side stream, beside the two kernels below: the whole
 //                   step compiled as one piece with the floor generator. A second, normally empty pass
 //                   after the monster kernel does the reset half of terminal steps that found no
 //                   prefetched game.
-//   k_step_player   every other env: key -> action -> player move / attack / pickup / search, hunger,
+//   k_step_player   slow list, one warp per env: key -> action -> player move / attack / pickup / search, hunger,
 //                   heal. Envs with an active monster go to the monster list; every other env is
 //                   finished here (finish_env).
 //   k_step_monsters monster list only: coin flips, lazy-BFS chase, attacks, then finish_env.
@@ -356,130 +365,342 @@ RG_DEV void finish_env(const DevBatch& b, Ctx& c, int64_t env, int auto_reset, i
   close_env(b, c, env);
 }
 
-// True when this key takes the env down the full path (k_step_gen): MoveUntil, or DownStair while
-// standing on a stair. Evaluated on the state the step starts from, after the same early-outs the
-// player kernel applies (state_impls.rs:52-54, core/src/lib.rs:314,322-327).
-RG_DEV bool takes_full_path(const DevBatch& b, const EnvState* st, int64_t env, int act) {
-  if (act != 1 && act != 3) return false;
-  if (st->error == RG_ERR_PANIC || st->error == RG_ERR_SETTING) return false;
-  if ((int64_t)st->steps > b.max_steps || st->ui_dead) return false;
-  return act == 1 || b.surface[env * b.CP + st->py * b.W + st->px] == S_STAIR;
+// ---------------------------------------------------------------------------------------------
+// k_step_fast: first kernel of a step, ONE THREAD PER ENV. It classifies every env and finishes the
+// common cheap steps itself; whatever needs warp-wide work goes to the warp-per-env kernels through lists.
+//   CL_FULL  descents and MoveUntil -> defer_list (k_step_gen, beside the other kernels)
+//   CL_FAST  the whole step is done here: early-outs (sticky errors, steps > max_steps, invalid key, input after
+//            death), NoOp, NoDownStair, a blocked move, a search with nothing hidden around, and a plain move -
+//            no active monster, no door under either foot, no monster or gold on the target, no monster whose
+//            drawing could change - for which only the <= 4x4 cells around the two positions are read, updated
+//            (Cell::left / Cell::approached, field.rs:20-34) and redrawn
+//   CL_SLOW  everything else -> slow_list (k_step_player)
+// Why the partial redraw is the full redraw: the screen in HBM is persistent and, whenever dirty_rows == 0 and
+// no monster is active, equal to a full compose of the state (every change of the planes, of the player's
+// position or of a drawn entity is followed by a compose in the same step; only ACTIVE monsters move without
+// one). A plain move changes the attr plane inside the two 3x3 neighbourhoods only, moves '@', and - by the
+// eligibility rules - leaves every monster's drawn / hidden status as it was.
+// Instruction count is the point: the warp-per-env kernel spends ~1 000 warp instructions per env-step with
+// 31 of 32 lanes duplicating scalar work (ncu, round 1); here a warp retires 32 envs at once.
+// ---------------------------------------------------------------------------------------------
+enum { CL_FAST = 0, CL_FULL = 1, CL_SLOW = 2 };
+
+RG_DEV uint32_t load4(const uint8_t* plane, int idx) {  // the 4 bytes at plane[idx .. idx+3], idx >= 0, any alignment
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(plane + (idx & ~3));
+  return __funnelshift_r(w[0], w[1], 8 * (idx & 3));
+}
+RG_DEV int cheb(int ax, int ay, int bx, int by) { return max(abs(ax - bx), abs(ay - by)); }
+RG_DEV int lut_room(const DevBatch& b, int x, int y) {  // room_of without a Ctx
+  if (x < 0 || y < 0 || x >= b.W || y >= b.H) return -1;
+  const uint32_t cx = __ldg(b.room_lut + x), ry = __ldg(b.room_lut + 160 + y);
+  return (cx == 0xFFu || ry == 0xFFu) ? -1 : (int)(ry * b.nx + cx);
 }
 
-// First kernel of a step: one thread per env looks at the key only and, for the few keys that can
-// lead to the full path, at the env's position. The full-path list is therefore complete before the
-// player kernel starts, and k_step_gen (a handful of ~150 us serial chains: a descent builds a floor)
-// runs beside the player and monster kernels instead of after them.
-__global__ void __launch_bounds__(256) k_step_scan(DevBatch b, const uint8_t* __restrict__ actions) {
+RG_DEV int fast_env(const DevBatch& b, int64_t env, uint8_t key, int auto_reset) {
+  (void)auto_reset;
+  EnvState* const stp = b.st + env;
+  const uint4* hot = reinterpret_cast<const uint4*>(stp);
+  const uint4 h0 = hot[0], h1 = hot[1], h2 = hot[2], h3 = hot[3], h4 = hot[4];
+  const int px = (int)(int16_t)(h0.x & 0xFFFFu), py = (int)(int16_t)(h0.x >> 16);
+  const uint32_t is_terminal = h0.y & 0xFFu, ui_dead = (h0.y >> 8) & 0xFFu, serr = (h0.y >> 16) & 0xFFu;
+  const uint32_t steps = h0.z;
+  uint32_t food_left = h1.x, quiet = h1.y;
+  const uint32_t gold = h1.z;
+  int32_t hp = (int32_t)h2.y;
+  const int32_t hp_max = (int32_t)h2.z, plevel = (int32_t)h2.w;
+  const uint64_t dirty_rows = ((uint64_t)h3.y << 32) | h3.x;
+  const uint32_t mon_present = h4.x & 0xFFFFu, mon_active = h4.x >> 16;
+  const int W = b.W, H = b.H;
+
+  int d;
+  const int act = map_key(key, d);
+  // ---- the early-outs of GameStateImpl::react / react_to_key (state_impls.rs:52-54, core/src/lib.rs:314,322-327)
+  {
+    int early = -1;
+    if (serr == RG_ERR_PANIC || serr == RG_ERR_SETTING) early = (int)serr;  // the reference's worker is gone
+    else if ((int64_t)steps > b.max_steps) early = 0;
+    else if (act < 0) early = RG_ERR_INVALID_INPUT;
+    else if (ui_dead) early = RG_ERR_IGNORED_INPUT;
+    if (early >= 0) {
+      if (!b.fast) return CL_SLOW;
+      b.reward[env] = 0;
+      b.done[env] = (uint8_t)is_terminal;
+      b.message[env] = h0.w;
+      b.error[env] = (uint8_t)early;
+      if (early) atomicOr(b.errflag, 1u << early);
+      return CL_FAST;
+    }
+  }
+  // ---- the full path: MoveUntil, or DownStair while standing on a stair
+  if (act == 1 || (act == 3 && b.surface[env * b.CP + py * W + px] == S_STAIR)) return CL_FULL;
+  if (!b.fast) return CL_SLOW;
+  if ((int64_t)steps + 1 >= b.max_steps) return CL_SLOW;  // the step ends the episode: finish_env's business
+  if (act != 4 && (mon_active != 0 || plevel >= 8)) return CL_SLOW;  // monster phase / heal draws on the enemy stream
+
+  uint32_t msg = 0;
+  bool moved = false;
+  int nx = px, ny = py;
+  uint64_t rows_touched = 0;
+  const uint8_t* S = b.surface + env * b.CP;
+  uint8_t* A = b.attr + env * b.CP;
+  if (act == 3) {
+    msg = MSG_NO_DOWNSTAIR;
+  } else if (act == 2) {  // Floor::search floor.rs:349-370 with nothing to find: no draw, no change, an empty redraw
+    if (dirty_rows != 0 || px < 1 || py < 1 || px + 1 >= W || py + 1 >= H) return CL_SLOW;
+    uint32_t any = 0;
+#pragma unroll
+    for (int r = -1; r <= 1; ++r) any |= load4(A, (py + r) * W + px - 1) & 0x00FFFFFFu;
+    if (any & (0x010101u * (A_HIDDEN | A_LOCKED))) return CL_SLOW;
+  } else if (act == 0) {  // actions::move_player actions.rs:168-195
+    nx = px + ddx(d);
+    ny = py + ddy(d);
+    bool can = nx >= 0 && ny >= 0 && nx < W && ny < H;
+    if (can) {  // Floor::can_move_impl floor.rs:169-182
+      const int ni = ny * W + nx;
+      can = can_walk(S[ni]) && !(A[ni] & (A_HIDDEN | A_LOCKED));
+      if (can && is_diag(d)) can = can_walk(S[py * W + nx]) && can_walk(S[ny * W + px]);
+    }
+    if (can) {
+      if (dirty_rows != 0) return CL_SLOW;
+      const int pi = py * W + px, ni = ny * W + nx;
+      if ((A[pi] | A[ni]) & A_DOOR) return CL_SLOW;  // leaves_room / enters_room
+      const uint4 i0 = hot[7], i1 = hot[8];
+      const uint32_t items[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+      // the box that holds both 3x3 neighbourhoods, clipped to the field: rows y0..y1 (<= 4), columns x0..x1 (<= 4)
+      const int x0 = max(min(px, nx) - 1, 0), x1 = min(max(px, nx) + 1, W - 1);
+      const int y0 = max(min(py, ny) - 1, 0), y1 = min(max(py, ny) + 1, H - 1);
+      const uint32_t base0 = (uint32_t)(y0 * W + x0);
+      uint32_t item_cells = 0;  // bit r*4+k: an item lies on box cell (y0+r, x0+k)
+#pragma unroll
+      for (int i = 0; i < MAX_ROOMS; ++i) {
+        const uint32_t ip = (items[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+        if (ip == 0xFFFFu) continue;
+        if (ip == (uint32_t)ni) return CL_SLOW;  // pickup: get_item actions.rs:206-231
+        const uint32_t dd = ip - base0;
+        if (dd <= (uint32_t)(3 * W + 3)) {
+          const uint32_t r = dd >= (uint32_t)(3 * W) ? 3u : dd >= (uint32_t)(2 * W) ? 2u : dd >= (uint32_t)W ? 1u : 0u;
+          const uint32_t k = dd - r * (uint32_t)W;
+          if (k < 4u) item_cells |= 1u << (r * 4u + k);
+        }
+      }
+      if (mon_present) {
+        const uint4 m0 = hot[5], m1 = hot[6];
+        const uint32_t mons[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+        const int room_old = lut_room(b, px, py), room_new = lut_room(b, nx, ny);
+#pragma unroll
+        for (int m = 0; m < MAX_ROOMS; ++m) {
+          if (!((mon_present >> m) & 1u)) continue;
+          const uint32_t xy = (mons[m >> 1] >> (16 * (m & 1))) & 0xFFFFu;
+          const int mx = (int)(xy & 0xFFu), my = (int)(xy >> 8);
+          // on the target (player_attack), or close enough for its adjacency / its cell's attributes to change
+          if (cheb(mx, my, px, py) <= 1 || cheb(mx, my, nx, ny) <= 1) return CL_SLOW;
+          const int rm = lut_room(b, mx, my);  // Dungeon::draw_enemy rogue/mod.rs:398-404 -> Floor::in_same_room
+          if (rm >= 0 && (rm == room_old || rm == room_new)) {
+            const RoomD r = stp->rooms[rm];
+            const bool in_m = in_rect(r, mx, my);
+            const bool so = rm == room_old && (r.kind == K_EMPTY || in_rect(r, px, py) == in_m);
+            const bool sn = rm == room_new && (r.kind == K_EMPTY || in_rect(r, nx, ny) == in_m);
+            if (so != sn) return CL_SLOW;
+          }
+        }
+      }
+      // ---- committed: Floor::player_out (floor.rs:298-312), Floor::player_in (:264-295), redraw of the box
+      uint8_t* scr = b.screen + env * b.CP;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int y = y0 + r;
+        if (y > y1) break;
+        const int rb = y * W + x0;
+        const uint32_t sw = load4(S, rb), aw = load4(A, rb);
+        const bool drawn_row = y >= 1 && y < H - 1;  // rows 0 and H-1 are never written (python/src/lib.rs:44)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int x = x0 + k;
+          if (x > x1) break;
+          const uint32_t sv = (sw >> (8 * k)) & 0xFFu, a_in = (aw >> (8 * k)) & 0xFFu;
+          uint32_t a = a_in;
+          const bool near_old = abs(x - px) <= 1 && abs(y - py) <= 1, near_new = abs(x - nx) <= 1 && abs(y - ny) <= 1;
+          if (!near_old && !near_new) continue;  // a corner of the box: nothing changes there (a monster may be drawn on it)
+          if (near_old && sv == S_FLOOR && (a & A_DARK)) a &= ~(uint32_t)A_VISIBLE;  // Cell::left
+          if (x == nx && y == ny) a |= A_VISITED;
+          if (near_new) {  // Cell::approached
+            const bool diag = x != nx && y != ny;
+            if (!(diag && sv == S_PASSAGE) && !(a & A_HIDDEN)) a |= A_DRAWN | A_VISIBLE;
+          }
+          if (a != a_in) A[rb + k] = (uint8_t)a;
+          if (drawn_row) {
+            uint32_t ch = (a & A_VISIBLE) ? surface_tile((uint8_t)(sv & 7u)) : ' ';
+            if (((item_cells >> (r * 4 + k)) & 1u) && (a & (A_VISIBLE | A_DRAWN))) ch = '*';
+            if (x == nx && y == ny && (a & (A_VISIBLE | A_DRAWN))) ch = '@';
+            scr[rb + k] = (uint8_t)ch;
+          }
+        }
+        rows_touched |= 1ull << y;
+      }
+      uint8_t* hb = b.hist + env * b.HB + (ni >> 3);  // Floor::history_map: the one cell that became visited
+      *hb = (uint8_t)(*hb | (1u << (ni & 7)));
+      b.scr_rows[env] |= rows_touched;
+      moved = true;
+    }
+  }
+  // ---- the turn: after_turn (actions.rs:67-80) = Player::turn_passed + heal (player.rs:163-176,221-240); no monster is active
+  bool status_upd = false;
+  if (act != 4) {
+    const rg_params* P = b.cfg_idx ? b.P + b.cfg_idx[env] : b.P;
+    food_left -= 1;
+    if (food_left != 0) {
+      const uint32_t hunger = P->hunger_time / 10;
+      const bool hungry = food_left == hunger || food_left == hunger * 2;
+      quiet += 1;
+      const int amount = max(min((int)quiet + (plevel << 1) - 20, 1), 0);  // plevel < 8
+      bool healed = false;
+      if (amount > 0) {
+        hp = min(hp + amount, hp_max);
+        quiet = 0;
+        healed = true;
+      }
+      status_upd = hungry || healed;
+    }
+    uint4* hw = reinterpret_cast<uint4*>(stp);
+    hw[1] = make_uint4(food_left, quiet, gold, h1.w);
+    if (hp != (int32_t)h2.y) hw[2] = make_uint4(h2.x, (uint32_t)hp, h2.z, h2.w);
+    if (moved) {
+      const uint64_t ov = (((uint64_t)h3.w << 32) | h3.z) | rows_touched;  // a superset is allowed (see EnvState::ov_rows)
+      hw[3] = make_uint4(0u, 0u, (uint32_t)ov, (uint32_t)(ov >> 32));
+    }
+    int32_t reward = 0;
+    if (status_upd) {  // RunTime::player_status -> Status::to_vec (refresh_status)
+      const uint32_t hunger = P->hunger_time / 10;
+      const uint32_t old_gold = stp->status[1];
+      const uint32_t v[10] = {h2.x, gold, (uint32_t)hp, (uint32_t)hp_max, 16u, 16u, 0u, (uint32_t)plevel, h1.w,
+                              food_left <= hunger ? 2u : (food_left <= hunger * 2 ? 1u : 0u)};
+      uint2* sp = reinterpret_cast<uint2*>(stp->status);
+      uint2* op = reinterpret_cast<uint2*>(b.status + env * 10);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) sp[i] = op[i] = make_uint2(v[2 * i], v[2 * i + 1]);
+      const int32_t diff = (int32_t)gold - (int32_t)old_gold;
+      reward = diff > 0 ? diff : 0;
+    }
+    b.reward[env] = reward;
+  } else {
+    b.reward[env] = 0;
+  }
+  // ---- finish (state_impls.rs:56-77): message, step count; not terminal (checked above)
+  {
+    const uint32_t pos = moved ? ((uint32_t)(uint16_t)nx | ((uint32_t)(uint16_t)ny << 16)) : h0.x;
+    reinterpret_cast<uint4*>(stp)[0] = make_uint4(pos, h0.y & 0xFFFFFF00u, steps + 1, msg);
+  }
+  b.done[env] = 0;
+  b.message[env] = msg;
+  b.error[env] = 0;
+  return CL_FAST;
+}
+
+__global__ void __launch_bounds__(128) k_step_fast(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset) {
   const int parity = (int)(*b.dstep & 1u);
+  TraceScope trace(b, TK_FINISH);
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // next step's counters
     b.defer_count[parity ^ 1] = 0;
     b.reset_count[parity ^ 1] = 0;
-    for (int k = 0; k < MAX_CHUNKS; ++k) {
-      b.mon_count[(parity ^ 1) * MAX_CHUNKS + k] = 0;
-      b.mon_count[(2 + (parity ^ 1)) * MAX_CHUNKS + k] = 0;  // the monster kernel's work cursor
-    }
+    b.slow_count[parity ^ 1] = 0;
+    b.slow_count[2 + (parity ^ 1)] = 0;  // the player kernel's work cursor
+    b.mon_count[parity ^ 1] = 0;
+    b.mon_count[2 + (parity ^ 1)] = 0;   // the monster kernel's work cursor
   }
   const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (env >= b.n) return;
-  int d;
-  const int act = map_key(actions[env], d);
-  const bool full = takes_full_path(b, b.st + env, env, act);
-  b.full_path[env] = full ? 1 : 0;  // the player kernel must not look at the env itself: k_step_gen is changing it
-  if (!full) return;
-  atomicAdd(b.stats + RGS_FULL_STEP, 1ull);
-  b.defer_list[atomicAdd(b.defer_count + parity, 1u)] = (uint32_t)env;
+  const int lane = threadIdx.x & 31;
+  int cls = -1;
+  if (env < b.n) {
+    cls = fast_env(b, env, actions[env], auto_reset);
+    b.full_path[env] = cls == CL_FAST ? FP_FAST : cls == CL_FULL ? FP_FULL : FP_PLAYER;
+  }
+  // warp-aggregated appends to the two work lists
+  const uint32_t slowM = __ballot_sync(RG_FULL, cls == CL_SLOW), fullM = __ballot_sync(RG_FULL, cls == CL_FULL);
+  const uint32_t fastM = __ballot_sync(RG_FULL, cls == CL_FAST);
+  uint32_t sbase = 0, fbase = 0;
+  if (lane == 0) {
+    if (slowM) sbase = atomicAdd(b.slow_count + parity, (uint32_t)__popc(slowM));
+    if (fullM) {
+      fbase = atomicAdd(b.defer_count + parity, (uint32_t)__popc(fullM));
+      atomicAdd(b.stats + RGS_FULL_STEP, (unsigned long long)__popc(fullM));
+    }
+    if (fastM) atomicAdd(b.stats + RGS_FAST_STEPS, (unsigned long long)__popc(fastM));
+  }
+  sbase = __shfl_sync(RG_FULL, sbase, 0);
+  fbase = __shfl_sync(RG_FULL, fbase, 0);
+  const uint32_t below = (1u << lane) - 1u;
+  if (cls == CL_SLOW) b.slow_list[sbase + __popc(slowM & below)] = (uint32_t)env;
+  if (cls == CL_FULL) b.defer_list[fbase + __popc(fullM & below)] = (uint32_t)env;
 }
 
-// Player phase of one env (see k_step_player). With SYNC the warps of a block move through the phases
-// together (a block barrier before the action and before the finish): the kernel's top stall is
-// instruction fetch - 4 100 instructions against a 6 KB L0 / 32 KB L1.5 instruction cache - and warps
-// that run the same few hundred instructions at the same time share the fetches.
-template <bool SYNC>
+// Player phase of one env of the slow list: key -> action -> player move / attack / pickup / search, hunger, heal.
+// An env with an active monster is handed to the monster kernel; every other env is finished here.
 RG_DEV void player_env(const DevBatch& b, Stager& sg, unsigned char* base, int64_t env, const uint8_t* __restrict__ actions,
-                       int auto_reset, int parity, int chunk, int64_t lo, int64_t hi) {
-  // The env's state and both planes are requested first; the two small global reads that decide what
-  // to do with them (is the env on the full path? which key?) overlap with the bulk loads instead of
-  // preceding them. k_step_gen may be rewriting a full-path env right now: its data is loaded but never
-  // looked at.
-  const bool present = env < hi;
-  uint8_t on_full_path = 1, key = 0;
-  if (present) {
-    stage_issue(b, sg, base, env, PL_BOTH);
-    on_full_path = b.full_path[env];
-    key = actions[env];
-    stage_wait(sg);
-  }
-  if (SYNC) __syncthreads();
+                       int auto_reset, int parity) {
+  // The env's state and both planes are requested first; the key is read while the bulk loads fly.
+  stage_issue(b, sg, base, env, PL_BOTH);
+  const uint8_t key = actions[env];
+  stage_wait(sg);
   Ctx c;
-  int d = 0, act = 4;
-  // what is left to do for this env: 0 nothing, 1 report `err` only, 2 the normal path
-  int todo = 0;
+  int d = 0;
+  const int act = map_key(key, d);
+  fill_ctx(b, c, sg, base, env, PL_BOTH, true);
+  EnvState* st = c.st;
+  // what is left to do for this env: 1 report `err` only, 2 the normal path
+  int todo = 1;
   uint8_t err = 0;
-  if (!on_full_path) {  // otherwise on k_step_scan's list: the whole step runs in k_step_gen, concurrently
-    act = map_key(key, d);
-    fill_ctx(b, c, sg, base, env, PL_BOTH, true);
-    EnvState* st = c.st;
-    todo = 1;
-    if (st->error == RG_ERR_PANIC || st->error == RG_ERR_SETTING) err = st->error;  // the reference's worker is gone
-    else if ((int64_t)st->steps > b.max_steps) err = 0;                           // state_impls.rs:52-54
-    else if (act < 0) err = RG_ERR_INVALID_INPUT;  // ErrorKind::InvalidInput: nothing changes (core/src/lib.rs:322-327)
-    else if (st->ui_dead) err = RG_ERR_IGNORED_INPUT;  // UiState::Mordal(Grave) + Act => IgnoredInput (core/src/lib.rs:314)
-    else todo = 2;
-    if (todo == 2) {
-      st->f_gold_before = st->status[1];
-      if (act == 0 || act == 2) {
-        process_action<true>(c, act, d);
-      } else if (act == 3) {
-        process_action<true>(c, act, d);  // NoDownStair: a turn passes, the grid is not consulted
-      }
-    }
-  }
-  if (SYNC) __syncthreads();
+  if (st->error == RG_ERR_PANIC || st->error == RG_ERR_SETTING) err = st->error;  // the reference's worker is gone
+  else if ((int64_t)st->steps > b.max_steps) err = 0;                           // state_impls.rs:52-54
+  else if (act < 0) err = RG_ERR_INVALID_INPUT;  // ErrorKind::InvalidInput: nothing changes (core/src/lib.rs:322-327)
+  else if (st->ui_dead) err = RG_ERR_IGNORED_INPUT;  // UiState::Mordal(Grave) + Act => IgnoredInput (core/src/lib.rs:314)
+  else todo = 2;
   if (todo == 1) {
     emit_obs(b, c, env, 0, err);
-  } else if (todo == 2) {
-    EnvState* st = c.st;
-    if (act != 4 && !c.panic && has_active_monster(c)) {
-      // hand over to the monster kernel: it runs the monster phase and then finishes the step
-      st->f_msg = c.msg;
-      st->f_flags = (uint8_t)((c.redraw ? SF_REDRAW : 0) | (c.status_upd ? SF_STATUS : 0));
-      if (c.lane == 0) {
-        b.mon_list[lo + atomicAdd(b.mon_count + parity * MAX_CHUNKS + chunk, 1u)] = (uint32_t)env;
-        b.full_path[env] = 2;  // finished by the monster kernel
-      }
-      count_event(b, c, RGS_MONSTER_ENVS);
-      close_env(b, c, env);
-    } else {
-      finish_env(b, c, env, auto_reset, parity);  // no monster moves this turn: the step ends here
+    return;
+  }
+  st->f_gold_before = st->status[1];
+  if (act == 0 || act == 2 || act == 3) process_action<true>(c, act, d);  // act 3 here = NoDownStair: a turn passes
+  if (act != 4 && !c.panic && has_active_monster(c)) {
+    // hand over to the monster kernel: it runs the monster phase and then finishes the step
+    st->f_msg = c.msg;
+    st->f_flags = (uint8_t)((c.redraw ? SF_REDRAW : 0) | (c.status_upd ? SF_STATUS : 0));
+    if (c.lane == 0) {
+      b.mon_list[atomicAdd(b.mon_count + parity, 1u)] = (uint32_t)env;
+      b.full_path[env] = FP_MONSTERS;
     }
+    count_event(b, c, RGS_MONSTER_ENVS);
+    close_env(b, c, env);
+  } else {
+    finish_env(b, c, env, auto_reset, parity);  // no monster moves this turn: the step ends here
   }
 }
 
-__global__ void __launch_bounds__(PLAYER_WPB * 32, RG_HOT_MIN_BLOCKS / PLAYER_WPB)
-k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset, int chunk) {
+// One-warp blocks over the slow list (what k_step_fast left). Envs are handed out one at a time: their cost
+// varies (a room reveal, a fight, an episode end with its 10 KB swap-in).
+__global__ void __launch_bounds__(32, RG_HOT_MIN_BLOCKS)
+k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset) {
   unsigned char* const smem = rg_smem;
   const int parity = (int)(*b.dstep & 1u);
   TraceScope trace(b, TK_PLAYER);
-  const int warp = threadIdx.x >> 5;
-  unsigned char* const base = smem + (size_t)warp * warp_smem(b);
-  Stager sg = stager_init(b, base);
-  const int64_t lo = b.n * chunk / b.chunks, hi = b.n * (chunk + 1) / b.chunks;  // this launch's piece of the env range
-  // the trip count is the same for every warp of a block (the block barriers need that)
-  for (int64_t env0 = lo + (int64_t)blockIdx.x * PLAYER_WPB; env0 < hi; env0 += (int64_t)gridDim.x * PLAYER_WPB) {
-    player_env<(PLAYER_WPB > 1)>(b, sg, base, env0 + warp, actions, auto_reset, parity, chunk, lo, hi);
+  const uint32_t count = b.slow_count[parity];
+  Stager sg = stager_init(b, smem);
+  for (;;) {
+    uint32_t i = 0;
+    if (threadIdx.x == 0) i = atomicAdd(b.slow_count + 2 + parity, 1u);
+    i = __shfl_sync(RG_FULL, i, 0);
+    if (i >= count) break;
+    player_env(b, sg, smem, (int64_t)b.slow_list[i], actions, auto_reset, parity);
     __syncwarp();
   }
 }
 
 // actions::move_active_enemies (actions.rs:82-119) for the envs that have an active monster
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 16)
-k_step_monsters(DevBatch b, int auto_reset, int chunk) {
+k_step_monsters(DevBatch b, int auto_reset) {
   unsigned char* const smem = rg_smem;
   const int parity = (int)(*b.dstep & 1u);
   TraceScope trace(b, TK_MONSTERS);
-  const int64_t lo = b.n * chunk / b.chunks;
-  const uint32_t count = b.mon_count[parity * MAX_CHUNKS + chunk];
+  const uint32_t count = b.mon_count[parity];
   const int warp = threadIdx.x >> 5;
   unsigned char* const base = smem + (size_t)warp * warp_smem(b);
   Stager sg = stager_init(b, base);
@@ -487,10 +708,10 @@ k_step_monsters(DevBatch b, int auto_reset, int chunk) {
   // and warps on SMs that also host a background generator block run slower
   for (;;) {
     uint32_t i = 0;
-    if ((threadIdx.x & 31) == 0) i = atomicAdd(b.mon_count + (2 + parity) * MAX_CHUNKS + chunk, 1u);
+    if ((threadIdx.x & 31) == 0) i = atomicAdd(b.mon_count + 2 + parity, 1u);
     i = __shfl_sync(RG_FULL, i, 0);
     if (i >= count) break;
-    const int64_t env = (int64_t)b.mon_list[lo + i];
+    const int64_t env = (int64_t)b.mon_list[i];
     Ctx c;
     fill_ctx(b, c, sg, base, env, PL_BOTH);  // surface for the moves, both planes if the step ends with a compose
     EnvState* st = c.st;
@@ -1077,7 +1298,7 @@ cudaError_t configure_kernels(const DevBatch& b) {
   size_t sm = block_smem(b);
   cudaError_t e = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_step_player, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PLAYER_WPB * one_warp_smem(b)));
+  e = cudaFuncSetAttribute(k_step_player, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one_warp_smem(b));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_step_monsters, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return e;
@@ -1095,19 +1316,18 @@ cudaError_t launch_reset(const DevBatch& b, cudaStream_t s) {
   k_reset<<<blocks, WARPS_PER_BLOCK * 32, block_smem(b), s>>>(b);
   return cudaGetLastError();
 }
-// Enqueues one env-step: key scan, the full-path kernel on `side` beside the player and monster
-// kernels, the synchronous-reset pass, the join, and the step counter. No per-step
-// arguments (the step parity lives on the device, the actions are read from a fixed buffer), so
+// Enqueues one env-step: the thread-per-env kernel (classification + the cheap steps), the full-path kernel on
+// `side` beside the player and monster kernels, the synchronous-reset pass, the join, and the step counter. No
+// per-step arguments (the step parity lives on the device, the actions are read from a fixed buffer), so
 // the whole sequence is captured once into a CUDA graph and replayed with one launch per step.
 cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_reset, const StepStreams& q,
                         const MirrorArgs* mirror, int sm_count) {
   cudaStream_t s = q.main;
-  const int blocks = (int)((b.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
   const size_t sm = block_smem(b);
   int gen_blocks = (int)std::min<int64_t>(b.gen_warps / GEN_WPB, (b.n + GEN_WPB - 1) / GEN_WPB);
   const size_t gen_sm = GEN_WPB * one_warp_smem(b);
   cudaError_t e;
-  k_step_scan<<<(unsigned)((b.n + 255) / 256), 256, 0, s>>>(b, actions);
+  k_step_fast<<<(unsigned)((b.n + 127) / 128), 128, 0, s>>>(b, actions, auto_reset);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   // full-path steps (descents, MoveUntil) are a few long serial chains: they start first, on the
   // high-priority side stream, and run beside the player and monster kernels
@@ -1116,43 +1336,22 @@ cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_rese
   k_step_gen<<<gen_blocks, GEN_WPB * 32, gen_sm, q.side>>>(b, actions, auto_reset, 0, 0);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if ((e = cudaEventRecord(q.ev_join, q.side)) != cudaSuccess) return e;
-  // The env range goes through in `chunks` pieces: the monster kernel of piece k (a few thousand
-  // latency-bound warps) runs on its own high-priority stream beside the player kernel of piece k+1
-  // (a throughput kernel), so only the last piece's monster phase is exposed.
-  for (int k = 0; k < b.chunks; ++k) {
-    const int64_t lo = b.n * k / b.chunks, hi = b.n * (k + 1) / b.chunks;
-    const int pblocks = (int)((hi - lo + PLAYER_WPB - 1) / PLAYER_WPB);
-    if (pblocks <= 0) continue;
-    k_step_player<<<b.player_blocks > 0 ? std::min(pblocks, b.player_blocks) : pblocks, PLAYER_WPB * 32,
-                    PLAYER_WPB * one_warp_smem(b), s>>>(b, actions, auto_reset, k);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    cudaStream_t ms = b.chunks > 1 ? q.mon : s;
-    if (b.chunks > 1 || mirror) {
-      if ((e = cudaEventRecord(q.ev_chunk[k], s)) != cudaSuccess) return e;  // this piece's player kernel is done
-    }
-    if (b.chunks > 1) {
-      if ((e = cudaStreamWaitEvent(q.mon, q.ev_chunk[k], 0)) != cudaSuccess) return e;
-    }
-    int mon_blocks = (int)std::min<int64_t>(b.mon_warps / WARPS_PER_BLOCK, (hi - lo + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-    k_step_monsters<<<mon_blocks, WARPS_PER_BLOCK * 32, sm, ms>>>(b, auto_reset, k);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    if (mirror) {
-      // host mirror, first pass: the envs of this piece that the player kernel finished (most of them),
-      // beside the monster, full-path and reset kernels (and the next piece's player kernel) - the pass
-      // is dominated by small PCIe writes, not by SM work
-      if ((e = cudaStreamWaitEvent(q.mir, q.ev_chunk[k], 0)) != cudaSuccess) return e;
-      k_mirror<<<mirror_blocks(b, sm_count), 256, 0, q.mir>>>(b, *mirror, 1, lo, hi);
-      if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    }
-  }
   if (mirror) {
+    // host mirror, first pass: the envs k_step_fast finished (most of them), beside every other kernel of the
+    // step - the pass is dominated by small PCIe writes, not by SM work
+    if ((e = cudaStreamWaitEvent(q.mir, q.ev_fork, 0)) != cudaSuccess) return e;
+    k_mirror<<<mirror_blocks(b, sm_count), 256, 0, q.mir>>>(b, *mirror, 1, 0, b.n);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if ((e = cudaEventRecord(q.ev_mir, q.mir)) != cudaSuccess) return e;
   }
-  if (b.chunks > 1) {
-    if ((e = cudaEventRecord(q.ev_mon, q.mon)) != cudaSuccess) return e;
-    if ((e = cudaStreamWaitEvent(s, q.ev_mon, 0)) != cudaSuccess) return e;
+  {
+    const int pblocks = (int)std::min<int64_t>(b.player_blocks > 0 ? b.player_blocks : (int64_t)sm_count * RG_HOT_MIN_BLOCKS, b.n);
+    k_step_player<<<pblocks, 32, one_warp_smem(b), s>>>(b, actions, auto_reset);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    const int mon_blocks = (int)std::min<int64_t>(b.mon_warps / WARPS_PER_BLOCK, (b.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    k_step_monsters<<<mon_blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, auto_reset);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
-  (void)blocks;
   if ((e = cudaStreamWaitEvent(s, q.ev_join, 0)) != cudaSuccess) return e;
   if (auto_reset) {
     // episode ends whose next game was not prefetched in time (normally none; with prefetching on, a
@@ -1163,7 +1362,7 @@ cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_rese
     k_step_end<<<1, 32, 0, s>>>(b, auto_reset);
   }
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  if (mirror) {  // second pass: the envs that were finished by the monster, full-path and reset kernels
+  if (mirror) {  // second pass: the envs that were finished by the player, monster, full-path and reset kernels
     if ((e = cudaStreamWaitEvent(s, q.ev_mir, 0)) != cudaSuccess) return e;
     k_mirror<<<mirror_blocks(b, sm_count), 256, 0, s>>>(b, *mirror, 2, 0, b.n);
   }

@@ -26,12 +26,10 @@ struct MirrorArgs {
 struct StepStreams {
   cudaStream_t main;   // the batch's stream
   cudaStream_t side;   // high priority: the full-path kernel
-  cudaStream_t mon;    // high priority: monster kernels when the env range is stepped in pieces
-  cudaStream_t mir;    // first host-mirror pass, beside the monster / full-path / reset kernels
-  cudaEvent_t ev_fork, ev_join, ev_mon, ev_player, ev_mir;
-  cudaEvent_t ev_chunk[MAX_CHUNKS];
+  cudaStream_t mir;    // first host-mirror pass, beside the player / monster / full-path / reset kernels
+  cudaEvent_t ev_fork, ev_join, ev_mir;
 };
-// one env-step = scan, full-path kernel beside {player, monster} kernels per piece, reset pass, end
+// one env-step = thread-per-env kernel, full-path kernel beside {player, monster} kernels, reset pass, end
 // `mirror` != nullptr adds the two host-mirror passes to the step (rg_step_mirror)
 cudaError_t launch_step(const DevBatch& b, const uint8_t* actions_dev, int auto_reset, const StepStreams& q,
                         const MirrorArgs* mirror, int sm_count);

@@ -12,6 +12,7 @@
 //   st        EnvState [N]     everything scalar / small        (RunTime + GameStateImpl + PlayerState.status)
 // CP = W*H rounded up to 16, HB = CP/8 rounded up to 16, WW = ceil(W/32).
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/rogue_b200.h"
@@ -21,7 +22,6 @@ namespace rg {
 constexpr int MAX_ROOMS = RG_MAX_ROOMS;
 constexpr int NCACHE = RG_DIST_CACHE;
 constexpr int SP_DEPTH = 2;  // prefetched next-episode games kept per env
-constexpr int MAX_CHUNKS = 8;  // pieces of the env range in one step (see launch_step)
 
 // Surface codes follow the reference's declaration order (rogue/mod.rs:137-146).
 enum : uint8_t { S_PASSAGE = 0, S_FLOOR = 1, S_WALLX = 2, S_WALLY = 3, S_STAIR = 4, S_DOOR = 5, S_TRAP = 6, S_NONE = 7 };
@@ -35,7 +35,9 @@ enum : uint8_t { K_NORMAL = 0, K_MAZE = 1, K_EMPTY = 2 };
 enum : uint8_t { RF_DARK = 1, RF_VISITED = 2, RF_GOLD = 4 };
 enum : uint8_t { MF_PRESENT = 1, MF_ACTIVE = 2 };
 enum { RGS_SWAP_IN = 0, RGS_SYNC_RESET = 1, RGS_FULL_STEP = 2, RGS_PREFETCH_BUILT = 3, RGS_PREFETCH_STALE = 4,
-       RGS_MONSTER_ENVS = 5, RGS_BFS_LEVELS = 6 };
+       RGS_MONSTER_ENVS = 5, RGS_BFS_LEVELS = 6, RGS_FAST_STEPS = 7 };
+// full_path[env]: which kernel leaves the env's step final (the host mirror's first pass takes the FP_FAST ones)
+enum : uint8_t { FP_FAST = 0, FP_FULL = 1, FP_MONSTERS = 2, FP_RESET = 3, FP_PLAYER = 5 };
 enum : uint8_t { SF_REDRAW = 1, SF_STATUS = 2, SF_DEAD = 4, SF_SKIP = 8, SF_PANIC = 16 };
 // EnemyAttr bits that the path reads (enemies.rs:125-137)
 enum : uint32_t { EA_MEAN = 1u, EA_RANDOM = 0x200u, EA_CONFUSED = 0x400u };
@@ -58,38 +60,52 @@ struct MonD {        // enemies.rs:159-171; level/defense/dice come from the kin
   uint32_t exp;
 };
 
+// The first HOT_BYTES bytes hold everything the thread-per-env fast kernel (k_step_fast) reads or writes, as
+// 16-byte pieces it loads with 128-bit accesses; the warp-per-env kernels stage the whole struct in shared memory.
 struct alignas(16) EnvState {
-  uint32_t rng[12];        // dungeon, item, enemy xorshift128 states
-  uint32_t seed[4];        // seed used by the next reset (thread_impls.rs:125-128)
-  uint32_t status[10];     // DISPLAYED status (stale semantics, state_impls.rs:63-65)
-  int32_t level;
-  int32_t hp, hp_max;
-  uint32_t exp;
-  int32_t plevel;
-  uint32_t food_left, quiet, gold;
-  uint32_t steps, message;
-  uint32_t episode;        // resets so far (drives fresh seeds when the config has none)
+  // piece 0
   int16_t px, py;
   uint8_t is_terminal, ui_dead, error, seeded;
-  uint8_t cache_n, cache_head, pad0, pad1;
-  uint8_t cache_x[NCACHE + 1], cache_y[NCACHE + 1];
-  uint32_t pad2;
-  uint16_t cache_lvl[NCACHE + 1];  // BFS levels finished per slot, 0xFFFF = map complete (lazy DistCache)
+  uint32_t steps, message;
+  // piece 1
+  uint32_t food_left, quiet, gold, exp;
+  // piece 2
+  int32_t level, hp, hp_max, plevel;
+  // piece 3: incremental compose - the screen is persistent, so only rows that can differ are recomputed
+  uint64_t dirty_rows;     // bit r: a cell of row r changed in the tile planes since the last compose
+  uint64_t ov_rows;        // bit r: the last compose drew an overlay (monster, item, player) in row r (may be a superset)
+  // piece 4: monster summary (recomputed from mon[] by every write-back of a warp kernel, see write_back)
+  uint16_t mon_present;    // bit m: mon[m] is present
+  uint16_t mon_active;     // bit m: mon[m] is present and active
+  uint32_t episode;        // resets so far (drives fresh seeds when the config has none)
   // per-step hand-over between the phase kernels (player -> monsters -> finish)
   uint32_t f_msg;          // message bits collected so far
   uint32_t f_gold_before;  // displayed gold when the step began (reward = max(0, after - before))
+  // pieces 5-6, 7-8
+  uint16_t mon_xy[MAX_ROOMS];    // x | y << 8 of mon[m] (valid where mon_present has the bit)
+  uint16_t item_pos[MAX_ROOMS];  // y*W+x or 0xFFFF ; slot = room id
+  // pieces 9-11
+  uint32_t status[10];     // DISPLAYED status (stale semantics, state_impls.rs:63-65)
   uint16_t cache_snap;     // bit s: cache slot s resumes on its private walkability snapshot (wsnap)
   uint8_t f_flags;         // SF_*
-  uint8_t pad3;
-  // incremental compose: the screen is persistent, so only rows that can differ are recomputed
-  uint64_t dirty_rows;     // bit r: a cell of row r changed in the tile planes since the last compose
-  uint64_t ov_rows;        // bit r: the last compose drew an overlay (monster, item, player) in row r
+  uint8_t cache_n, cache_head, pad0, pad1, pad2;
+  // ---- not touched by the fast kernel
+  uint32_t rng[12];        // dungeon, item, enemy xorshift128 states
+  uint32_t seed[4];        // seed used by the next reset (thread_impls.rs:125-128)
+  uint8_t cache_x[NCACHE + 1], cache_y[NCACHE + 1];
+  uint32_t pad3;
+  uint16_t cache_lvl[NCACHE + 1];  // BFS levels finished per slot, 0xFFFF = map complete (lazy DistCache)
+  uint32_t pad4;
   RoomD rooms[MAX_ROOMS];
-  uint16_t item_pos[MAX_ROOMS];  // y*W+x or 0xFFFF ; slot = room id
   uint32_t item_amt[MAX_ROOMS];
   MonD mon[MAX_ROOMS];           // slot = room id the monster was spawned in
 };
+constexpr int HOT_BYTES = 192;
 static_assert(sizeof(EnvState) % 16 == 0, "EnvState must be a multiple of 16 bytes");
+static_assert(offsetof(EnvState, food_left) == 16 && offsetof(EnvState, level) == 32 && offsetof(EnvState, dirty_rows) == 48 &&
+                  offsetof(EnvState, mon_present) == 64 && offsetof(EnvState, mon_xy) == 80 &&
+                  offsetof(EnvState, item_pos) == 112 && offsetof(EnvState, status) == 144 && offsetof(EnvState, rng) == HOT_BYTES,
+              "k_step_fast unpacks the hot block by offset");
 
 struct DevBatch {
   int64_t n;
@@ -119,7 +135,10 @@ struct DevBatch {
   uint64_t* scr_rows; // [N] bit r: row r of screen / history was rewritten since the host mirror last looked
   uint32_t* defer_list;   // [N] env id | DEFER_* : work handed to the full-path kernel k_step_gen
   uint32_t* defer_count;  // [2] ping-pong by step parity
-  uint8_t* full_path;     // [N] 1 = this step of the env runs in k_step_gen (written by k_step_scan every step)
+  uint8_t* full_path;     // [N] who finishes this step of the env (FP_*), written by k_step_fast every step
+  uint32_t* slow_list;    // [N] envs k_step_fast left to the warp-per-env player kernel
+  uint32_t* slow_count;   // [2] ping-pong by step parity, then [2] work cursors of the player kernel
+  int32_t fast;           // 0 = k_step_fast only classifies (every env goes to the player kernel; RG_FAST=0)
   uint32_t* reset_list;   // [N] terminal envs whose next game was not prefetched in time (finish_env -> reset pass of k_step_gen)
   uint32_t* reset_count;  // [2]
   // "next episode" buffers, filled in the background by k_prefetch and swapped in by finish_env
@@ -145,11 +164,10 @@ struct DevBatch {
   int32_t pf_wpb;         // warps per block of k_prefetch (0 = default)
   int32_t pf_exclusive;   // k_prefetch blocks take a whole SM each (see launch_prefetch)
   int32_t prefetch;       // 0 = off (every reset is generated synchronously by k_step_gen)
-  uint32_t* mon_list;     // [N] envs with an active monster this step (player kernel -> monster kernel); chunk k's list starts at its first env id
-  uint32_t* mon_count;    // [2][MAX_CHUNKS] list lengths by step parity and chunk, then [2][MAX_CHUNKS] work cursors
-  int32_t chunks;         // the env range is stepped in this many pieces (player kernel k+1 beside monster kernel k)
+  uint32_t* mon_list;     // [N] envs with an active monster this step (player kernel -> monster kernel)
+  uint32_t* mon_count;    // [2] list lengths by step parity, then [2] work cursors
   int32_t mon_warps;      // warps of the (grid-stride) monster kernel
-  int32_t player_blocks;  // > 0: the player kernel runs as that many persistent blocks (grid-stride); 0: one block per env
+  int32_t player_blocks;  // > 0: one-warp blocks of the player kernel (default: 32 per SM)
 };
 
 }  // namespace rg

@@ -38,7 +38,8 @@ def synthetic_actions(t, env_ids):
 class Shard:
     """One GPU's block of envs behind the raw C ABI (device-resident stepping, no per-env objects)."""
 
-    def __init__(self, config_json, env_lo, env_hi, max_steps=1000, device=0, base_seed=1):
+    def __init__(self, config_json, env_lo, env_hi, max_steps=1000, device=0, base_seed=1, seeds=None):
+        """seeds: None = env i gets base_seed + i; else (lo, hi) uint64 arrays, one 128-bit seed per env."""
         self.L = _cabi.lib()
         self.n = env_hi - env_lo
         self.env_ids = np.arange(env_lo, env_hi, dtype=np.uint64)
@@ -50,11 +51,15 @@ class Shard:
         _cabi.check(self.L.rg_parse_config(config_json.encode(), C.byref(self.params), None, 0))
         self.W, self.H = self.params.width, self.params.height
         self.base_seed = base_seed
+        self.seeds = seeds
         self.reseed_and_reset()
 
     def reseed_and_reset(self):
-        seeds = env_seeds(self.env_ids, self.base_seed)
-        _cabi.check(self.L.rg_seed(self.h, seeds.ctypes.data, None), self.h)
+        if self.seeds is None:
+            lo, hi = env_seeds(self.env_ids, self.base_seed), None
+        else:
+            lo, hi = (np.ascontiguousarray(a, np.uint64) for a in self.seeds)
+        _cabi.check(self.L.rg_seed(self.h, lo.ctypes.data, hi.ctypes.data if hi is not None else None), self.h)
         _cabi.check(self.L.rg_reset(self.h), self.h)
         rc = self.L.rg_sync(self.h)
         if rc not in (_cabi.RG_OK, _cabi.RG_ERR_PANIC):
@@ -113,7 +118,8 @@ class Shard:
     def stats(self):
         out = np.zeros(8, np.uint64)
         _cabi.check(self.L.rg_stats(self.h, out.ctypes.data), self.h)
-        names = ("swap_in", "sync_reset", "full_step", "prefetch_built", "prefetch_stale", "monster_env_steps")
+        names = ("swap_in", "sync_reset", "full_step", "prefetch_built", "prefetch_stale", "monster_env_steps", "bfs_levels",
+                 "fast_steps")
         return {k: int(v) for k, v in zip(names, out)}
 
     def launches(self):

@@ -38,7 +38,8 @@ def _raw_batch(cabi, cfg, n, max_steps, seeds):
 def _stats(L, h, cabi):
     out = np.zeros(8, np.uint64)
     cabi.check(L.rg_stats(h, out.ctypes.data), h)
-    names = ("swap_in", "sync_reset", "full_step", "prefetch_built", "prefetch_stale", "monster_env_steps")
+    names = ("swap_in", "sync_reset", "full_step", "prefetch_built", "prefetch_stale", "monster_env_steps", "bfs_levels",
+             "fast_steps")
     return {k: int(v) for k, v in zip(names, out)}
 
 
