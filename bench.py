@@ -27,6 +27,7 @@ sys.path.insert(0, os.path.join(ROOT, "rogue-gym_b200", "python"))
 
 ENVS_PER_GPU = 65536
 MAX_STEPS = 1000
+BURN_IN = 600
 CONFIG = {}  # config-default: every field at its default ("{}" => default, core/src/lib.rs:453-457)
 # algorithmic bytes of one env-step with the compact observation at 80x24
 #   read  grid 2C (3840) + small state 1536 + action 1
@@ -146,17 +147,17 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     n = args.envs_per_gpu
     t0 = time.time()
-    value, secs = cpu_port_rollout(n, args.steps, args.warmup, threads)
+    value, secs = cpu_port_rollout(n, args.steps, args.burn_in + args.warmup, threads)
     long_v, long_s = cpu_port_rollout(min(8192, n), args.long_steps, 0, threads)
     line = {
         "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_total": n, "envs_per_gpu": n,
+        "config": {"workload": WORKLOAD, "envs_total": n, "envs_per_gpu": n, "burn_in_steps": args.burn_in,
                    "note": "CPU arm: one GPU's shard (%d envs) whatever --gpus says; %d host threads" % (n, threads)},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                         "sample": "all %d envs x %d steps (+%d warm-up), C++ oracle port of the Rust core; the Rust reference "
-                                   "cannot be built here (no rustc/cargo, crates not vendored)" % (n, args.steps, args.warmup),
+                         "sample": "all %d envs x %d steps (after %d burn-in + %d warm-up steps), C++ oracle port of the Rust core; the Rust "
+                                   "reference cannot be built here (no rustc/cargo, crates not vendored)" % (n, args.steps, args.burn_in, args.warmup),
                          "long_window": {"value": long_v, "unit": "env-steps/s",
                                          "sample": "%d envs x %d steps (%.1f s)" % (min(8192, n), args.long_steps, long_s)}},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -183,7 +184,8 @@ def run_extras(args, rank, world, local_rank, lo, dev_actions, barrier, reduce_m
     from rogue_gym_python import _cabi
     from rogue_gym_python.rollout import Shard
     n = args.envs_per_gpu
-    K, Wm = min(args.steps, 600), min(args.warmup, 100)
+    K = min(args.steps, 600)
+    Wm = max(0, args.burn_in) + min(args.warmup, 100)  # same burn-in as the headline
     dev = torch.device("cuda", local_rank)
     threads = os.cpu_count() or 1
     out = {}
@@ -221,7 +223,7 @@ def run_extras(args, rank, world, local_rank, lo, dev_actions, barrier, reduce_m
     err, chk = check(sh, CONFIG, dn, [int(slo[i]) | (int(shi[i]) << 64) for i in range(dn)])
     sh.close()
     ms_all, live_all = reduce_max_sum(ms, float((err == 0).sum()))
-    out["mixed_seeds"] = {"workload": WORKLOAD + "; seeds = splitmix64-mixed 128-bit per env", "steps": K, "warmup": Wm,
+    out["mixed_seeds"] = {"workload": WORKLOAD + "; seeds = splitmix64-mixed 128-bit per env", "steps": K, "untimed_steps_before": Wm,
                           "ms_per_step": ms_all / K, "value": live_all * K / (ms_all * 1e-3), "unit": "env-steps/s",
                           "panicked_envs": int(n * world - live_all), "oracle_check_rank0": chk}
     # (2) BASELINE configs[1]: 4 096 envs per GPU, config-mini
@@ -233,7 +235,7 @@ def run_extras(args, rank, world, local_rank, lo, dev_actions, barrier, reduce_m
     sh.close()
     ms_all, live_all = reduce_max_sum(ms, float((err == 0).sum()))
     out["mini_4096"] = {"workload": "4096 envs/GPU, config-mini 32x16 (2x2 rooms), seeds 1+i, random 11-action rollout", "steps": K,
-                        "warmup": Wm, "ms_per_step": ms_all / K, "value": live_all * K / (ms_all * 1e-3), "unit": "env-steps/s",
+                        "untimed_steps_before": Wm, "ms_per_step": ms_all / K, "value": live_all * K / (ms_all * 1e-3), "unit": "env-steps/s",
                         "panicked_envs": int(m * world - live_all), "oracle_check_rank0": chk}
     # (3) BASELINE configs[4]: reset-only, 65 536 envs x 16 resets per size, fresh seeds every reset
     out["reset_sweep"] = {}
@@ -293,6 +295,9 @@ def main():
     ap.add_argument("--no-oracle-check", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--long-steps", type=int, default=4000, help="steps of the long-window CPU sample (8192 envs)")
+    ap.add_argument("--burn-in", type=int, default=BURN_IN,
+                    help="untimed steps from reset before the warm-up: brings the batch to the desynchronised steady state "
+                         "of a long rollout (right after a reset every env is in its monster-heavy first steps)")
     ap.add_argument("--config-json", default=None, help="experiments only: replaces config-default (the line is then not the headline workload)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -317,7 +322,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
 
-    K, Wm, n = args.steps, args.warmup, args.envs_per_gpu
+    K, n, B = args.steps, args.envs_per_gpu, max(0, args.burn_in)
+    Wm = B + args.warmup  # untimed steps before the timed region: burn-in from reset, then the warm-up proper
     lo, hi = shard_range(n * world, rank, world)
     shard = Shard(args.config_json or json.dumps(CONFIG), lo, hi, max_steps=MAX_STEPS, device=local_rank)
     stream = torch.cuda.ExternalStream(shard.stream(), device=torch.device("cuda", local_rank))
@@ -469,10 +475,10 @@ def main():
         kernel_ms = ms / K
         achieved = BYTES_PER_ENV_STEP * n / (kernel_ms * 1e-3) / 1e9
         line = {
-            "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD if not args.config_json else "EXPERIMENT " + args.config_json, "envs_total": total_envs, "envs_per_gpu": n, "sharding": "contiguous env-id blocks, no collective",
+            "config": {"workload": WORKLOAD if not args.config_json else "EXPERIMENT " + args.config_json, "burn_in_steps": B, "envs_total": total_envs, "envs_per_gpu": n, "sharding": "contiguous env-id blocks, no collective",
                        "cache": "inputs larger than L2: each step touches ~%.0f MB of env state per GPU (L2 is 126 MB)" % (n * 9000 / 1e6),
                        "live_envs": int(live_all), "panicked_envs": int(total_envs - live_all),
                        "panic_note": "envs in a state where the reference panics (monster at x=0 probing x=-1, rogue/mod.rs:361) are sticky-dead like the reference's worker and are not counted",

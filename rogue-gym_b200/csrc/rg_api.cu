@@ -37,6 +37,13 @@ struct rg_batch {
     q.ev_fork = ev_fork; q.ev_join = ev_join; q.ev_mir = ev_mir;
     return q;
   }
+  // background builder of next-level skeletons (speculative descents): one pass per step, on SPEC_STREAMS rotating
+  // streams so that a pass (one skeleton ~ 140 us) has several steps' time before the main stream waits for it
+  static constexpr int SPEC_STREAMS = 4;
+  cudaStream_t spec[SPEC_STREAMS] = {};
+  cudaEvent_t ev_spec[SPEC_STREAMS] = {};  // end of the last pass on each stream
+  cudaEvent_t ev_step = nullptr;  // "this step is queued up to here" for the skeleton pass
+  int64_t spec_passes = 0;
   cudaEvent_t ev_main = nullptr;  // "this step's kernels are queued up to here"
   cudaEvent_t ev_bg[2] = {nullptr, nullptr};  // end of the last pass on each background stream
   int64_t passes = 0;             // background passes kicked so far
@@ -302,6 +309,38 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
     for (size_t i = 0; i < init.size(); ++i) init[i] = (i & 1) ? 0ull : ~0ull;
     RG_TRY(cudaMemcpy(d.trace, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
   }
+  {  // speculative descents (RG_SPEC=0 turns them off)
+    const char* sp = getenv("RG_SPEC");
+    d.spec = (sp && sp[0] == '0') ? 0 : 1;
+    if (d.spec) {
+      RG_TRY(dev_alloc(b, &d.spec_S, N * d.CP));
+      RG_TRY(dev_alloc(b, &d.spec_A, N * d.CP));
+      RG_TRY(dev_alloc(b, &d.spec_rooms, N * rg::MAX_ROOMS));
+      RG_TRY(dev_alloc(b, &d.spec_tag, N));
+      RG_TRY(cudaMemsetAsync(d.spec_tag, 0, N * sizeof(rg::SpecTag), b->stream));
+      RG_TRY(dev_alloc(b, &d.spec_seq, N));
+      RG_TRY(cudaMemsetAsync(d.spec_seq, 0, N * 4, b->stream));
+      RG_TRY(dev_alloc(b, &d.spec_lock, N));
+      RG_TRY(cudaMemsetAsync(d.spec_lock, 0, N * 4, b->stream));
+      uint32_t cap = 1;
+      while (cap < 2 * N) cap <<= 1;
+      d.spec_cap = cap;
+      RG_TRY(dev_alloc(b, &d.spec_ring, cap));
+      RG_TRY(dev_alloc(b, &d.spec_ctl, 4));
+      RG_TRY(cudaMemsetAsync(d.spec_ctl, 0, 16, b->stream));
+      RG_TRY(dev_alloc(b, &d.spec_win, 16));
+      RG_TRY(cudaMemsetAsync(d.spec_win, 0, 64, b->stream));
+      d.spec_warps = (int)std::min<int64_t>(256, ((int64_t)N + 7) / 8 * 8);
+      if (const char* e = getenv("RG_SPEC_WARPS")) d.spec_warps = std::max(8, atoi(e) / 8 * 8);
+      int lo = 0, hi = 0;
+      RG_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      for (int i = 0; i < rg_batch::SPEC_STREAMS; ++i) {
+        RG_TRY(cudaStreamCreateWithPriority(&b->spec[i], cudaStreamNonBlocking, hi));
+        RG_TRY(cudaEventCreateWithFlags(&b->ev_spec[i], cudaEventDisableTiming));
+      }
+      RG_TRY(cudaEventCreateWithFlags(&b->ev_step, cudaEventDisableTiming));
+    }
+  }
   RG_TRY(dev_alloc(b, &d.stats, 8));
   RG_TRY(cudaMemsetAsync(d.stats, 0, 64, b->stream));
   RG_TRY(dev_alloc(b, &d.dstep, 4));
@@ -416,6 +455,22 @@ int kick_prefetch(rg_batch* b) {
   return RG_OK;
 }
 
+// Queue the skeleton pass that serves the requests made up to the end of the step just queued (window slot
+// step % 8, fixed by that step's step_end). Passes rotate over SPEC_STREAMS streams; the main stream waits for
+// pass k - SPEC_STREAMS, so a pass may take that many steps without holding the steps up.
+int kick_spec(rg_batch* b, int slot) {
+  if (!b->d.spec) return RG_OK;
+  const int64_t k = b->spec_passes++;
+  const int i = (int)(k % rg_batch::SPEC_STREAMS);
+  RG_CUDA(b, cudaEventRecord(b->ev_step, b->stream));
+  RG_CUDA(b, cudaStreamWaitEvent(b->spec[i], b->ev_step, 0));
+  RG_CUDA(b, rg::launch_spec_build(b->d, slot, b->spec[i]));
+  if (k >= rg_batch::SPEC_STREAMS) RG_CUDA(b, cudaStreamWaitEvent(b->stream, b->ev_spec[i], 0));
+  RG_CUDA(b, cudaEventRecord(b->ev_spec[i], b->spec[i]));
+  b->launches += 1;
+  return RG_OK;
+}
+
 int copy_obs(rg_batch* b, rg_host_obs* out) {
   if (!out) return RG_OK;
   const DevBatch& d = b->d;
@@ -481,6 +536,14 @@ void rg_destroy(rg_batch* b) {
   for (int i = 0; i < 2; ++i)
     if (b->bg[i]) cudaStreamSynchronize(b->bg[i]);
   if (b->side) cudaStreamSynchronize(b->side);
+  for (int i = 0; i < rg_batch::SPEC_STREAMS; ++i) {
+    if (b->spec[i]) {
+      cudaStreamSynchronize(b->spec[i]);
+      cudaStreamDestroy(b->spec[i]);
+    }
+    if (b->ev_spec[i]) cudaEventDestroy(b->ev_spec[i]);
+  }
+  if (b->ev_step) cudaEventDestroy(b->ev_step);
   for (int i = 0; i < 2; ++i) {
     if (b->graph[i]) cudaGraphExecDestroy(b->graph[i]);
     if (b->graph_m[i]) cudaGraphExecDestroy(b->graph_m[i]);
@@ -583,6 +646,10 @@ int step_impl(rg_batch* b, const uint8_t* actions_dev, int auto_reset, bool with
     }
   }
   b->launches += 5 + (with_mirror ? 2 : 0);
+  {
+    int rc = kick_spec(b, (int)((b->steps_launched - 1) % 8));
+    if (rc != RG_OK) return rc;
+  }
   if (auto_reset && (b->auto_steps++ % b->prefetch_every) == 0)
     return kick_prefetch(b);  // refill the next-episode buffers consumed so far
   return RG_OK;
@@ -602,6 +669,8 @@ int rg_stats(rg_batch* b, uint64_t* out8) {
   RG_CUDA(b, cudaStreamSynchronize(b->stream));
   for (int i = 0; i < 2; ++i)
     if (b->bg[i]) RG_CUDA(b, cudaStreamSynchronize(b->bg[i]));
+  for (int i = 0; i < rg_batch::SPEC_STREAMS; ++i)
+    if (b->spec[i]) RG_CUDA(b, cudaStreamSynchronize(b->spec[i]));
   RG_CUDA(b, cudaMemcpy(out8, b->d.stats, 64, cudaMemcpyDeviceToHost));
   return RG_OK;
 }
@@ -627,6 +696,9 @@ int rg_quiesce(rg_batch* b) {
   if (!b) return set_err(b, RG_ERR_ARG, "rg_quiesce: null batch");
   if (b->d.prefetch && b->prefetch_running)
     for (int i = 0; i < 2; ++i) RG_CUDA(b, cudaStreamWaitEvent(b->stream, b->ev_bg[i], 0));
+  if (b->d.spec && b->spec_passes > 0)
+    for (int i = 0; i < rg_batch::SPEC_STREAMS && i < b->spec_passes; ++i)
+      RG_CUDA(b, cudaStreamWaitEvent(b->stream, b->ev_spec[i], 0));
   return RG_OK;
 }
 

@@ -133,6 +133,13 @@ struct Ctx {
   uint16_t* g_dist;
   uint32_t* g_bfs;    // per cache slot: frontier rows then visited rows of a suspended BFS
   uint32_t* g_wsnap;  // per cache slot: private walkability snapshot (see snapshot_suspended_maps)
+  // this env's speculative next-level skeleton (nullptr = off); see take_spec
+  const uint8_t* g_spec_S;
+  const uint8_t* g_spec_A;
+  const RoomD* g_spec_rooms;
+  const SpecTag* g_spec_tag;
+  const uint32_t* g_spec_seq;
+  unsigned long long* g_spec_hits;
   Rng rd, ri, re;     // dungeon / item / enemy streams (registers)
   // per-step reaction summary (state_impls.rs:57-75 collapses to these)
   uint32_t redraw, status_upd, dead, msg, hist_done, a_dirty, s_dirty, panic;
@@ -309,6 +316,42 @@ __device__ void build_walk(Ctx& c) {
 }
 
 __device__ void snapshot_suspended_maps(Ctx& c);  // lazy DistCache, defined with the BFS below
+
+// A descent looks for the skeleton of the level it is about to generate (rooms, mazes, passages, attributes:
+// gen_skeleton) among the ones k_spec_build produced in the background. It is taken only if it was generated for
+// exactly this level from exactly the dungeon-stream state the descent starts with - then it is, bit for bit,
+// what gen_skeleton would produce now - and if the slot was not rewritten while it was being copied (seqlock).
+// Returns false with the planes in an undefined state; the caller then generates (which overwrites everything).
+__device__ bool take_spec(Ctx& c, Rng& rd, uint32_t level) {
+  if (!c.g_spec_seq) return false;
+  RG_PLANES(c);
+  const uint32_t s1 = *reinterpret_cast<const volatile uint32_t*>(c.g_spec_seq);
+  __threadfence();
+  const uint4 before = __ldcg(reinterpret_cast<const uint4*>(c.g_spec_tag->rd_before));
+  const uint4 after = __ldcg(reinterpret_cast<const uint4*>(c.g_spec_tag->rd_after));
+  const int2 lv_ok = __ldcg(reinterpret_cast<const int2*>(&c.g_spec_tag->level));
+  bool good = !(s1 & 1u) && lv_ok.y != 0 && lv_ok.x == (int)level && before.x == rd.x && before.y == rd.y &&
+              before.z == rd.z && before.w == rd.w;
+  good = __shfl_sync(RG_FULL, good ? 1 : 0, 0) != 0;  // one decision per warp
+  if (!good) return false;
+  __syncwarp();
+  for (int i = c.lane; i < c.CP / 16; i += 32) {
+    reinterpret_cast<uint4*>(S)[i] = __ldcg(reinterpret_cast<const uint4*>(c.g_spec_S) + i);
+    reinterpret_cast<uint4*>(A)[i] = __ldcg(reinterpret_cast<const uint4*>(c.g_spec_A) + i);
+  }
+  if (c.lane < MAX_ROOMS) {
+    const uint2 r = __ldcg(reinterpret_cast<const uint2*>(c.g_spec_rooms) + c.lane);
+    reinterpret_cast<uint2*>(st->rooms)[c.lane] = r;
+  }
+  __threadfence();
+  __syncwarp();
+  uint32_t same = *reinterpret_cast<const volatile uint32_t*>(c.g_spec_seq) == s1 ? 1u : 0u;
+  same = __shfl_sync(RG_FULL, same, 0);
+  if (!same) return false;
+  rd.x = after.x; rd.y = after.y; rd.z = after.z; rd.w = after.w;
+  if (c.lane == 0 && c.g_spec_hits) atomicAdd(c.g_spec_hits, 1ull);
+  return true;
+}
 
 #define RG_GEN_SECOND_HALF
 namespace gen_inl {
@@ -648,6 +691,7 @@ __device__ int move_enemy(Ctx& c, int mx, int my, int tx, int ty, uint32_t moved
 // rogue::Dungeon::move_enemy_randomly rogue/mod.rs:376-397
 __device__ int move_enemy_randomly(Ctx& c, int mx, int my, uint32_t moved, int& ox, int& oy) {
   RG_PLANES(c);
+  st->spec_req = 0;  // the dungeon stream moves on: a skeleton built from its old state is dead, ask again
   int d = (int)c.rd.range64(0, 8);
   int nx = mx + ddx(d), ny = my + ddy(d);
   if (cell_blocked(c, nx, ny, moved) || !can_move(c, mx, my, d, true)) return MV_CANT;
@@ -878,6 +922,7 @@ __device__ void search(Ctx& c) {
     if ((A[idx] & (A_HIDDEN | A_LOCKED)) && !maps_done) {  // walkability may change below
       snapshot_suspended_maps(c);
       maps_done = true;
+      st->spec_req = 0;  // the dungeon stream is drawn from below (see move_enemy_randomly)
     }
     if ((A[idx] & A_HIDDEN) && c.rd.does_happen(c.P->passage_unlock_rate_inv)) {
       A[idx] = (A[idx] & (uint8_t)~(A_LOCKED | A_HIDDEN)) | A_VISIBLE;

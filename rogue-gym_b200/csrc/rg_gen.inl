@@ -376,6 +376,28 @@ __device__ void dig_passages(Ctx& c, Rng& rd, ConnList& cl) {
   }
 }
 
+// Floor::gen_floor floor.rs:50-104 up to and including the passages: the part of a level that depends on the
+// dungeon stream, the level number and the config only (no items, monsters, player). Leaves A_MARK on maze cells.
+__device__ void gen_skeleton(Ctx& c, Rng& rd, uint32_t level) {
+  RG_PLANES(c);
+  __syncwarp();
+  for (int ch = c.lane; ch < c.CP / 16; ch += 32) {  // fresh field
+    *reinterpret_cast<uint4*>(S + ch * 16) = make_uint4(0x07070707u, 0x07070707u, 0x07070707u, 0x07070707u);
+    *reinterpret_cast<uint4*>(A + ch * 16) = make_uint4(0, 0, 0, 0);
+  }
+  __syncwarp();
+  gen_rooms(c, rd, level);
+  lay_rooms(c, rd, level);
+  // dig (dungeon stream), then lay the recorded passages while a second stream, which starts where the
+  // dig ended, rolls the cell attributes (connect_2rooms / apply_connections)
+  ConnList cl;
+  cl.n = 0;
+  dig_passages(c, rd, cl);
+  Rng ra = rd;
+  apply_connections(c, ra, cl, level);
+  rd = ra;
+}
+
 // Room::select_cell rooms.rs:132-144 over the implicit set "free cells of this room":
 // interior floor cells (normal) or marked cells (maze), minus at most one occupied cell
 // (`excl`, a cell index or -1). During generation a room's set never loses more than one
@@ -494,29 +516,15 @@ RG_GEN_NEW_LEVEL_ATTR void new_level(Ctx* cp, bool is_initial) {
   }
   st->level += 1;
   st->dirty_rows = ~0ull;  // a new floor: everything is recomposed
+  st->spec_req = 0;
   const uint32_t level = (uint32_t)st->level;
-  // fresh field
-  __syncwarp();
-  for (int ch = c.lane; ch < c.CP / 16; ch += 32) {
-    *reinterpret_cast<uint4*>(S + ch * 16) = make_uint4(0x07070707u, 0x07070707u, 0x07070707u, 0x07070707u);
-    *reinterpret_cast<uint4*>(A + ch * 16) = make_uint4(0, 0, 0, 0);
-  }
-  __syncwarp();
   Rng rd = c.rd;
-  gen_rooms(c, rd, level);
-  lay_rooms(c, rd, level);
-  {  // dig (dungeon stream), then lay the recorded passages while a second stream, which starts where the
-     // dig ended, rolls the cell attributes (connect_2rooms / apply_connections)
-    ConnList cl;
-    cl.n = 0;
-    dig_passages(c, rd, cl);
-    Rng ra = rd;
-    apply_connections(c, ra, cl, level);
-    rd = ra;
-  }
+  // rooms, mazes, passages and their attributes: a function of (dungeon stream, level, config) alone. A descent
+  // first looks for that part built ahead of time by k_spec_build from the same stream state (take_spec).
+  if (is_initial || !take_spec(c, rd, level)) gen_skeleton(c, rd, level);
   // Floor::setup_items: cell from the dungeon stream, amount from the item stream (gold.rs:18-24)
   Rng ri = c.ri;
-  for (int i = 0; i < c.nrooms; ++i) {
+  for (int i = 0; i < MAX_ROOMS; ++i) {  // every slot: k_step_fast looks at all of them
     st->item_pos[i] = 0xFFFF;
     st->item_amt[i] = 0;
   }
@@ -534,6 +542,7 @@ RG_GEN_NEW_LEVEL_ATTR void new_level(Ctx* cp, bool is_initial) {
     int pos = select_in_floor(c, rd, 0);
     if (pos < 0) set_panic(c);
     else S[pos] = S_STAIR;
+    st->stair_pos = (uint16_t)(pos < 0 ? 0xFFFF : pos);
   }
   for (int i = 0; i < MAX_ROOMS; ++i) st->mon[i].flags = 0;  // remove_enemies (a fresh handler is empty too)
   if (P.n_enemies != 0) {  // Floor::place_enemies

@@ -26,6 +26,7 @@ constexpr int WARPS_PER_BLOCK = RG_WPB;
 // k_prefetch takes its warps per block from the launch (DevBatch::pf_wpb, at most PF_MAX_WPB and as many
 // as fit in shared memory). The full-path kernel handles ~10 envs per step: one warp per block, spread.
 constexpr int PF_MAX_WPB = 16;
+constexpr int SPEC_WPB = 8;  // warps per block of k_spec_build (a few dozen requests per step: a handful of blocks)
 constexpr int PF_EXCLUSIVE_SMEM = 227 * 1024 - 4608;  // leaves less than one step-kernel block's worth (4.4 KB + 1 KB reserved)
 #ifndef RG_GEN_WPB
 #define RG_GEN_WPB 1
@@ -115,6 +116,16 @@ RG_DEV void fill_ctx(const DevBatch& b, Ctx& c, Stager& sg, unsigned char* base,
   c.g_dist = b.dist + env * (int64_t)NCACHE * b.CP;
   c.g_bfs = b.bfs + env * (int64_t)NCACHE * 2 * b.H * b.WW;
   c.g_wsnap = b.wsnap + env * (int64_t)NCACHE * b.H * b.WW;
+  c.g_spec_seq = nullptr;
+  c.g_spec_hits = nullptr;
+  if (b.spec) {
+    c.g_spec_S = b.spec_S + env * b.CP;
+    c.g_spec_A = b.spec_A + env * b.CP;
+    c.g_spec_rooms = b.spec_rooms + env * MAX_ROOMS;
+    c.g_spec_tag = b.spec_tag + env;
+    c.g_spec_seq = b.spec_seq + env;
+    c.g_spec_hits = b.stats + RGS_SPEC_HITS;
+  }
   c.redraw = c.status_upd = c.dead = c.msg = c.hist_done = c.a_dirty = c.s_dirty = c.panic = 0;
   c.rd.load(c.st->rng);
   c.ri.load(c.st->rng + 4);
@@ -207,6 +218,29 @@ RG_DEV void defer(const DevBatch& b, Ctx& c, int64_t env, uint32_t code, int par
   }
 }
 
+// Speculative descents: once per level (and again after the dungeon stream was drawn from during play), when the
+// player comes within SPEC_RADIUS of the stair, ask the background builder for the next level's skeleton.
+RG_DEV void push_spec_request(const DevBatch& b, int64_t env) {
+  const uint32_t t = atomicAdd(b.spec_ctl, 1u);
+  b.spec_ring[t & (b.spec_cap - 1u)] = (uint32_t)env;
+}
+RG_DEV bool near_stair(int W, int px, int py, uint32_t stair_pos) {
+  if (stair_pos == 0xFFFFu) return false;
+  const int sy = (int)stair_pos / W, sx = (int)stair_pos - sy * W;
+  return max(abs(px - sx), abs(py - sy)) <= SPEC_RADIUS;
+}
+// for the warp kernels: `st` is the env's state staged in shared memory, about to be written back as the live state
+RG_DEV void maybe_request_spec(const DevBatch& b, Ctx& c, int64_t env) {
+  if (!b.spec) return;
+  EnvState* st = c.st;
+  if (st->spec_req || st->error || st->ui_dead) return;
+  if (!near_stair(c.W, st->px, st->py, st->stair_pos)) return;
+  __syncwarp();
+  st->spec_req = 1;
+  if (c.lane == 0) push_spec_request(b, env);
+  __syncwarp();
+}
+
 // ThreadWorker::run Instruction::Reset for every env (python/src/thread_impls.rs:117-124)
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_HOT_MIN_BLOCKS) k_reset(DevBatch b) {
   unsigned char* const smem = rg_smem;
@@ -225,6 +259,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_HOT_MIN_BLOCKS) k_res
   }
   compose(c);
   emit_obs(b, c, env, 0, err);
+  maybe_request_spec(b, c, env);
   close_env(b, c, env);
 }
 
@@ -341,6 +376,7 @@ RG_DEV void finish_env(const DevBatch& b, Ctx& c, int64_t env, int auto_reset, i
         st->is_terminal = 1;
         const int32_t d0 = (int32_t)st->status[1] - (int32_t)gold_before;
         emit_obs(b, c, env, d0 > 0 ? d0 : 0, perr);
+        maybe_request_spec(b, c, env);
         store_state(b, c, env);
         __threadfence();
         __syncwarp();
@@ -362,6 +398,7 @@ RG_DEV void finish_env(const DevBatch& b, Ctx& c, int64_t env, int auto_reset, i
   }
   const int32_t diff = (int32_t)st->status[1] - (int32_t)gold_before;
   emit_obs(b, c, env, diff > 0 ? diff : 0, err);
+  maybe_request_spec(b, c, env);
   close_env(b, c, env);
 }
 
@@ -541,6 +578,13 @@ RG_DEV int fast_env(const DevBatch& b, int64_t env, uint8_t key, int auto_reset)
       *hb = (uint8_t)(*hb | (1u << (ni & 7)));
       b.scr_rows[env] |= rows_touched;
       moved = true;
+      if (b.spec) {
+        const uint32_t tailw = hot[11].w;  // cache_head, spec_req, stair_pos
+        if (!((tailw >> 8) & 0xFFu) && near_stair(W, nx, ny, tailw >> 16)) {
+          stp->spec_req = 1;
+          push_spec_request(b, env);
+        }
+      }
     }
   }
   // ---- the turn: after_turn (actions.rs:67-80) = Player::turn_passed + heal (player.rs:163-176,221-240); no monster is active
@@ -741,6 +785,7 @@ RG_DEV void step_env_full(const DevBatch& b, Ctx& c, int64_t env, const uint8_t*
     compose(c);
     const int32_t diff = (int32_t)st->status[1] - (int32_t)gold_before;
     emit_obs(b, c, env, diff > 0 ? diff : 0, err);
+    maybe_request_spec(b, c, env);
     close_env(b, c, env);
     return;
   }
@@ -771,6 +816,7 @@ RG_DEV void step_env_full(const DevBatch& b, Ctx& c, int64_t env, const uint8_t*
   }
   const int32_t diff = (int32_t)st->status[1] - (int32_t)gold_before;
   emit_obs(b, c, env, diff > 0 ? diff : 0, err);
+  maybe_request_spec(b, c, env);
   close_env(b, c, env);
 }
 
@@ -784,6 +830,11 @@ RG_DEV void fix_window(const DevBatch& b) {  // window of background pass number
   win[1] = b.refill_ctl[2] = *reinterpret_cast<volatile uint32_t*>(b.refill_ctl);
 }
 RG_DEV void step_end(const DevBatch& b, int auto_reset) {
+  if (b.spec) {  // the window of skeleton requests the pass kicked after this step serves
+    uint32_t* win = b.spec_win + 2 * (b.dstep[0] % 8u);
+    win[0] = b.spec_ctl[2];
+    win[1] = b.spec_ctl[2] = *reinterpret_cast<volatile uint32_t*>(b.spec_ctl);
+  }
   b.dstep[0] += 1u;
   if (!auto_reset || !b.prefetch) return;
   const uint32_t k = b.dstep[1]++;
@@ -900,6 +951,87 @@ __global__ void __launch_bounds__(PF_MAX_WPB * 32, 1) k_prefetch(DevBatch b, int
     __threadfence();
     __syncwarp();
     if (lane == 0) atomicExch(b.sp_lock + env, 0u);
+  }
+}
+
+// Background builder of next-level skeletons (speculative descents). One warp per request: it snapshots the env's
+// level and dungeon stream (a racy read of the live state - the consumer, take_spec, accepts a skeleton only if both
+// still match when the descent happens), runs gen_skeleton for level + 1 in shared memory and publishes planes,
+// rooms and the tag under the env's seqlock. A descent that finds no valid skeleton simply generates as before.
+__global__ void __launch_bounds__(PF_MAX_WPB * 32, 1) k_spec_build(DevBatch b, int slot) {
+  const uint32_t WPB = blockDim.x >> 5;
+  unsigned char* const smem = rg_smem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // per warp: the two planes and a state block like every warp kernel, then CP bytes for dig_maze's stack (passes
+  // overlap on several streams, so the stack cannot live in a buffer indexed by the warp's number)
+  unsigned char* const base = smem + (size_t)warp * (warp_smem(b) + (size_t)b.CP);
+  const uint32_t gwarp = blockIdx.x * WPB + warp;
+  const uint32_t begin = b.spec_win[2 * slot], end = b.spec_win[2 * slot + 1];
+  for (uint32_t it = begin + gwarp; (int32_t)(end - it) > 0; it += gridDim.x * WPB) {
+    const int64_t env = (int64_t)b.spec_ring[it & (b.spec_cap - 1u)];
+    const int level = *reinterpret_cast<const volatile int32_t*>(&b.st[env].level);
+    const uint4 r4 = __ldcg(reinterpret_cast<const uint4*>(b.st[env].rng));
+    {  // already built for this very state (a repeated request)?
+      const SpecTag* t = b.spec_tag + env;
+      const uint4 have = __ldcg(reinterpret_cast<const uint4*>(t->rd_before));
+      const int2 lv_ok = __ldcg(reinterpret_cast<const int2*>(&t->level));
+      const uint32_t sq = *reinterpret_cast<const volatile uint32_t*>(b.spec_seq + env);
+      if (!(sq & 1u) && lv_ok.y && lv_ok.x == level + 1 && have.x == r4.x && have.y == r4.y && have.z == r4.z && have.w == r4.w)
+        continue;
+    }
+    uint32_t got = 0;  // one builder per env at a time (duplicate requests inside one window)
+    if (lane == 0) got = atomicCAS(b.spec_lock + env, 0u, 1u) == 0u ? 1u : 0u;
+    got = __shfl_sync(RG_FULL, got, 0);
+    if (!got) continue;
+    if (lane == 0) atomicAdd(b.spec_seq + env, 1u);  // odd: being written
+    __threadfence();
+    __syncwarp();
+    Ctx c;
+    c.soff = (uint32_t)(base - rg_smem);
+    c.S = base;
+    c.A = base + b.CP;
+    c.st = reinterpret_cast<EnvState*>(base + 2 * (size_t)b.CP);
+    c.col_room = b.room_lut;
+    c.row_room = b.room_lut + 160;
+    c.P = b.cfg_idx ? b.P + b.cfg_idx[env] : b.P;
+    c.W = b.W; c.H = b.H; c.C = b.C; c.CP = b.CP; c.WW = b.WW;
+    c.lane = lane;
+    c.nx = b.nx; c.ny = b.ny;
+    c.rsx = b.rsx; c.rsy = b.rsy;
+    c.nrooms = c.nx * c.ny;
+    c.g_screen = base + warp_smem(b);  // dig_maze's stack
+    c.g_hist = nullptr; c.g_rows = nullptr; c.g_walk = nullptr; c.g_dist = nullptr; c.g_bfs = nullptr; c.g_wsnap = nullptr;
+    c.g_spec_seq = nullptr; c.g_spec_hits = nullptr;
+    c.redraw = c.status_upd = c.dead = c.msg = c.hist_done = c.a_dirty = c.s_dirty = c.panic = 0;
+    if (lane < MAX_ROOMS) reinterpret_cast<uint2*>(c.st->rooms)[lane] = make_uint2(0u, 0u);
+    Rng rd;
+    rd.x = r4.x; rd.y = r4.y; rd.z = r4.z; rd.w = r4.w;
+    gen_call::gen_skeleton(c, rd, (uint32_t)(level + 1));
+    __syncwarp();
+    if (lane < MAX_ROOMS) reinterpret_cast<uint2*>(b.spec_rooms + env * MAX_ROOMS)[lane] = reinterpret_cast<const uint2*>(c.st->rooms)[lane];
+    if (lane == 0) {
+      SpecTag* t = b.spec_tag + env;
+      *reinterpret_cast<uint4*>(t->rd_before) = r4;
+      *reinterpret_cast<uint4*>(t->rd_after) = make_uint4(rd.x, rd.y, rd.z, rd.w);
+      t->level = level + 1;
+      t->ok = c.panic ? 0u : 1u;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      bulk_s2g(b.spec_S + env * b.CP, smem_u32(c.S), (uint32_t)b.CP);
+      bulk_s2g(b.spec_A + env * b.CP, smem_u32(c.A), (uint32_t)b.CP);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the writes themselves, not just the reads
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+      atomicAdd(b.spec_seq + env, 1u);  // even: published
+      __threadfence();
+      atomicExch(b.spec_lock + env, 0u);
+    }
+    __syncwarp();
   }
 }
 
@@ -1307,6 +1439,9 @@ cudaError_t configure_kernels(const DevBatch& b) {
   e = cudaFuncSetAttribute(k_prefetch, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            b.pf_exclusive ? PF_EXCLUSIVE_SMEM : (int)(pf_warps_per_block(b) * one_warp_smem(b)));
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_spec_build, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(SPEC_WPB * (one_warp_smem(b) + (size_t)b.CP)));
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_complete_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one_warp_smem(b));
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(k_test_move_enemy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one_warp_smem(b));
@@ -1377,6 +1512,10 @@ cudaError_t launch_prefetch(const DevBatch& b, int warps, int slot, cudaStream_t
   // pf_exclusive: the block asks for (nearly) all of an SM's shared memory, so no step-kernel block shares
   // the SM with it - the generator's code and the step kernels' code stop evicting each other
   k_prefetch<<<blocks, PF_WPB * 32, b.pf_exclusive ? (size_t)PF_EXCLUSIVE_SMEM : PF_WPB * one_warp_smem(b), s>>>(b, slot);
+  return cudaGetLastError();
+}
+cudaError_t launch_spec_build(const DevBatch& b, int slot, cudaStream_t s) {
+  k_spec_build<<<b.spec_warps / SPEC_WPB, SPEC_WPB * 32, SPEC_WPB * (one_warp_smem(b) + (size_t)b.CP), s>>>(b, slot);
   return cudaGetLastError();
 }
 cudaError_t launch_test_move_enemy(const DevBatch& b, int64_t env, int fx, int fy, int tx, int ty, int* out3,

@@ -35,6 +35,8 @@ cudaError_t launch_step(const DevBatch& b, const uint8_t* actions_dev, int auto_
                         const MirrorArgs* mirror, int sm_count);
 // background generation of next-episode games into the sp_* buffers; serves window `slot` of refill_win
 cudaError_t launch_prefetch(const DevBatch& b, int warps, int slot, cudaStream_t s);
+// background build of next-level skeletons requested up to the end of step slot (speculative descents)
+cudaError_t launch_spec_build(const DevBatch& b, int slot, cudaStream_t s);
 cudaError_t launch_test_move_enemy(const DevBatch& b, int64_t env, int fx, int fy, int tx, int ty, int* out3_dev,
                                    cudaStream_t s);
 cudaError_t launch_encode(const DevBatch& b, int mode, uint32_t flag, int with_hist, int channels, float* out_dev,

@@ -35,7 +35,7 @@ enum : uint8_t { K_NORMAL = 0, K_MAZE = 1, K_EMPTY = 2 };
 enum : uint8_t { RF_DARK = 1, RF_VISITED = 2, RF_GOLD = 4 };
 enum : uint8_t { MF_PRESENT = 1, MF_ACTIVE = 2 };
 enum { RGS_SWAP_IN = 0, RGS_SYNC_RESET = 1, RGS_FULL_STEP = 2, RGS_PREFETCH_BUILT = 3, RGS_PREFETCH_STALE = 4,
-       RGS_MONSTER_ENVS = 5, RGS_BFS_LEVELS = 6, RGS_FAST_STEPS = 7 };
+       RGS_MONSTER_ENVS = 5, RGS_SPEC_HITS = 6, RGS_FAST_STEPS = 7 };
 // full_path[env]: which kernel leaves the env's step final (the host mirror's first pass takes the FP_FAST ones)
 enum : uint8_t { FP_FAST = 0, FP_FULL = 1, FP_MONSTERS = 2, FP_RESET = 3, FP_PLAYER = 5 };
 enum : uint8_t { SF_REDRAW = 1, SF_STATUS = 2, SF_DEAD = 4, SF_SKIP = 8, SF_PANIC = 16 };
@@ -88,7 +88,9 @@ struct alignas(16) EnvState {
   uint32_t status[10];     // DISPLAYED status (stale semantics, state_impls.rs:63-65)
   uint16_t cache_snap;     // bit s: cache slot s resumes on its private walkability snapshot (wsnap)
   uint8_t f_flags;         // SF_*
-  uint8_t cache_n, cache_head, pad0, pad1, pad2;
+  uint8_t cache_n, cache_head;
+  uint8_t spec_req;        // 1 = the next level's skeleton has been requested from k_spec_build for this level
+  uint16_t stair_pos;      // y*W+x of this level's stair (0xFFFF: none)
   // ---- not touched by the fast kernel
   uint32_t rng[12];        // dungeon, item, enemy xorshift128 states
   uint32_t seed[4];        // seed used by the next reset (thread_impls.rs:125-128)
@@ -106,6 +108,20 @@ static_assert(offsetof(EnvState, food_left) == 16 && offsetof(EnvState, level) =
                   offsetof(EnvState, mon_present) == 64 && offsetof(EnvState, mon_xy) == 80 &&
                   offsetof(EnvState, item_pos) == 112 && offsetof(EnvState, status) == 144 && offsetof(EnvState, rng) == HOT_BYTES,
               "k_step_fast unpacks the hot block by offset");
+static_assert(offsetof(EnvState, spec_req) == 189 && offsetof(EnvState, stair_pos) == 190 && offsetof(EnvState, rooms) % 8 == 0 &&
+                  sizeof(RoomD) == 8,
+              "layout assumed by k_step_fast / take_spec");
+
+// A level skeleton built ahead of time (k_spec_build): valid for a descent whose dungeon stream and level match.
+struct SpecTag {
+  uint32_t rd_before[4];   // dungeon stream the skeleton was generated from
+  uint32_t rd_after[4];    // ... and where it ended
+  int32_t level;           // the level it is the skeleton of
+  uint32_t ok;             // 0 = the build hit a panic state: never used
+  uint32_t pad[2];
+};
+static_assert(sizeof(SpecTag) == 48, "take_spec reads the tag with 128-bit loads");
+constexpr int SPEC_RADIUS = 6;  // a skeleton is requested when the player comes this close (Chebyshev) to the stair
 
 struct DevBatch {
   int64_t n;
@@ -164,6 +180,20 @@ struct DevBatch {
   int32_t pf_wpb;         // warps per block of k_prefetch (0 = default)
   int32_t pf_exclusive;   // k_prefetch blocks take a whole SM each (see launch_prefetch)
   int32_t prefetch;       // 0 = off (every reset is generated synchronously by k_step_gen)
+  // speculative descents: the next level's skeleton per env, built in the background from a snapshot of the
+  // dungeon stream, taken by new_level when level and stream still match (seqlock: odd = being written)
+  int32_t spec;             // 0 = off (RG_SPEC=0)
+  uint8_t* spec_S;          // [N][CP]
+  uint8_t* spec_A;          // [N][CP] (A_MARK still set on maze cells)
+  RoomD* spec_rooms;        // [N][MAX_ROOMS]
+  SpecTag* spec_tag;        // [N]
+  uint32_t* spec_seq;       // [N]
+  uint32_t* spec_lock;      // [N] 1 = a builder warp is working on this env's slot
+  uint32_t* spec_ring;      // [spec_cap] env ids with a pending request (producers: step kernels)
+  uint32_t* spec_ctl;       // [0] tail, [2] end of the last window handed to a pass
+  uint32_t* spec_win;       // [8][2] window served by the pass kicked after step s % 8
+  uint32_t spec_cap;        // power of two
+  int32_t spec_warps;
   uint32_t* mon_list;     // [N] envs with an active monster this step (player kernel -> monster kernel)
   uint32_t* mon_count;    // [2] list lengths by step parity, then [2] work cursors
   int32_t mon_warps;      // warps of the (grid-stride) monster kernel
