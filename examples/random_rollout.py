@@ -48,7 +48,7 @@ game.close()
 n = 16384
 denv = DeviceRogueEnv({}, num_envs=n, image_setting=ImageSetting(DungeonType.GRAY, StatusFlag.HP_CURRENT, True),
                       seeds=range(1, n + 1), stair_reward=50.0)
-obs = denv.reset()                                       # float32 [N, 3, 24, 80] on cuda:0, rewritten in place by step()
+obs = denv.reset()                                       # CompactObs on cuda:0 (symbol ids u8 [N,24,80], status i32 [N,9], visited map), rewritten in place by step()
 torch.cuda.synchronize()
 t0 = time.time()
 total = torch.zeros((), device="cuda")
@@ -57,6 +57,8 @@ for _ in range(300):
     obs, reward, done, _ = denv.step(actions)
     total += reward.sum()
 torch.cuda.synchronize()
-print("device env: obs", tuple(obs.shape), "| %.1f M env-steps/s incl. encode | reward sum %.0f | errors %d"
+image = denv.expand(obs)                                 # float32 [N, 3, 24, 80]: the reference's ImageSetting.expand, on the device
+print("device env: obs", tuple(obs.symbols.shape), "-> image", tuple(image.shape),
+      "| %.1f M env-steps/s incl. observation | reward sum %.0f | errors %d"
       % (n * 300 / (time.time() - t0) / 1e6, float(total), int((denv.errors() != 0).sum())))
 denv.close()

@@ -236,6 +236,14 @@ int64_t rg_launch_count(rg_batch* b); /* kernels launched so far by this batch *
  * Returns channels through *channels. InvalidTileError (symbol.rs:62-64) sets error[env]. */
 int rg_encode(rg_batch* b, int mode, uint32_t status_flag, int with_hist, float* out_dev, int* channels);
 int rg_encode_channels(const rg_batch* b, int mode, uint32_t status_flag, int with_hist);
+/* Compact observation: what symbol_image carries, without the one-hot expansion (1.9 KB instead of 401 KB per env
+ * for the reference-default ImageSetting; a policy embeds / one-hots the ids on the device, see
+ * rogue_gym.envs.device.SymbolExpand). sym_out_dev u8 [N][W*H]: Symbol::from_tile of every screen cell
+ * (symbol.rs:17-40), 0 .. symbols-1; a tile without a symbol sets RG_ERR_SETTING in error[env] and is written as 0.
+ * (The id symbols-1 - the largest monster tile - is passed through: gray_image encodes it, symbol_image raises
+ * InvalidTileError for it, symbol.rs:60-64; SymbolExpand leaves its plane empty.) status_out_dev i32 [N][9]: the status vector in StatusFlagInner order (flags.rs:63-85), nullable.
+ * hist_out_dev u8 [N][W*H] 0/1 visited map, nullable. Device buffers, on the batch's stream. */
+int rg_encode_compact(rg_batch* b, uint8_t* sym_out_dev, int32_t* status_out_dev, uint8_t* hist_out_dev);
 /* The same encoders for n detached PlayerState values held on the host (what PlayerState.gray_image /
  * symbol_image do per object, python/src/lib.rs:158-205): screens [n][W*H], history [n][W*H] 0/1 bytes
  * (may be NULL unless with_hist), status [n][10]; out_host f32 [n][channels][H][W]. Runs on the device. */

@@ -30,11 +30,12 @@ struct rg_batch {
   cudaStream_t bg[2] = {nullptr, nullptr};  // background streams: k_prefetch passes alternate, so two can be in flight
   cudaStream_t side = nullptr;    // full-path steps, forked after the player kernel and joined at the end of the step
   cudaStream_t mir = nullptr;     // first host-mirror pass of a step
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mir = nullptr;
+  cudaStream_t mon = nullptr;     // player + monster kernels of the envs with an active monster, beside k_step_fast
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mir = nullptr, ev_mon = nullptr, ev_fast = nullptr;
   rg::StepStreams step_streams() const {
     rg::StepStreams q;
-    q.main = stream; q.side = side; q.mir = mir;
-    q.ev_fork = ev_fork; q.ev_join = ev_join; q.ev_mir = ev_mir;
+    q.main = stream; q.side = side; q.mon = mon; q.mir = mir;
+    q.ev_fork = ev_fork; q.ev_join = ev_join; q.ev_mon = ev_mon; q.ev_fast = ev_fast; q.ev_mir = ev_mir;
     return q;
   }
   // background builder of next-level skeletons (speculative descents): one pass per step, on SPEC_STREAMS rotating
@@ -353,19 +354,31 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
     int lo = 0, hi = 0;
     RG_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     RG_TRY(cudaStreamCreateWithPriority(&b->side, cudaStreamNonBlocking, hi));
+    RG_TRY(cudaStreamCreateWithPriority(&b->mon, cudaStreamNonBlocking, hi));
     RG_TRY(cudaStreamCreateWithFlags(&b->mir, cudaStreamNonBlocking));
     RG_TRY(cudaEventCreateWithFlags(&b->ev_mir, cudaEventDisableTiming));
+    RG_TRY(cudaEventCreateWithFlags(&b->ev_mon, cudaEventDisableTiming));
+    RG_TRY(cudaEventCreateWithFlags(&b->ev_fast, cudaEventDisableTiming));
   }
   RG_TRY(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
   RG_TRY(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
   RG_TRY(dev_alloc(b, &d.mon_list, N));
-  RG_TRY(dev_alloc(b, &d.mon_count, 4));
-  RG_TRY(cudaMemsetAsync(d.mon_count, 0, 16, b->stream));
+  RG_TRY(dev_alloc(b, &d.mon_list_b, N));
+  RG_TRY(dev_alloc(b, &d.mon_count, 8));
+  RG_TRY(cudaMemsetAsync(d.mon_count, 0, 32, b->stream));
+  RG_TRY(dev_alloc(b, &d.fast_list_m, N));
+  RG_TRY(dev_alloc(b, &d.fast_list_l, N));
+  RG_TRY(dev_alloc(b, &d.fast_count, 4));
+  RG_TRY(cudaMemsetAsync(d.fast_count, 0, 16, b->stream));
   RG_TRY(dev_alloc(b, &d.slow_list, N));
-  RG_TRY(dev_alloc(b, &d.slow_count, 4));
-  RG_TRY(cudaMemsetAsync(d.slow_count, 0, 16, b->stream));
+  RG_TRY(dev_alloc(b, &d.slow_list_b, N));
+  RG_TRY(dev_alloc(b, &d.slow_count, 8));
+  RG_TRY(cudaMemsetAsync(d.slow_count, 0, 32, b->stream));
   d.fast = 1;
   if (const char* e = getenv("RG_FAST")) d.fast = e[0] != '0';
+  d.branches = 1;
+  if (const char* e = getenv("RG_BRANCHES")) d.branches = e[0] != '0';
+  if (const char* e = getenv("RG_MON_WARPS")) d.mon_warps = std::max(32, atoi(e));
   RG_TRY(dev_alloc(b, &b->d_actions, N));
   RG_TRY(dev_alloc(b, &b->d_u64, 2 * N));
   RG_TRY(dev_alloc(b, &b->d_out3, 4));
@@ -536,6 +549,12 @@ void rg_destroy(rg_batch* b) {
   for (int i = 0; i < 2; ++i)
     if (b->bg[i]) cudaStreamSynchronize(b->bg[i]);
   if (b->side) cudaStreamSynchronize(b->side);
+  if (b->mon) {
+    cudaStreamSynchronize(b->mon);
+    cudaStreamDestroy(b->mon);
+  }
+  if (b->ev_mon) cudaEventDestroy(b->ev_mon);
+  if (b->ev_fast) cudaEventDestroy(b->ev_fast);
   for (int i = 0; i < rg_batch::SPEC_STREAMS; ++i) {
     if (b->spec[i]) {
       cudaStreamSynchronize(b->spec[i]);
@@ -645,7 +664,7 @@ int step_impl(rg_batch* b, const uint8_t* actions_dev, int auto_reset, bool with
       RG_CUDA(b, cudaMemcpyAsync(b->h_errflag, b->d.errflag, sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
     }
   }
-  b->launches += 5 + (with_mirror ? 2 : 0);
+  b->launches += 8 + (with_mirror ? 2 : 0);
   {
     int rc = kick_spec(b, (int)((b->steps_launched - 1) % 8));
     if (rc != RG_OK) return rc;
@@ -907,6 +926,14 @@ int rg_encode(rg_batch* b, int mode, uint32_t status_flag, int with_hist, float*
   if (ch < 0) return set_err(b, RG_ERR_ARG, "rg_encode: mode must be 0 (gray) or 1 (symbol)");
   if (channels) *channels = ch;
   RG_CUDA(b, rg::launch_encode(b->d, mode, status_flag & 0x1FFu, with_hist, ch, out_dev, b->stream));
+  b->launches += 1;
+  return RG_OK;
+}
+
+int rg_encode_compact(rg_batch* b, uint8_t* sym_out_dev, int32_t* status_out_dev, uint8_t* hist_out_dev) {
+  if (!b || !sym_out_dev) return set_err(b, RG_ERR_ARG, "rg_encode_compact: null argument");
+  RG_CUDA(b, cudaSetDevice(b->device));
+  RG_CUDA(b, rg::launch_encode_compact(b->d, sym_out_dev, status_out_dev, hist_out_dev, b->sm_count, b->stream));
   b->launches += 1;
   return RG_OK;
 }

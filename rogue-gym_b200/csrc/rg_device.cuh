@@ -663,7 +663,22 @@ __device__ int move_enemy(Ctx& c, int mx, int my, int tx, int ty, uint32_t moved
   const int d = c.lane;
   const bool valid = d < 9;
   const int nx = mx + ddx(valid ? d : 8), ny = my + ddy(valid ? d : 8);
-  const bool skip = valid && !noskip && cell_blocked(c, nx, ny, moved);
+  // skip(q) for the nine probed cells at once: lane m looks at monster m and, if it counts (placed, or active and
+  // already moved: enemies.rs:383-384) and stands inside the 3x3 block, sets the bit of the direction that leads to it
+  bool skip = false;
+  if (!noskip) {
+    RG_PLANES(c);
+    uint32_t bit = 0;
+    if (c.lane < c.nrooms) {
+      const MonD mo = st->mon[c.lane];
+      const bool counts = (mo.flags & MF_PRESENT) && (!(mo.flags & MF_ACTIVE) || ((moved >> c.lane) & 1u));
+      const int dx = (int)mo.x - mx, dy = (int)mo.y - my;
+      if (counts && dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1)  // (dy+1)*3 + (dx+1) -> direction index (coord.rs:198-208)
+        bit = 1u << (uint32_t)((0x716382504ull >> (4 * ((dy + 1) * 3 + dx + 1))) & 15ull);
+    }
+    const uint32_t occ = __reduce_or_sync(RG_FULL, bit);
+    skip = valid && ((occ >> d) & 1u);
+  }
   const bool live = valid && !skip;
   const bool oob = live && !inb(c, nx, ny);
   uint32_t nd = 0xFFFFu;

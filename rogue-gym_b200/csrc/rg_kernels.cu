@@ -178,9 +178,10 @@ RG_DEV void emit_obs(const DevBatch& b, Ctx& c, int64_t env, int32_t reward, uin
   }
 }
 
-// Optional timeline (RG_TRACE=1): first start / last end of every kernel of a step, sampled by
-// one block in 64, read back with rg_trace.
-enum { TK_PLAYER = 0, TK_MONSTERS = 1, TK_FINISH = 2, TK_FULL = 3, TK_RESETS = 4, TK_PREFETCH = 5 };
+// Optional timeline (RG_TRACE=1): first start / last end of every kernel of a step over all its blocks,
+// read back with rg_trace.
+enum { TK_PLAYER = 0, TK_MONSTERS = 1, TK_FINISH = 2, TK_FULL = 3, TK_RESETS = 4, TK_PREFETCH = 5, TK_PLAYER_B = 6,
+       TK_MONSTERS_B = 7 };
 RG_DEV unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -190,8 +191,8 @@ struct TraceScope {
   unsigned long long* slot;
   RG_DEV TraceScope(const DevBatch& b, int kernel) {
     slot = nullptr;
-    // the generator kernels are sampled in full: their few working blocks have consecutive indices and the slowest one matters
-    if (b.trace && ((blockIdx.x & 63) == 0 || kernel == TK_FULL || kernel == TK_RESETS) && threadIdx.x == 0) {
+    // every block reports (tracing is a diagnostic mode): the last block to finish is what the next kernel waits for
+    if (b.trace && threadIdx.x == 0) {
       slot = b.trace + ((size_t)(kernel == TK_PREFETCH ? b.trace_step : (int)(*b.dstep % 512u)) * 8 + kernel) * 2;
       atomicMin(slot, gtime());
     }
@@ -283,14 +284,16 @@ RG_DEV bool has_active_monster(const Ctx& c) {
 // resident in the instruction caches (the single-kernel version spent most of its stall samples
 // on instruction fetch: 17-30 k SASS instructions executed divergently by independent warps):
 //
-//   k_step_fast     one THREAD per env: classifies the env from its key and a few state words and finishes the
-//                   cheap common steps itself (see there); descents and MoveUntil go to the full-path list,
-//                   everything else that needs warp-wide work to the slow list. full_path[] says who ends the step.
+//   k_step_scan     one thread per env, key + two state words: descents and MoveUntil go to the full-path list, envs
+//                   with an active monster to the first slow list. Three branches run side by side from here.
+//   k_step_fast     (main stream) one THREAD per remaining env: finishes the cheap common steps itself (see there);
+//                   what needs warp-wide work goes to the second slow list. full_path[] says who ends the step.
 //   k_step_gen      full-path list, high-priority side stream, beside the two kernels below: the whole
 //                   step compiled as one piece with the floor generator. A second, normally empty pass
 //                   after the monster kernel does the reset half of terminal steps that found no
 //                   prefetched game.
-//   k_step_player   slow list, one warp per env: key -> action -> player move / attack / pickup / search, hunger,
+//   k_step_player   a slow list (first list: own stream, beside k_step_fast; second list: after it), one warp per
+//                   env: key -> action -> player move / attack / pickup / search, hunger,
 //                   heal. Envs with an active monster go to the monster list; every other env is
 //                   finished here (finish_env).
 //   k_step_monsters monster list only: coin flips, lazy-BFS chase, attacks, then finish_env.
@@ -420,7 +423,7 @@ RG_DEV void finish_env(const DevBatch& b, Ctx& c, int64_t env, int auto_reset, i
 // Instruction count is the point: the warp-per-env kernel spends ~1 000 warp instructions per env-step with
 // 31 of 32 lanes duplicating scalar work (ncu, round 1); here a warp retires 32 envs at once.
 // ---------------------------------------------------------------------------------------------
-enum { CL_FAST = 0, CL_FULL = 1, CL_SLOW = 2 };
+enum { CL_FAST = 0, CL_FULL = 1, CL_SLOW = 2, CL_FAST_MOVE = 3, CL_FAST_LIGHT = 4 };
 
 RG_DEV uint32_t load4(const uint8_t* plane, int idx) {  // the 4 bytes at plane[idx .. idx+3], idx >= 0, any alignment
   const uint32_t* w = reinterpret_cast<const uint32_t*>(plane + (idx & ~3));
@@ -433,11 +436,23 @@ RG_DEV int lut_room(const DevBatch& b, int x, int y) {  // room_of without a Ctx
   return (cx == 0xFFu || ry == 0xFFu) ? -1 : (int)(ry * b.nx + cx);
 }
 
+RG_DEV uint32_t sel4(const uint32_t (&v)[4], int r) { return r == 0 ? v[0] : r == 1 ? v[1] : r == 2 ? v[2] : v[3]; }
+
+// Loads are issued in two dependent rounds (the kernel is latency-bound: 2 048 warps, each thread a chain of
+// scattered 16-byte reads): round 1 = the key and every piece of the hot block the action can need; round 2 = what
+// the position decides - the <= 4 rows of both planes around the move, the visited-map byte, the sector table
+// entries. Only the rare reads (a room record, the displayed gold) come later.
 RG_DEV int fast_env(const DevBatch& b, int64_t env, uint8_t key, int auto_reset) {
   (void)auto_reset;
   EnvState* const stp = b.st + env;
   const uint4* hot = reinterpret_cast<const uint4*>(stp);
+  int d;
+  const int act = map_key(key, d);
   const uint4 h0 = hot[0], h1 = hot[1], h2 = hot[2], h3 = hot[3], h4 = hot[4];
+  uint4 m0 = make_uint4(0, 0, 0, 0), m1 = m0, i0 = m0, i1 = m0, h11 = m0;
+  if (act == 0 && b.fast) {  // a move may need the monster and item tables and the stair: same round trip
+    m0 = hot[5]; m1 = hot[6]; i0 = hot[7]; i1 = hot[8]; h11 = hot[11];
+  }
   const int px = (int)(int16_t)(h0.x & 0xFFFFu), py = (int)(int16_t)(h0.x >> 16);
   const uint32_t is_terminal = h0.y & 0xFFu, ui_dead = (h0.y >> 8) & 0xFFu, serr = (h0.y >> 16) & 0xFFu;
   const uint32_t steps = h0.z;
@@ -449,8 +464,6 @@ RG_DEV int fast_env(const DevBatch& b, int64_t env, uint8_t key, int auto_reset)
   const uint32_t mon_present = h4.x & 0xFFFFu, mon_active = h4.x >> 16;
   const int W = b.W, H = b.H;
 
-  int d;
-  const int act = map_key(key, d);
   // ---- the early-outs of GameStateImpl::react / react_to_key (state_impls.rs:52-54, core/src/lib.rs:314,322-327)
   {
     int early = -1;
@@ -468,8 +481,7 @@ RG_DEV int fast_env(const DevBatch& b, int64_t env, uint8_t key, int auto_reset)
       return CL_FAST;
     }
   }
-  // ---- the full path: MoveUntil, or DownStair while standing on a stair
-  if (act == 1 || (act == 3 && b.surface[env * b.CP + py * W + px] == S_STAIR)) return CL_FULL;
+  // (the full path - MoveUntil, DownStair on a stair - and the envs with an active monster are on k_step_scan's lists)
   if (!b.fast) return CL_SLOW;
   if ((int64_t)steps + 1 >= b.max_steps) return CL_SLOW;  // the step ends the episode: finish_env's business
   if (act != 4 && (mon_active != 0 || plevel >= 8)) return CL_SLOW;  // monster phase / heal draws on the enemy stream
@@ -492,97 +504,117 @@ RG_DEV int fast_env(const DevBatch& b, int64_t env, uint8_t key, int auto_reset)
     nx = px + ddx(d);
     ny = py + ddy(d);
     bool can = nx >= 0 && ny >= 0 && nx < W && ny < H;
-    if (can) {  // Floor::can_move_impl floor.rs:169-182
-      const int ni = ny * W + nx;
-      can = can_walk(S[ni]) && !(A[ni] & (A_HIDDEN | A_LOCKED));
-      if (can && is_diag(d)) can = can_walk(S[py * W + nx]) && can_walk(S[ny * W + px]);
-    }
     if (can) {
-      if (dirty_rows != 0) return CL_SLOW;
-      const int pi = py * W + px, ni = ny * W + nx;
-      if ((A[pi] | A[ni]) & A_DOOR) return CL_SLOW;  // leaves_room / enters_room
-      const uint4 i0 = hot[7], i1 = hot[8];
-      const uint32_t items[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
       // the box that holds both 3x3 neighbourhoods, clipped to the field: rows y0..y1 (<= 4), columns x0..x1 (<= 4)
       const int x0 = max(min(px, nx) - 1, 0), x1 = min(max(px, nx) + 1, W - 1);
       const int y0 = max(min(py, ny) - 1, 0), y1 = min(max(py, ny) + 1, H - 1);
-      const uint32_t base0 = (uint32_t)(y0 * W + x0);
-      uint32_t item_cells = 0;  // bit r*4+k: an item lies on box cell (y0+r, x0+k)
-#pragma unroll
-      for (int i = 0; i < MAX_ROOMS; ++i) {
-        const uint32_t ip = (items[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
-        if (ip == 0xFFFFu) continue;
-        if (ip == (uint32_t)ni) return CL_SLOW;  // pickup: get_item actions.rs:206-231
-        const uint32_t dd = ip - base0;
-        if (dd <= (uint32_t)(3 * W + 3)) {
-          const uint32_t r = dd >= (uint32_t)(3 * W) ? 3u : dd >= (uint32_t)(2 * W) ? 2u : dd >= (uint32_t)W ? 1u : 0u;
-          const uint32_t k = dd - r * (uint32_t)W;
-          if (k < 4u) item_cells |= 1u << (r * 4u + k);
-        }
-      }
-      if (mon_present) {
-        const uint4 m0 = hot[5], m1 = hot[6];
-        const uint32_t mons[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-        const int room_old = lut_room(b, px, py), room_new = lut_room(b, nx, ny);
-#pragma unroll
-        for (int m = 0; m < MAX_ROOMS; ++m) {
-          if (!((mon_present >> m) & 1u)) continue;
-          const uint32_t xy = (mons[m >> 1] >> (16 * (m & 1))) & 0xFFFFu;
-          const int mx = (int)(xy & 0xFFu), my = (int)(xy >> 8);
-          // on the target (player_attack), or close enough for its adjacency / its cell's attributes to change
-          if (cheb(mx, my, px, py) <= 1 || cheb(mx, my, nx, ny) <= 1) return CL_SLOW;
-          const int rm = lut_room(b, mx, my);  // Dungeon::draw_enemy rogue/mod.rs:398-404 -> Floor::in_same_room
-          if (rm >= 0 && (rm == room_old || rm == room_new)) {
-            const RoomD r = stp->rooms[rm];
-            const bool in_m = in_rect(r, mx, my);
-            const bool so = rm == room_old && (r.kind == K_EMPTY || in_rect(r, px, py) == in_m);
-            const bool sn = rm == room_new && (r.kind == K_EMPTY || in_rect(r, nx, ny) == in_m);
-            if (so != sn) return CL_SLOW;
-          }
-        }
-      }
-      // ---- committed: Floor::player_out (floor.rs:298-312), Floor::player_in (:264-295), redraw of the box
-      uint8_t* scr = b.screen + env * b.CP;
+      const int pi = py * W + px, ni = ny * W + nx;
+      // ---- round 2: every load whose address the position decides
+      uint32_t sw[4], aw[4];
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        const int y = y0 + r;
-        if (y > y1) break;
-        const int rb = y * W + x0;
-        const uint32_t sw = load4(S, rb), aw = load4(A, rb);
-        const bool drawn_row = y >= 1 && y < H - 1;  // rows 0 and H-1 are never written (python/src/lib.rs:44)
+        const int rb = min(y0 + r, y1) * W + x0;  // rows past y1 repeat the last one (never used)
+        sw[r] = load4(S, rb);
+        aw[r] = load4(A, rb);
+      }
+      uint8_t* const hb = b.hist + env * b.HB + (ni >> 3);
+      const uint32_t hist_byte = *hb;
+      const uint64_t scr_rows = b.scr_rows[env];
+      const int room_old = lut_room(b, px, py), room_new = lut_room(b, nx, ny);
+      const uint32_t mons[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+      int mon_room[MAX_ROOMS];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int x = x0 + k;
-          if (x > x1) break;
-          const uint32_t sv = (sw >> (8 * k)) & 0xFFu, a_in = (aw >> (8 * k)) & 0xFFu;
-          uint32_t a = a_in;
-          const bool near_old = abs(x - px) <= 1 && abs(y - py) <= 1, near_new = abs(x - nx) <= 1 && abs(y - ny) <= 1;
-          if (!near_old && !near_new) continue;  // a corner of the box: nothing changes there (a monster may be drawn on it)
-          if (near_old && sv == S_FLOOR && (a & A_DARK)) a &= ~(uint32_t)A_VISIBLE;  // Cell::left
-          if (x == nx && y == ny) a |= A_VISITED;
-          if (near_new) {  // Cell::approached
-            const bool diag = x != nx && y != ny;
-            if (!(diag && sv == S_PASSAGE) && !(a & A_HIDDEN)) a |= A_DRAWN | A_VISIBLE;
-          }
-          if (a != a_in) A[rb + k] = (uint8_t)a;
-          if (drawn_row) {
-            uint32_t ch = (a & A_VISIBLE) ? surface_tile((uint8_t)(sv & 7u)) : ' ';
-            if (((item_cells >> (r * 4 + k)) & 1u) && (a & (A_VISIBLE | A_DRAWN))) ch = '*';
-            if (x == nx && y == ny && (a & (A_VISIBLE | A_DRAWN))) ch = '@';
-            scr[rb + k] = (uint8_t)ch;
+      for (int m = 0; m < MAX_ROOMS; ++m) {
+        mon_room[m] = -1;
+        if ((mon_present >> m) & 1u) {
+          const uint32_t xy = (mons[m >> 1] >> (16 * (m & 1))) & 0xFFFFu;
+          mon_room[m] = lut_room(b, (int)(xy & 0xFFu), (int)(xy >> 8));
+        }
+      }
+      // ---- Floor::can_move_impl floor.rs:169-182, from the rows just loaded
+      const int ro = py - y0, rn = ny - y0, co = px - x0, cn = nx - x0;
+      const uint32_t s_n = (sel4(sw, rn) >> (8 * cn)) & 0xFFu, a_n = (sel4(aw, rn) >> (8 * cn)) & 0xFFu;
+      const uint32_t a_p = (sel4(aw, ro) >> (8 * co)) & 0xFFu;
+      can = can_walk((uint8_t)s_n) && !(a_n & (A_HIDDEN | A_LOCKED));
+      if (can && is_diag(d))
+        can = can_walk((uint8_t)((sel4(sw, ro) >> (8 * cn)) & 0xFFu)) && can_walk((uint8_t)((sel4(sw, rn) >> (8 * co)) & 0xFFu));
+      if (can) {
+        if (dirty_rows != 0) return CL_SLOW;
+        if ((a_p | a_n) & A_DOOR) return CL_SLOW;  // leaves_room / enters_room
+        const uint32_t items[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+        const uint32_t base0 = (uint32_t)(y0 * W + x0);
+        uint32_t item_cells = 0;  // bit r*4+k: an item lies on box cell (y0+r, x0+k)
+#pragma unroll
+        for (int i = 0; i < MAX_ROOMS; ++i) {
+          const uint32_t ip = (items[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+          if (ip == 0xFFFFu) continue;
+          if (ip == (uint32_t)ni) return CL_SLOW;  // pickup: get_item actions.rs:206-231
+          const uint32_t dd = ip - base0;
+          if (dd <= (uint32_t)(3 * W + 3)) {
+            const uint32_t r = dd >= (uint32_t)(3 * W) ? 3u : dd >= (uint32_t)(2 * W) ? 2u : dd >= (uint32_t)W ? 1u : 0u;
+            const uint32_t k = dd - r * (uint32_t)W;
+            if (k < 4u) item_cells |= 1u << (r * 4u + k);
           }
         }
-        rows_touched |= 1ull << y;
-      }
-      uint8_t* hb = b.hist + env * b.HB + (ni >> 3);  // Floor::history_map: the one cell that became visited
-      *hb = (uint8_t)(*hb | (1u << (ni & 7)));
-      b.scr_rows[env] |= rows_touched;
-      moved = true;
-      if (b.spec) {
-        const uint32_t tailw = hot[11].w;  // cache_head, spec_req, stair_pos
-        if (!((tailw >> 8) & 0xFFu) && near_stair(W, nx, ny, tailw >> 16)) {
-          stp->spec_req = 1;
-          push_spec_request(b, env);
+        if (mon_present) {
+#pragma unroll
+          for (int m = 0; m < MAX_ROOMS; ++m) {
+            if (!((mon_present >> m) & 1u)) continue;
+            const uint32_t xy = (mons[m >> 1] >> (16 * (m & 1))) & 0xFFFFu;
+            const int mx = (int)(xy & 0xFFu), my = (int)(xy >> 8);
+            // on the target (player_attack), or close enough for its adjacency / its cell's attributes to change
+            if (cheb(mx, my, px, py) <= 1 || cheb(mx, my, nx, ny) <= 1) return CL_SLOW;
+            const int rm = mon_room[m];  // Dungeon::draw_enemy rogue/mod.rs:398-404 -> Floor::in_same_room
+            if (rm >= 0 && (rm == room_old || rm == room_new)) {
+              const RoomD r = stp->rooms[rm];
+              const bool in_m = in_rect(r, mx, my);
+              const bool so = rm == room_old && (r.kind == K_EMPTY || in_rect(r, px, py) == in_m);
+              const bool sn = rm == room_new && (r.kind == K_EMPTY || in_rect(r, nx, ny) == in_m);
+              if (so != sn) return CL_SLOW;
+            }
+          }
+        }
+        // ---- committed: Floor::player_out (floor.rs:298-312), Floor::player_in (:264-295), redraw of the box
+        uint8_t* scr = b.screen + env * b.CP;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int y = y0 + r;
+          if (y > y1) break;
+          const int rb = y * W + x0;
+          const bool drawn_row = y >= 1 && y < H - 1;  // rows 0 and H-1 are never written (python/src/lib.rs:44)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int x = x0 + k;
+            if (x > x1) break;
+            const uint32_t sv = (sw[r] >> (8 * k)) & 0xFFu, a_in = (aw[r] >> (8 * k)) & 0xFFu;
+            uint32_t a = a_in;
+            const bool near_old = abs(x - px) <= 1 && abs(y - py) <= 1, near_new = abs(x - nx) <= 1 && abs(y - ny) <= 1;
+            if (!near_old && !near_new) continue;  // a corner of the box: nothing changes there (a monster may be drawn on it)
+            if (near_old && sv == S_FLOOR && (a & A_DARK)) a &= ~(uint32_t)A_VISIBLE;  // Cell::left
+            if (x == nx && y == ny) a |= A_VISITED;
+            if (near_new) {  // Cell::approached
+              const bool diag = x != nx && y != ny;
+              if (!(diag && sv == S_PASSAGE) && !(a & A_HIDDEN)) a |= A_DRAWN | A_VISIBLE;
+            }
+            if (a != a_in) A[rb + k] = (uint8_t)a;
+            if (drawn_row) {
+              uint32_t ch = (a & A_VISIBLE) ? surface_tile((uint8_t)(sv & 7u)) : ' ';
+              if (((item_cells >> (r * 4 + k)) & 1u) && (a & (A_VISIBLE | A_DRAWN))) ch = '*';
+              if (x == nx && y == ny && (a & (A_VISIBLE | A_DRAWN))) ch = '@';
+              scr[rb + k] = (uint8_t)ch;
+            }
+          }
+          rows_touched |= 1ull << y;
+        }
+        *hb = (uint8_t)(hist_byte | (1u << (ni & 7)));  // Floor::history_map: the one cell that became visited
+        b.scr_rows[env] = scr_rows | rows_touched;
+        moved = true;
+        if (b.spec) {
+          const uint32_t tailw = h11.w;  // cache_head, spec_req, stair_pos
+          if (!((tailw >> 8) & 0xFFu) && near_stair(W, nx, ny, tailw >> 16)) {
+            stp->spec_req = 1;
+            push_spec_request(b, env);
+          }
         }
       }
     }
@@ -640,47 +672,96 @@ RG_DEV int fast_env(const DevBatch& b, int64_t env, uint8_t key, int auto_reset)
   return CL_FAST;
 }
 
-__global__ void __launch_bounds__(128) k_step_fast(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset) {
+// First kernel of a step, one thread per env, two state words and the key: the envs whose step is known to need the
+// warp kernels whatever else happens - the full path (descents, MoveUntil) and the envs with an active monster
+// (player phase, then monster phase) - are listed at once, so that both chains start ~6 us into the step and run
+// beside k_step_fast instead of after it. Everything else is left to k_step_fast (full_path[] = FP_FAST so far).
+__global__ void __launch_bounds__(256) k_step_scan(DevBatch b, const uint8_t* __restrict__ actions) {
   const int parity = (int)(*b.dstep & 1u);
-  TraceScope trace(b, TK_FINISH);
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // next step's counters
     b.defer_count[parity ^ 1] = 0;
     b.reset_count[parity ^ 1] = 0;
-    b.slow_count[parity ^ 1] = 0;
-    b.slow_count[2 + (parity ^ 1)] = 0;  // the player kernel's work cursor
-    b.mon_count[parity ^ 1] = 0;
-    b.mon_count[2 + (parity ^ 1)] = 0;   // the monster kernel's work cursor
+    b.fast_count[(parity ^ 1) * 2] = b.fast_count[(parity ^ 1) * 2 + 1] = 0;
+    for (int w = 0; w < 2; ++w) {
+      b.slow_count[w * 2 + (parity ^ 1)] = 0;
+      b.slow_count[4 + w * 2 + (parity ^ 1)] = 0;  // the player kernels' work cursors
+      b.mon_count[w * 2 + (parity ^ 1)] = 0;
+      b.mon_count[4 + w * 2 + (parity ^ 1)] = 0;   // the monster kernels' work cursors
+    }
   }
   const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   int cls = -1;
   if (env < b.n) {
-    cls = fast_env(b, env, actions[env], auto_reset);
+    const uint4* hot = reinterpret_cast<const uint4*>(b.st + env);
+    const uint4 h0 = hot[0];
+    const uint32_t mon_active = hot[4].x >> 16;
+    const uint32_t ui_dead = (h0.y >> 8) & 0xFFu, serr = (h0.y >> 16) & 0xFFu;
+    int d;
+    const int act = map_key(actions[env], d);
+    cls = CL_FAST;
+    const bool early = serr == RG_ERR_PANIC || serr == RG_ERR_SETTING || (int64_t)h0.z > b.max_steps || act < 0 || ui_dead;
+    if (!early) {
+      const int px = (int)(int16_t)(h0.x & 0xFFFFu), py = (int)(int16_t)(h0.x >> 16);
+      if (act == 1 || (act == 3 && b.surface[env * b.CP + py * b.W + px] == S_STAIR)) cls = CL_FULL;
+      else if (act != 4 && mon_active != 0) cls = CL_SLOW;
+    }
     b.full_path[env] = cls == CL_FAST ? FP_FAST : cls == CL_FULL ? FP_FULL : FP_PLAYER;
+    // k_step_fast takes its envs grouped by what they do, so that the threads of a warp run the same code: the moves
+    // (long: cells, monsters, items, redraw) in one list, everything else (early-outs, NoOp, NoDownStair, search) in
+    // the other. Unsorted, a warp executed every path with 5 of its 32 threads active on average (ncu).
+    if (cls == CL_FAST) cls = (!early && act == 0) ? CL_FAST_MOVE : CL_FAST_LIGHT;
   }
-  // warp-aggregated appends to the two work lists
   const uint32_t slowM = __ballot_sync(RG_FULL, cls == CL_SLOW), fullM = __ballot_sync(RG_FULL, cls == CL_FULL);
-  const uint32_t fastM = __ballot_sync(RG_FULL, cls == CL_FAST);
-  uint32_t sbase = 0, fbase = 0;
+  const uint32_t moveM = __ballot_sync(RG_FULL, cls == CL_FAST_MOVE), lightM = __ballot_sync(RG_FULL, cls == CL_FAST_LIGHT);
+  uint32_t sbase = 0, fbase = 0, mbase = 0, lbase = 0;
   if (lane == 0) {
     if (slowM) sbase = atomicAdd(b.slow_count + parity, (uint32_t)__popc(slowM));
     if (fullM) {
       fbase = atomicAdd(b.defer_count + parity, (uint32_t)__popc(fullM));
       atomicAdd(b.stats + RGS_FULL_STEP, (unsigned long long)__popc(fullM));
     }
-    if (fastM) atomicAdd(b.stats + RGS_FAST_STEPS, (unsigned long long)__popc(fastM));
+    if (moveM) mbase = atomicAdd(b.fast_count + parity * 2, (uint32_t)__popc(moveM));
+    if (lightM) lbase = atomicAdd(b.fast_count + parity * 2 + 1, (uint32_t)__popc(lightM));
   }
   sbase = __shfl_sync(RG_FULL, sbase, 0);
   fbase = __shfl_sync(RG_FULL, fbase, 0);
+  mbase = __shfl_sync(RG_FULL, mbase, 0);
+  lbase = __shfl_sync(RG_FULL, lbase, 0);
   const uint32_t below = (1u << lane) - 1u;
   if (cls == CL_SLOW) b.slow_list[sbase + __popc(slowM & below)] = (uint32_t)env;
   if (cls == CL_FULL) b.defer_list[fbase + __popc(fullM & below)] = (uint32_t)env;
+  if (cls == CL_FAST_MOVE) b.fast_list_m[mbase + __popc(moveM & below)] = (uint32_t)env;
+  if (cls == CL_FAST_LIGHT) b.fast_list_l[lbase + __popc(lightM & below)] = (uint32_t)env;
 }
 
-// Player phase of one env of the slow list: key -> action -> player move / attack / pickup / search, hunger, heal.
-// An env with an active monster is handed to the monster kernel; every other env is finished here.
+__global__ void __launch_bounds__(128) k_step_fast(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset) {
+  const int parity = (int)(*b.dstep & 1u);
+  TraceScope trace(b, TK_FINISH);
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const uint32_t n_move = b.fast_count[parity * 2], n_light = b.fast_count[parity * 2 + 1];
+  int cls = -1;
+  int64_t env = -1;
+  if (t < (int64_t)n_move) env = (int64_t)b.fast_list_m[t];
+  else if (t < (int64_t)n_move + (int64_t)n_light) env = (int64_t)b.fast_list_l[t - (int64_t)n_move];
+  if (env >= 0) {
+    cls = fast_env(b, env, actions[env], auto_reset);
+    if (cls != CL_FAST) b.full_path[env] = FP_PLAYER;
+  }
+  // warp-aggregated append of the leftovers to the second slow list
+  const uint32_t slowM = __ballot_sync(RG_FULL, cls == CL_SLOW), fastM = __ballot_sync(RG_FULL, cls == CL_FAST);
+  uint32_t sbase = 0;
+  if (lane == 0) {
+    if (slowM) sbase = atomicAdd(b.slow_count + 2 + parity, (uint32_t)__popc(slowM));
+    if (fastM) atomicAdd(b.stats + RGS_FAST_STEPS, (unsigned long long)__popc(fastM));
+  }
+  sbase = __shfl_sync(RG_FULL, sbase, 0);
+  if (cls == CL_SLOW) b.slow_list_b[sbase + __popc(slowM & ((1u << lane) - 1u))] = (uint32_t)env;
+}
+
 RG_DEV void player_env(const DevBatch& b, Stager& sg, unsigned char* base, int64_t env, const uint8_t* __restrict__ actions,
-                       int auto_reset, int parity) {
+                       int auto_reset, int parity, int which) {
   // The env's state and both planes are requested first; the key is read while the bulk loads fly.
   stage_issue(b, sg, base, env, PL_BOTH);
   const uint8_t key = actions[env];
@@ -709,7 +790,7 @@ RG_DEV void player_env(const DevBatch& b, Stager& sg, unsigned char* base, int64
     st->f_msg = c.msg;
     st->f_flags = (uint8_t)((c.redraw ? SF_REDRAW : 0) | (c.status_upd ? SF_STATUS : 0));
     if (c.lane == 0) {
-      b.mon_list[atomicAdd(b.mon_count + parity, 1u)] = (uint32_t)env;
+      (which ? b.mon_list_b : b.mon_list)[atomicAdd(b.mon_count + which * 2 + parity, 1u)] = (uint32_t)env;
       b.full_path[env] = FP_MONSTERS;
     }
     count_event(b, c, RGS_MONSTER_ENVS);
@@ -719,32 +800,38 @@ RG_DEV void player_env(const DevBatch& b, Stager& sg, unsigned char* base, int64
   }
 }
 
-// One-warp blocks over the slow list (what k_step_fast left). Envs are handed out one at a time: their cost
-// varies (a room reveal, a fight, an episode end with its 10 KB swap-in).
+// One-warp blocks over a slow list: `which` = 0 the envs k_step_scan found with an active monster (this launch and
+// its monster kernel run on a stream of their own beside k_step_fast), 1 the envs k_step_fast left over. Envs are
+// handed out one at a time: their cost varies (a room reveal, a fight, an episode end with its 10 KB swap-in).
 __global__ void __launch_bounds__(32, RG_HOT_MIN_BLOCKS)
-k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset) {
+k_step_player(DevBatch b, const uint8_t* __restrict__ actions, int auto_reset, int which) {
   unsigned char* const smem = rg_smem;
   const int parity = (int)(*b.dstep & 1u);
-  TraceScope trace(b, TK_PLAYER);
-  const uint32_t count = b.slow_count[parity];
+  TraceScope trace(b, which ? TK_PLAYER_B : TK_PLAYER);
+  const uint32_t count = b.slow_count[which * 2 + parity];
+  const uint32_t* const list = which ? b.slow_list_b : b.slow_list;
   Stager sg = stager_init(b, smem);
   for (;;) {
     uint32_t i = 0;
-    if (threadIdx.x == 0) i = atomicAdd(b.slow_count + 2 + parity, 1u);
+    if (threadIdx.x == 0) i = atomicAdd(b.slow_count + 4 + which * 2 + parity, 1u);
     i = __shfl_sync(RG_FULL, i, 0);
     if (i >= count) break;
-    player_env(b, sg, smem, (int64_t)b.slow_list[i], actions, auto_reset, parity);
+    player_env(b, sg, smem, (int64_t)list[i], actions, auto_reset, parity, which);
     __syncwarp();
   }
 }
 
 // actions::move_active_enemies (actions.rs:82-119) for the envs that have an active monster
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 16)
-k_step_monsters(DevBatch b, int auto_reset) {
+#ifndef RG_MON_MIN_BLOCKS
+#define RG_MON_MIN_BLOCKS 16
+#endif
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_MON_MIN_BLOCKS)
+k_step_monsters(DevBatch b, int auto_reset, int which) {
   unsigned char* const smem = rg_smem;
   const int parity = (int)(*b.dstep & 1u);
-  TraceScope trace(b, TK_MONSTERS);
-  const uint32_t count = b.mon_count[parity];
+  TraceScope trace(b, which ? TK_MONSTERS_B : TK_MONSTERS);
+  const uint32_t count = b.mon_count[which * 2 + parity];
+  const uint32_t* const list = which ? b.mon_list_b : b.mon_list;
   const int warp = threadIdx.x >> 5;
   unsigned char* const base = smem + (size_t)warp * warp_smem(b);
   Stager sg = stager_init(b, base);
@@ -752,10 +839,10 @@ k_step_monsters(DevBatch b, int auto_reset) {
   // and warps on SMs that also host a background generator block run slower
   for (;;) {
     uint32_t i = 0;
-    if ((threadIdx.x & 31) == 0) i = atomicAdd(b.mon_count + 2 + parity, 1u);
+    if ((threadIdx.x & 31) == 0) i = atomicAdd(b.mon_count + 4 + which * 2 + parity, 1u);
     i = __shfl_sync(RG_FULL, i, 0);
     if (i >= count) break;
-    const int64_t env = (int64_t)b.mon_list[i];
+    const int64_t env = (int64_t)list[i];
     Ctx c;
     fill_ctx(b, c, sg, base, env, PL_BOTH);  // surface for the moves, both planes if the step ends with a compose
     EnvState* st = c.st;
@@ -1241,6 +1328,74 @@ __global__ void __launch_bounds__(256) k_encode_gray(DevBatch b, uint32_t flag, 
   }
 }
 
+// Compact observation (rg_encode_compact): symbol ids, not one-hot planes. A thread maps 16 cells (one 128-bit load,
+// one 128-bit store) through a 256-entry table in shared memory; HBM-bound at 2 bytes per cell.
+__global__ void __launch_bounds__(256) k_encode_compact(DevBatch b, uint8_t* __restrict__ sym_out, int32_t* __restrict__ status_out,
+                                                       uint8_t* __restrict__ hist_out) {
+  __shared__ uint8_t sym_of_tile[256];
+  {
+    const int sym = tile_sym(threadIdx.x);
+    sym_of_tile[threadIdx.x] = sym < 0 ? 0xFFu : (uint8_t)sym;  // no symbol at all: InvalidTileError symbol.rs:60-64
+  }
+  __syncthreads();
+  const int pieces = b.CP / 16;
+  const int64_t total = b.n * pieces;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t env = i / pieces;
+    const int piece = (int)(i - env * pieces), base = piece * 16;
+    const uint4 v = *reinterpret_cast<const uint4*>(b.screen + env * b.CP + base);
+    const uint32_t in[4] = {v.x, v.y, v.z, v.w};
+    uint32_t out[4];
+    bool bad = false;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t o = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t sy = sym_of_tile[(in[q] >> (8 * k)) & 0xFFu];
+        if (sy == 0xFFu) {
+          if (base + q * 4 + k < b.C) bad = true;
+          sy = 0;
+        }
+        o |= sy << (8 * k);
+      }
+      out[q] = o;
+    }
+    if (bad) {
+      b.error[env] = RG_ERR_SETTING;
+      atomicOr(b.errflag, 1u << RG_ERR_SETTING);
+    }
+    uint8_t* dst = sym_out + env * (int64_t)b.C + base;
+    if ((b.C & 15) == 0) {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
+    } else {  // odd sizes: the dense rows are not 16-byte aligned
+      for (int k = 0; k < 16 && base + k < b.C; ++k) dst[k] = (uint8_t)(out[k >> 2] >> (8 * (k & 3)));
+    }
+    if (hist_out) {  // Floor::history_map as 0/1 bytes
+      const uint32_t bits = reinterpret_cast<const uint16_t*>(b.hist + env * b.HB)[piece];
+      uint8_t* hd = hist_out + env * (int64_t)b.C + base;
+      if ((b.C & 15) == 0) {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t nib = (bits >> (4 * q)) & 0xFu;
+          w[q] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+        }
+        *reinterpret_cast<uint4*>(hd) = make_uint4(w[0], w[1], w[2], w[3]);
+      } else {
+        for (int k = 0; k < 16 && base + k < b.C; ++k) hd[k] = (uint8_t)((bits >> k) & 1u);
+      }
+    }
+    if (status_out && piece == 0) {  // StatusFlagInner::to_vector order python/src/flags.rs:63-85
+      const uint32_t* st = b.status + env * 10;
+      int32_t* so = status_out + env * 9;
+      so[0] = (int32_t)st[0];
+#pragma unroll
+      for (int k = 1; k < 9; ++k) so[k] = (int32_t)st[k + 1];
+    }
+  }
+}
+
 // ---------------------------------------------------------------- trainer-facing step (rg_step_train)
 // Before the step: gym action index -> ASCII key (RogueEnv.ACTIONS, python/rogue_gym/envs/rogue_env.py:159-172).
 __global__ void __launch_bounds__(256) k_keys_from_index(DevBatch b, const void* __restrict__ idx, int index_bytes,
@@ -1431,6 +1586,7 @@ cudaError_t configure_kernels(const DevBatch& b) {
   cudaError_t e = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_step_player, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one_warp_smem(b));
+
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_step_monsters, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return e;
@@ -1461,33 +1617,43 @@ cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_rese
   const size_t sm = block_smem(b);
   int gen_blocks = (int)std::min<int64_t>(b.gen_warps / GEN_WPB, (b.n + GEN_WPB - 1) / GEN_WPB);
   const size_t gen_sm = GEN_WPB * one_warp_smem(b);
+  const int pblocks = (int)std::min<int64_t>(b.player_blocks > 0 ? b.player_blocks : (int64_t)sm_count * RG_HOT_MIN_BLOCKS, b.n);
+  const int mon_blocks = (int)std::min<int64_t>(b.mon_warps / WARPS_PER_BLOCK, (b.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
   cudaError_t e;
-  k_step_fast<<<(unsigned)((b.n + 127) / 128), 128, 0, s>>>(b, actions, auto_reset);
+  k_step_scan<<<(unsigned)((b.n + 255) / 256), 256, 0, s>>>(b, actions);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  // full-path steps (descents, MoveUntil) are a few long serial chains: they start first, on the
-  // high-priority side stream, and run beside the player and monster kernels
   if ((e = cudaEventRecord(q.ev_fork, s)) != cudaSuccess) return e;
+  // branch 1, high-priority side stream: full-path steps (descents, MoveUntil) - a few long serial chains
   if ((e = cudaStreamWaitEvent(q.side, q.ev_fork, 0)) != cudaSuccess) return e;
   k_step_gen<<<gen_blocks, GEN_WPB * 32, gen_sm, q.side>>>(b, actions, auto_reset, 0, 0);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if ((e = cudaEventRecord(q.ev_join, q.side)) != cudaSuccess) return e;
+  // branch 2, high-priority stream: the envs with an active monster - player phase, then monster phase
+  cudaStream_t m = b.branches ? q.mon : s;
+  if (b.branches && (e = cudaStreamWaitEvent(q.mon, q.ev_fork, 0)) != cudaSuccess) return e;
+  k_step_player<<<pblocks, 32, one_warp_smem(b), m>>>(b, actions, auto_reset, 0);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  k_step_monsters<<<b.mon_warps / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, sm, m>>>(b, auto_reset, 0);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (b.branches && (e = cudaEventRecord(q.ev_mon, q.mon)) != cudaSuccess) return e;
+  // branch 3, main stream: every other env, one thread each; then what that kernel could not finish
+  k_step_fast<<<(unsigned)((b.n + 127) / 128), 128, 0, s>>>(b, actions, auto_reset);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (mirror) {
     // host mirror, first pass: the envs k_step_fast finished (most of them), beside every other kernel of the
     // step - the pass is dominated by small PCIe writes, not by SM work
-    if ((e = cudaStreamWaitEvent(q.mir, q.ev_fork, 0)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(q.ev_fast, s)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(q.mir, q.ev_fast, 0)) != cudaSuccess) return e;
     k_mirror<<<mirror_blocks(b, sm_count), 256, 0, q.mir>>>(b, *mirror, 1, 0, b.n);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if ((e = cudaEventRecord(q.ev_mir, q.mir)) != cudaSuccess) return e;
   }
-  {
-    const int pblocks = (int)std::min<int64_t>(b.player_blocks > 0 ? b.player_blocks : (int64_t)sm_count * RG_HOT_MIN_BLOCKS, b.n);
-    k_step_player<<<pblocks, 32, one_warp_smem(b), s>>>(b, actions, auto_reset);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    const int mon_blocks = (int)std::min<int64_t>(b.mon_warps / WARPS_PER_BLOCK, (b.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-    k_step_monsters<<<mon_blocks, WARPS_PER_BLOCK * 32, sm, s>>>(b, auto_reset);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  }
+  k_step_player<<<pblocks, 32, one_warp_smem(b), s>>>(b, actions, auto_reset, 1);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  k_step_monsters<<<std::max(1, mon_blocks / 4), WARPS_PER_BLOCK * 32, sm, s>>>(b, auto_reset, 1);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if ((e = cudaStreamWaitEvent(s, q.ev_join, 0)) != cudaSuccess) return e;
+  if (b.branches && (e = cudaStreamWaitEvent(s, q.ev_mon, 0)) != cudaSuccess) return e;
   if (auto_reset) {
     // episode ends whose next game was not prefetched in time (normally none; with prefetching on, a
     // small grid is enough), and the end-of-step bookkeeping in the last block to finish
@@ -1532,6 +1698,13 @@ cudaError_t launch_encode(const DevBatch& b, int mode, uint32_t flag, int with_h
   } else {
     k_encode<<<(unsigned)b.n, 256, 0, s>>>(b, mode, flag, with_hist, channels, out);
   }
+  return cudaGetLastError();
+}
+cudaError_t launch_encode_compact(const DevBatch& b, uint8_t* sym_out, int32_t* status_out, uint8_t* hist_out, int sm_count,
+                                  cudaStream_t s) {
+  const int64_t total = b.n * (b.CP / 16);
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count * 16);
+  k_encode_compact<<<blocks, 256, 0, s>>>(b, sym_out, status_out, hist_out);
   return cudaGetLastError();
 }
 cudaError_t launch_complete_maps(const DevBatch& b, int64_t env_lo, int64_t env_hi, cudaStream_t s) {

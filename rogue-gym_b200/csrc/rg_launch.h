@@ -26,10 +26,12 @@ struct MirrorArgs {
 struct StepStreams {
   cudaStream_t main;   // the batch's stream
   cudaStream_t side;   // high priority: the full-path kernel
+  cudaStream_t mon;    // high priority: player + monster kernels of the envs with an active monster
   cudaStream_t mir;    // first host-mirror pass, beside the player / monster / full-path / reset kernels
-  cudaEvent_t ev_fork, ev_join, ev_mir;
+  cudaEvent_t ev_fork, ev_join, ev_mon, ev_fast, ev_mir;
 };
-// one env-step = thread-per-env kernel, full-path kernel beside {player, monster} kernels, reset pass, end
+// one env-step = scan, then three branches side by side (full path | active-monster envs | thread-per-env kernel
+// and its leftovers), reset pass, end
 // `mirror` != nullptr adds the two host-mirror passes to the step (rg_step_mirror)
 cudaError_t launch_step(const DevBatch& b, const uint8_t* actions_dev, int auto_reset, const StepStreams& q,
                         const MirrorArgs* mirror, int sm_count);
@@ -41,6 +43,8 @@ cudaError_t launch_test_move_enemy(const DevBatch& b, int64_t env, int fx, int f
                                    cudaStream_t s);
 cudaError_t launch_encode(const DevBatch& b, int mode, uint32_t flag, int with_hist, int channels, float* out_dev,
                           cudaStream_t s);
+cudaError_t launch_encode_compact(const DevBatch& b, uint8_t* sym_out_dev, int32_t* status_out_dev, uint8_t* hist_out_dev,
+                                  int sm_count, cudaStream_t s);
 cudaError_t launch_complete_maps(const DevBatch& b, int64_t env_lo, int64_t env_hi, cudaStream_t s);
 // delta write-back of the whole observation block into the mapped host mirror (k_mirror, every env)
 cudaError_t launch_mirror(const DevBatch& b, const MirrorArgs& m, int sm_count, cudaStream_t s);

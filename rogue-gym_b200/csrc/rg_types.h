@@ -152,8 +152,13 @@ struct DevBatch {
   uint32_t* defer_list;   // [N] env id | DEFER_* : work handed to the full-path kernel k_step_gen
   uint32_t* defer_count;  // [2] ping-pong by step parity
   uint8_t* full_path;     // [N] who finishes this step of the env (FP_*), written by k_step_fast every step
-  uint32_t* slow_list;    // [N] envs k_step_fast left to the warp-per-env player kernel
-  uint32_t* slow_count;   // [2] ping-pong by step parity, then [2] work cursors of the player kernel
+  uint32_t* fast_list_m;  // [N] k_step_fast's envs whose action is a move (k_step_scan groups them: no divergence)
+  uint32_t* fast_list_l;  // [N] k_step_fast's other envs
+  uint32_t* fast_count;   // [parity][move, other] list lengths
+  uint32_t* slow_list;    // [N] envs with an active monster (k_step_scan -> player kernel, first list)
+  uint32_t* slow_list_b;  // [N] envs k_step_fast left to the warp-per-env player kernel (second list)
+  uint32_t* slow_count;   // [list][parity] lengths, then [list][parity] work cursors of the player kernels
+  int32_t branches;       // 1 = the active-monster envs' kernels run on a stream of their own beside k_step_fast
   int32_t fast;           // 0 = k_step_fast only classifies (every env goes to the player kernel; RG_FAST=0)
   uint32_t* reset_list;   // [N] terminal envs whose next game was not prefetched in time (finish_env -> reset pass of k_step_gen)
   uint32_t* reset_count;  // [2]
@@ -194,8 +199,9 @@ struct DevBatch {
   uint32_t* spec_win;       // [8][2] window served by the pass kicked after step s % 8
   uint32_t spec_cap;        // power of two
   int32_t spec_warps;
-  uint32_t* mon_list;     // [N] envs with an active monster this step (player kernel -> monster kernel)
-  uint32_t* mon_count;    // [2] list lengths by step parity, then [2] work cursors
+  uint32_t* mon_list;     // [N] envs with an active monster this step (player kernel -> monster kernel), first list
+  uint32_t* mon_list_b;   // [N] the same for the second slow list
+  uint32_t* mon_count;    // [list][parity] lengths, then [list][parity] work cursors
   int32_t mon_warps;      // warps of the (grid-stride) monster kernel
   int32_t player_blocks;  // > 0: one-warp blocks of the player kernel (default: 32 per SM)
 };

@@ -9,8 +9,10 @@ policy reads, and screen / status / reward / done are zero-copy tensor views of 
 `rg_views` block. No per-env Python objects are created.
 
     env = DeviceRogueEnv({"seed": None}, num_envs=65536, image_setting=ImageSetting(), seeds=range(1, 65537))
-    obs = env.reset()                                  # float32 [N, C, H, W] on cuda
+    obs = env.reset()                                  # CompactObs(symbols u8 [N,H,W], status i32 [N,9], history) on cuda
     obs, reward, done, info = env.step(actions)        # actions: int tensor [N], indices into ACTIONS
+    image = env.expand(obs)                            # float32 [N, C, H, W] == ImageSetting.expand per state
+(`observation="image"` makes every step write that image instead: 401 KB per env for the reference default.)
 
 Semantics are those of `ParallelRogueEnv` (auto-reset: a terminal env returns the first observation
 of its next episode with done = 1; reward = max(0, gold gained), parallel.py:60-66) plus the optional
@@ -19,14 +21,56 @@ thread would have panicked stay frozen and are reported by `errors()`; nothing i
 """
 import ctypes as C
 import json
-from typing import Iterable, Optional, Sequence
+from typing import Iterable, NamedTuple, Optional, Sequence
 
 import numpy as np
 
 from rogue_gym_python import _cabi
 
 from .._gymapi import spaces
-from .rogue_env import ImageSetting, RogueEnv
+from .rogue_env import DungeonType, ImageSetting, RogueEnv
+
+
+class CompactObs(NamedTuple):
+    """The default observation of DeviceRogueEnv: what `ImageSetting.expand` carries, before the one-hot expansion.
+    symbols uint8 [N, H, W] (Symbol ids, core/src/symbol.rs:17-40), status int32 [N, 9] (StatusFlag order),
+    history uint8 [N, H, W] 0/1 or None. The tensors are the env's own buffers, overwritten by the next step."""
+
+    symbols: "object"
+    status: "object"
+    history: "object"
+
+
+class SymbolExpand:
+    """CompactObs -> the float32 [N, C, H, W] image of `ImageSetting.expand` (python/rogue_gym/envs/rogue_env.py:84-98,
+    python/src/lib.rs:158-205), on the device, bit for bit: one-hot symbol planes (the last one is always empty,
+    SURVEY.md 8a a14), one constant plane per selected status value, the visited map. A policy would rather feed
+    `obs.symbols.long()` to an nn.Embedding and `obs.status` to its head; this is the proof that nothing is lost."""
+
+    def __init__(self, image_setting: "ImageSetting", symbols: int):
+        self.setting, self.symbols = image_setting, int(symbols)
+
+    def __call__(self, obs: CompactObs):
+        import torch
+        import torch.nn.functional as F
+        n, h, w = obs.symbols.shape
+        planes = []
+        if self.setting.dungeon == DungeonType.SYMBOL:
+            hot = F.one_hot(obs.symbols.long(), self.symbols).permute(0, 3, 1, 2).to(torch.float32)
+            hot[:, self.symbols - 1] = 0
+            planes.append(hot)
+        else:
+            # one IEEE f32 division per cell like python/src/lib.rs:72-84 (a Python-scalar divisor would be turned
+            # into a multiplication by its reciprocal, which rounds differently)
+            div = torch.full((), float(self.symbols), dtype=torch.float32, device=obs.symbols.device)
+            planes.append((obs.symbols.to(torch.float32) / div).unsqueeze(1))
+        flag = self.setting.status.value
+        cols = [k for k in range(9) if flag & (1 << k)]
+        if cols:
+            planes.append(obs.status[:, cols].to(torch.float32)[:, :, None, None].expand(n, len(cols), h, w))
+        if self.setting.includes_hist:
+            planes.append(obs.history.to(torch.float32).unsqueeze(1))
+        return torch.cat(planes, dim=1)
 
 
 class _DevPtr:
@@ -53,7 +97,14 @@ class DeviceRogueEnv:
         device: int = 0,
         seeds: Optional[Iterable[int]] = None,
         stair_reward: float = 0.0,
+        observation: str = "compact",
     ) -> None:
+        """observation: "compact" (default) - every step returns a CompactObs of device tensors (symbol ids + status
+        vector [+ visited map if image_setting.includes_hist]: 1.9 KB per env, `env.expand(obs)` gives the image);
+        "image" - the float32 [N, C, H, W] image of `image_setting` (401 KB per env for the reference default)."""
+        if observation not in ("compact", "image"):
+            raise ValueError("observation must be 'compact' or 'image'")
+        self.observation = observation
         import torch
 
         self._torch = torch
@@ -86,7 +137,13 @@ class DeviceRogueEnv:
         self.observation_space = image_setting.detect_space(v.height, v.width, self.symbols)
         self._enc = image_setting.encoder_args()
         self.channels = int(self._L.rg_encode_channels(h, *self._enc))
-        self.obs = torch.empty((n, self.channels, v.height, v.width), dtype=torch.float32, device=self.device)
+        self.expand = SymbolExpand(image_setting, self.symbols)
+        if observation == "image":
+            self.obs = torch.empty((n, self.channels, v.height, v.width), dtype=torch.float32, device=self.device)
+        else:
+            hist = torch.empty((n, v.height, v.width), dtype=torch.uint8, device=self.device) if image_setting.includes_hist else None
+            self.obs = CompactObs(torch.empty((n, v.height, v.width), dtype=torch.uint8, device=self.device),
+                                  torch.empty((n, 9), dtype=torch.int32, device=self.device), hist)
         self.reward = torch.zeros(n, dtype=torch.float32, device=self.device)
         self._stream = torch.cuda.ExternalStream(int(self._L.rg_stream(h)), device=self.device)
         if seeds is not None:
@@ -105,8 +162,13 @@ class DeviceRogueEnv:
     def _observe(self):
         ch = C.c_int()
         with self._torch.cuda.stream(self._stream):
-            _cabi.check(self._L.rg_encode(self._h, self._enc[0], self._enc[1], self._enc[2], self.obs.data_ptr(),
-                                          C.byref(ch)), self._h)
+            if self.observation == "image":
+                _cabi.check(self._L.rg_encode(self._h, self._enc[0], self._enc[1], self._enc[2], self.obs.data_ptr(),
+                                              C.byref(ch)), self._h)
+            else:
+                o = self.obs
+                _cabi.check(self._L.rg_encode_compact(self._h, o.symbols.data_ptr(), o.status.data_ptr(),
+                                                      o.history.data_ptr() if o.history is not None else None), self._h)
 
     def _alive(self):
         if not self._h:
@@ -162,9 +224,12 @@ class DeviceRogueEnv:
         # record_stream() (the batch owns that stream and destroys it in close(), which the caching
         # allocator's bookkeeping for recorded streams does not survive at interpreter exit)
         self._last_actions = a
+        image = self.observation == "image"
         _cabi.check(self._L.rg_step_train(self._h, a.data_ptr(), index_bytes, self._enc[0], self._enc[1],
-                                          self._enc[2], self.obs.data_ptr(), self.reward.data_ptr(),
+                                          self._enc[2], self.obs.data_ptr() if image else None, self.reward.data_ptr(),
                                           C.c_float(self.stair_reward)), self._h)
+        if not image:
+            self._observe()
         cur.wait_stream(self._stream)
         return self.obs, self.reward, self.done, {}
 

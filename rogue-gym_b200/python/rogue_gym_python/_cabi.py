@@ -115,6 +115,7 @@ SYMBOLS = {
     "rg_launch_count": (_i64, [_vp]),
     "rg_encode": (_i, [_vp, _i, _u32, _i, _vp, C.POINTER(_i)]),
     "rg_encode_channels": (_i, [_vp, _i, _u32, _i]),
+    "rg_encode_compact": (_i, [_vp, _vp, _vp, _vp]),
     "rg_encode_states": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _u32, _i, _vp, C.POINTER(_i)]),
     "rg_dump_env": (_i, [_vp, _i64, C.POINTER(Dump)]),
     "rg_state_hash": (_i, [_vp, _vp]),

@@ -304,18 +304,47 @@ def _panic_free_seeds(oracle, cfg, n, steps, max_steps):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("observation", ["compact", "image"])
 @pytest.mark.parametrize("setting_args", [(2, 0x1FF, False), (1, 0x03, True), (2, 0, True)])
-def test_device_env_matches_list_api(envs, oracle, setting_args):
+def test_device_env_matches_list_api(envs, oracle, setting_args, observation):
+    """Both observation forms of DeviceRogueEnv against the list API: "image" is the float32 image itself; "compact"
+    (the default: symbol ids + status vector [+ visited map], 1.9 KB instead of 401 KB per env) must expand on the
+    device - env.expand = SymbolExpand - to exactly that image, every step."""
     import torch
     n, steps, max_steps = 96, 120, 40
     setting = envs.ImageSetting(envs.DungeonType(setting_args[0]), envs.StatusFlag(setting_args[1]), setting_args[2])
     cfg = {}
     seeds = _panic_free_seeds(oracle, cfg, n, steps, max_steps)
-    dev = envs.DeviceRogueEnv(cfg, num_envs=n, max_steps=max_steps, image_setting=setting, seeds=seeds, stair_reward=50.0)
+    dev = envs.DeviceRogueEnv(cfg, num_envs=n, max_steps=max_steps, image_setting=setting, seeds=seeds, stair_reward=50.0,
+                              observation=observation)
+    assert envs.DeviceRogueEnv.__init__.__defaults__[-1] == "compact"
     ref = envs.StairRewardParallel(config_dicts=[cfg] * n, max_steps=max_steps, image_setting=setting)
     ref.seed([int(s) for s in seeds])
     states = ref.reset()
     obs = dev.reset()
+    if observation == "compact":
+        raw = obs
+        assert raw.symbols.is_cuda and raw.symbols.dtype == torch.uint8 and raw.symbols.shape == (n, 24, 80)
+        assert raw.status.shape == (n, 9) and (raw.history is not None) == setting.includes_hist
+        assert int(raw.symbols.max()) <= dev.symbols - 1
+
+        class _Expanding:  # the rest of the test sees images
+            def __init__(self, env):
+                self.env = env
+
+            def __getattr__(self, name):
+                return getattr(self.env, name)
+
+            def step(self, a):
+                o, r, d, i = self.env.step(a)
+                return self.env.expand(o), r, d, i
+
+            def step_keys(self, k):
+                o, r, d, i = self.env.step_keys(k)
+                return self.env.expand(o), r, d, i
+
+        obs = dev.expand(obs)
+        dev = _Expanding(dev)
     assert obs.shape == (n,) + dev.observation_space.shape and obs.is_cuda
     assert np.array_equal(obs.cpu().numpy(), ref.game.encode_states(states, *setting.encoder_args()))
     key_to_index = {ord(k): i for i, k in enumerate(envs.RogueEnv.ACTIONS)}

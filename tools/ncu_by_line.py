@@ -3,7 +3,7 @@
 
   ncu -i prof.ncu-rep --page source --csv > sass.csv
   cuobjdump -xelf all librogue_b200.so; nvdisasm -g -c rg_kernels.sm_100a.cubin > k.sass
-  python tools/ncu_by_line.py sass.csv k.sass <mangled kernel name> [top_n]
+  python tools/ncu_by_line.py sass.csv k.sass <mangled kernel name> [top_n] [substring of the instance's kernel name]
 
 Joins on instruction offset (nvdisasm `/*0040*/` vs ncu address - first address); prints the
 share of warp-stall samples and executed instructions per source line and per enclosing
@@ -50,6 +50,7 @@ def function_table(path):
 def main():
     sass_csv, disasm, kernel = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+    want = sys.argv[5] if len(sys.argv) > 5 else None  # substring of the "Kernel Name" row of the instance to take
     off2line = parse_sass(disasm, kernel)
     rows = list(csv.reader(open(sass_csv)))
     # several kernel instances may be concatenated: take the first whose name matches
@@ -60,6 +61,8 @@ def main():
     stall_cols = None
     for k, h in enumerate(hdr_i):
         end = name_i[name_i.index(h - 1) + 1] if (h - 1) in name_i and name_i.index(h - 1) + 1 < len(name_i) else len(rows)
+        if want and not any(want in c for c in rows[h - 1]):
+            continue
         hdr = rows[h]
         si, ii = hdr.index("# Samples"), hdr.index("Instructions Executed")
         stall_cols = [(j, c) for j, c in enumerate(hdr) if c.startswith("stall_") and "Not Issued" not in c]

@@ -20,7 +20,7 @@ for t in range(steps):
     sh.step_device(d.data_ptr() + t * n)
 sh.sync()
 _cabi.check(sh.L.rg_trace(sh.h, out.ctypes.data, C.byref(launched)), sh.h)
-names = ["player", "monsters", "fast", "full", "resets", "prefetch"]
+names = ["playerA", "monstersA", "fast", "full", "resets", "prefetch", "playerB", "monstersB"]
 last = (launched.value - 1) % 512
 order = [(last - k) % 512 for k in range(12, 0, -1)]
 t0 = int(out[order[0], 0, 0])
