@@ -183,6 +183,9 @@ const char* rg_version(void);
 
 /* ---- stepping */
 int rg_seed(rg_batch* b, const uint64_t* seed_lo, const uint64_t* seed_hi /* nullable */);
+/* Seeds only the first `count` envs (arrays of `count` entries); the others keep the seed they have:
+ * ThreadConductor::seed zips workers with seeds (python/src/thread_impls.rs:45-50). */
+int rg_seed_first(rg_batch* b, const uint64_t* seed_lo, const uint64_t* seed_hi /* nullable */, int64_t count);
 int rg_reset(rg_batch* b);
 int rg_step(rg_batch* b, const uint8_t* actions_dev, int auto_reset);
 int rg_step_host(rg_batch* b, const uint8_t* actions_host, int auto_reset, rg_host_obs* out);
@@ -201,6 +204,17 @@ int rg_trace(rg_batch* b, uint64_t* out, int64_t* steps_launched);
 int rg_sync(rg_batch* b);          /* waits for the stream and raises per-env errors like the reference */
 int rg_views_get(rg_batch* b, rg_views* out);
 int rg_fetch(rg_batch* b, rg_host_obs* out);
+/* The states' own terminal flags, out_host u8 [N] (ParallelGameState::states -> Instruction::State,
+ * python/src/thread_impls.rs:51-60,131): after an auto-reset step `done` is 1 - the conductor flags the copy it
+ * returns (thread_impls.rs:69-79) - while the env's state, the fresh game, is not terminal. */
+int rg_fetch_terminal(rg_batch* b, uint8_t* out_host);
+/* What happens to an env that reaches a state in which the reference panics (the reference loses
+ * the worker thread and with it the whole conductor, python/src/thread_impls.rs:111-135):
+ *   0 sticky (default)  the env is frozen; every later step reports RG_ERR_PANIC for it
+ *   1 terminal          on auto-reset steps the step that hits the state reports done = 1 together with
+ *                       RG_ERR_PANIC once, and the env goes on with a fresh episode (its next seed)
+ * Also settable at creation through the environment variable RG_PANIC_POLICY=sticky|terminal. */
+int rg_set_panic_policy(rg_batch* b, int policy);
 /* ---- trainer-facing step: everything a policy loop needs from one call, all on the device and on the
  * batch's stream (what ParallelRogueEnv.step + StairRewardParallel + ImageSetting.expand per state do in
  * Python: python/rogue_gym/envs/parallel.py:44-66, wrappers.py:44-64, rogue_env.py:84-98).

@@ -869,6 +869,9 @@ struct Env {
   Status status;
   uint32_t message = 0;
   bool is_terminal = false;
+  // what the last step RETURNED: ThreadConductor::step flags the copy it returns after an auto-reset
+  // (thread_impls.rs:69-79); the worker's own state (is_terminal above, Instruction::State) is the fresh game's
+  bool returned_terminal = false;
   int64_t steps = 0;
   int error = 0;
 
@@ -1491,20 +1494,21 @@ void orc_set_seed(void* env, uint64_t lo, uint64_t hi) {
 int orc_reset(void* env) {
   Env* e = (Env*)env;
   e->error = 0;
+  e->returned_terminal = false;
   return guarded(e, [&] { e->reset(); });
 }
 int orc_react(void* env, uint8_t key) {
   Env* e = (Env*)env;
-  return guarded(e, [&] { e->react(key); });
+  int rc = guarded(e, [&] { e->react(key); });
+  if (rc == ORC_OK) e->returned_terminal = e->is_terminal;
+  return rc;
 }
 int orc_step_auto(void* env, uint8_t key) {
   Env* e = (Env*)env;
   int rc = guarded(e, [&] { e->react(key); });
   if (rc != ORC_OK) return rc;
-  if (e->is_terminal) {
-    rc = guarded(e, [&] { e->reset(); });
-    e->is_terminal = true;
-  }
+  e->returned_terminal = e->is_terminal;
+  if (e->is_terminal) rc = guarded(e, [&] { e->reset(); });  // the fresh state itself is not terminal
   return rc;
 }
 const char* orc_last_error(void* env) { return ((Env*)env)->last_error.c_str(); }
@@ -1516,7 +1520,7 @@ void orc_get_obs(void* env, uint8_t* screen, uint8_t* history, uint32_t* status1
   if (history) memcpy(history, e->history.data(), e->history.size());
   if (status10) e->status.to_vec(status10);
   if (message) *message = e->message;
-  if (is_terminal) *is_terminal = e->is_terminal;
+  if (is_terminal) *is_terminal = e->returned_terminal;
 }
 
 void orc_get_scalars(void* env, orc_scalars* o) {

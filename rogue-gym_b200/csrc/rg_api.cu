@@ -376,6 +376,7 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
   RG_TRY(cudaMemsetAsync(d.slow_count, 0, 32, b->stream));
   d.fast = 1;
   if (const char* e = getenv("RG_FAST")) d.fast = e[0] != '0';
+  if (const char* e = getenv("RG_PANIC_POLICY")) d.panic_policy = (e[0] == 't' || e[0] == '1') ? 1 : 0;
   d.branches = 1;
   if (const char* e = getenv("RG_BRANCHES")) d.branches = e[0] != '0';
   if (const char* e = getenv("RG_MON_WARPS")) d.mon_warps = std::max(32, atoi(e));
@@ -417,7 +418,7 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
     }
     RG_TRY(cudaMemcpyAsync(b->d_u64, lo.data(), N * 8, cudaMemcpyHostToDevice, b->stream));
     RG_TRY(cudaMemcpyAsync(b->d_u64 + N, hi.data(), N * 8, cudaMemcpyHostToDevice, b->stream));
-    RG_TRY(rg::launch_seed(d, b->d_u64, b->d_u64 + N, seeded ? 1 : 0, b->stream));
+    RG_TRY(rg::launch_seed(d, b->d_u64, b->d_u64 + N, seeded ? 1 : 0, (int64_t)N, b->stream));
     RG_TRY(cudaStreamSynchronize(b->stream));
   }
   // GameStateImpl::new builds the game and takes the first PlayerState (state_impls.rs:20-37)
@@ -588,20 +589,26 @@ void rg_destroy(rg_batch* b) {
   delete b;
 }
 
-int rg_seed(rg_batch* b, const uint64_t* seed_lo, const uint64_t* seed_hi) {
+int rg_seed_first(rg_batch* b, const uint64_t* seed_lo, const uint64_t* seed_hi, int64_t count) {
   if (!b || !seed_lo) return set_err(b, RG_ERR_ARG, "rg_seed: null argument");
-  const size_t N = (size_t)b->n;
+  if (count < 0 || count > b->n) return set_err(b, RG_ERR_ARG, "rg_seed_first: count out of range");
+  if (count == 0) return RG_OK;
+  const size_t N = (size_t)b->n, K = (size_t)count;
   RG_CUDA(b, cudaSetDevice(b->device));
   {
     int rc = invalidate_prefetched(b);
     if (rc != RG_OK) return rc;
   }
-  RG_CUDA(b, cudaMemcpyAsync(b->d_u64, seed_lo, N * 8, cudaMemcpyHostToDevice, b->stream));
-  if (seed_hi) RG_CUDA(b, cudaMemcpyAsync(b->d_u64 + N, seed_hi, N * 8, cudaMemcpyHostToDevice, b->stream));
-  RG_CUDA(b, rg::launch_seed(b->d, b->d_u64, seed_hi ? b->d_u64 + N : nullptr, 1, b->stream));
+  RG_CUDA(b, cudaMemcpyAsync(b->d_u64, seed_lo, K * 8, cudaMemcpyHostToDevice, b->stream));
+  if (seed_hi) RG_CUDA(b, cudaMemcpyAsync(b->d_u64 + N, seed_hi, K * 8, cudaMemcpyHostToDevice, b->stream));
+  RG_CUDA(b, rg::launch_seed(b->d, b->d_u64, seed_hi ? b->d_u64 + N : nullptr, 1, count, b->stream));
   b->launches += 1;
   RG_CUDA(b, cudaStreamSynchronize(b->stream));  // the host arrays may be pageable
   return RG_OK;
+}
+
+int rg_seed(rg_batch* b, const uint64_t* seed_lo, const uint64_t* seed_hi) {
+  return rg_seed_first(b, seed_lo, seed_hi, b ? b->n : 0);
 }
 
 int rg_reset(rg_batch* b) {
@@ -755,6 +762,31 @@ int rg_fetch(rg_batch* b, rg_host_obs* out) {
   int rc = copy_obs(b, out);
   if (rc != RG_OK) return rc;
   RG_CUDA(b, cudaStreamSynchronize(b->stream));
+  return RG_OK;
+}
+
+int rg_fetch_terminal(rg_batch* b, uint8_t* out_host) {
+  if (!b || !out_host) return set_err(b, RG_ERR_ARG, "rg_fetch_terminal: null argument");
+  RG_CUDA(b, cudaSetDevice(b->device));
+  uint8_t* tmp = reinterpret_cast<uint8_t*>(b->d_u64);  // [2N] u64 scratch
+  RG_CUDA(b, rg::launch_state_terminal(b->d, tmp, b->stream));
+  b->launches += 1;
+  RG_CUDA(b, cudaMemcpyAsync(out_host, tmp, (size_t)b->n, cudaMemcpyDeviceToHost, b->stream));
+  RG_CUDA(b, cudaStreamSynchronize(b->stream));
+  return RG_OK;
+}
+
+int rg_set_panic_policy(rg_batch* b, int policy) {
+  if (!b || (policy != 0 && policy != 1)) return set_err(b, RG_ERR_ARG, "rg_set_panic_policy: policy must be 0 (sticky) or 1 (terminal)");
+  if (b->d.panic_policy == policy) return RG_OK;
+  RG_CUDA(b, cudaSetDevice(b->device));
+  RG_CUDA(b, cudaStreamSynchronize(b->stream));
+  b->d.panic_policy = policy;
+  for (int i = 0; i < 2; ++i) {  // the captured step graphs hold a copy of the batch descriptor: capture again
+    if (b->graph[i]) cudaGraphExecDestroy(b->graph[i]);
+    if (b->graph_m[i]) cudaGraphExecDestroy(b->graph_m[i]);
+    b->graph[i] = b->graph_m[i] = nullptr;
+  }
   return RG_OK;
 }
 

@@ -167,10 +167,12 @@ RG_DEV void write_back(const DevBatch& b, Ctx& c, int64_t env, bool with_s, bool
 RG_DEV void close_env(const DevBatch& b, Ctx& c, int64_t env) {
   write_back(b, c, env, c.s_dirty != 0, c.a_dirty != 0, b.st, b.surface, b.attr);
 }
-RG_DEV void emit_obs(const DevBatch& b, Ctx& c, int64_t env, int32_t reward, uint8_t err) {
+// `done` is what the step RETURNS: after an auto-reset the conductor flags the copy it hands back while the
+// worker's own state - the fresh game - is not terminal (thread_impls.rs:69-79); -1 = the state's own flag
+RG_DEV void emit_obs(const DevBatch& b, Ctx& c, int64_t env, int32_t reward, uint8_t err, int done = -1) {
   if (c.lane < 10) b.status[env * 10 + c.lane] = c.st->status[c.lane];
   if (c.lane == 10) b.reward[env] = reward;
-  if (c.lane == 11) b.done[env] = c.st->is_terminal;
+  if (c.lane == 11) b.done[env] = done < 0 ? c.st->is_terminal : (uint8_t)done;
   if (c.lane == 12) b.message[env] = c.st->message;
   if (c.lane == 13) {
     b.error[env] = err;
@@ -349,14 +351,24 @@ RG_DEV void finish_env(const DevBatch& b, Ctx& c, int64_t env, int auto_reset, i
   EnvState* st = c.st;
   const uint32_t gold_before = st->f_gold_before;
   uint8_t err = 0;
-  if (c.panic) {
+  // Panic policy. A state in which the reference panics kills that env's worker thread and with it the whole
+  // conductor (thread_impls.rs:111-135). "sticky" (default): the env is frozen and reports RG_ERR_PANIC on every
+  // step. "terminal" (rg_set_panic_policy / RG_PANIC_POLICY=terminal, auto-reset steps only): the step that hits
+  // the state reports done = 1 with error RG_ERR_PANIC once and the env goes on with a fresh episode.
+  const bool revive = c.panic && b.panic_policy == 1 && auto_reset;
+  if (c.panic && !revive) {
     st->error = RG_ERR_PANIC;
     err = RG_ERR_PANIC;
   } else {
-    st->message = c.msg;
-    if (c.status_upd) refresh_status(c);
-    st->steps += 1;
-    st->is_terminal = (c.dead || (int64_t)st->steps >= b.max_steps) ? 1 : 0;
+    if (revive) {
+      st->is_terminal = 1;
+      err = RG_ERR_PANIC;
+    } else {
+      st->message = c.msg;
+      if (c.status_upd) refresh_status(c);
+      st->steps += 1;
+      st->is_terminal = (c.dead || (int64_t)st->steps >= b.max_steps) ? 1 : 0;
+    }
     if (st->is_terminal && auto_reset) {
       // the game for episode e+1 lives in ring slot (e+1) % SP_DEPTH
       const int64_t sp = env * SP_DEPTH + (int64_t)((st->episode + 1) % SP_DEPTH);
@@ -375,10 +387,9 @@ RG_DEV void finish_env(const DevBatch& b, Ctx& c, int64_t env, int auto_reset, i
         // The next episode of this env was generated ahead of time (k_prefetch): move it in.
         count_event(b, c, RGS_SWAP_IN);
         swap_in_prefetched(b, c, env, sp);
-        const uint8_t perr = st->error;
-        st->is_terminal = 1;
+        const uint8_t perr = st->error;  // the fresh game's own (generation) panic, if any
         const int32_t d0 = (int32_t)st->status[1] - (int32_t)gold_before;
-        emit_obs(b, c, env, d0 > 0 ? d0 : 0, perr);
+        emit_obs(b, c, env, d0 > 0 ? d0 : 0, err ? err : perr, 1);
         maybe_request_spec(b, c, env);
         store_state(b, c, env);
         __threadfence();
@@ -392,7 +403,10 @@ RG_DEV void finish_env(const DevBatch& b, Ctx& c, int64_t env, int auto_reset, i
       // build of the same episode that is still under way must not be published afterwards
       if (b.prefetch && c.lane == 0) *reinterpret_cast<volatile uint32_t*>(b.sp_cancel + sp) = st->episode + 1;
       request_refill(b, c, env);
-      if (c.lane == 0) b.reward[env] = (int32_t)gold_before;
+      if (c.lane == 0) {  // hand-over to the reset pass
+        b.reward[env] = (int32_t)gold_before;
+        b.error[env] = err;
+      }
       store_state(b, c, env);
       defer(b, c, env, DEFER_RESET, parity);
       return;
@@ -443,7 +457,6 @@ RG_DEV uint32_t sel4(const uint32_t (&v)[4], int r) { return r == 0 ? v[0] : r =
 // the position decides - the <= 4 rows of both planes around the move, the visited-map byte, the sector table
 // entries. Only the rare reads (a room record, the displayed gold) come later.
 RG_DEV int fast_env(const DevBatch& b, int64_t env, uint8_t key, int auto_reset) {
-  (void)auto_reset;
   EnvState* const stp = b.st + env;
   const uint4* hot = reinterpret_cast<const uint4*>(stp);
   int d;
@@ -472,7 +485,7 @@ RG_DEV int fast_env(const DevBatch& b, int64_t env, uint8_t key, int auto_reset)
     else if (act < 0) early = RG_ERR_INVALID_INPUT;
     else if (ui_dead) early = RG_ERR_IGNORED_INPUT;
     if (early >= 0) {
-      if (!b.fast) return CL_SLOW;
+      if (!b.fast || (early == RG_ERR_PANIC && b.panic_policy == 1 && auto_reset)) return CL_SLOW;
       b.reward[env] = 0;
       b.done[env] = (uint8_t)is_terminal;
       b.message[env] = h0.w;
@@ -774,6 +787,14 @@ RG_DEV void player_env(const DevBatch& b, Stager& sg, unsigned char* base, int64
   // what is left to do for this env: 1 report `err` only, 2 the normal path
   int todo = 1;
   uint8_t err = 0;
+  if (st->error == RG_ERR_PANIC && b.panic_policy == 1 && auto_reset) {
+    // a game that was born in a panic state (or froze before the policy was switched): ends now, a fresh one follows
+    st->f_gold_before = st->status[1];
+    st->error = 0;
+    c.panic = 1;
+    finish_env(b, c, env, auto_reset, parity);
+    return;
+  }
   if (st->error == RG_ERR_PANIC || st->error == RG_ERR_SETTING) err = st->error;  // the reference's worker is gone
   else if ((int64_t)st->steps > b.max_steps) err = 0;                           // state_impls.rs:52-54
   else if (act < 0) err = RG_ERR_INVALID_INPUT;  // ErrorKind::InvalidInput: nothing changes (core/src/lib.rs:322-327)
@@ -858,53 +879,30 @@ k_step_monsters(DevBatch b, int auto_reset, int which) {
 // The whole step as one piece (with the floor generator), for the envs on the full-path list:
 // descents, MoveUntil, and the reset half of a terminal step.
 RG_DEV void step_env_full(const DevBatch& b, Ctx& c, int64_t env, const uint8_t* __restrict__ actions, int auto_reset,
-                          bool reset_only) {
+                          bool reset_only, int parity) {
   EnvState* st = c.st;
-  if (reset_only) {  // second half of a terminal step: finish_env left gold_before in reward[]
+  if (reset_only) {  // second half of a terminal step: finish_env left gold_before in reward[] and its error in error[]
     const uint32_t gold_before = (uint32_t)b.reward[env];
+    uint8_t err = b.error[env];
     reset_env<false>(c);
-    uint8_t err = 0;
     if (c.panic) {
       st->error = RG_ERR_PANIC;
-      err = RG_ERR_PANIC;
+      if (!err) err = RG_ERR_PANIC;
     }
-    st->is_terminal = 1;
     compose(c);
     const int32_t diff = (int32_t)st->status[1] - (int32_t)gold_before;
-    emit_obs(b, c, env, diff > 0 ? diff : 0, err);
+    emit_obs(b, c, env, diff > 0 ? diff : 0, err, 1);
     maybe_request_spec(b, c, env);
     close_env(b, c, env);
     return;
   }
-  // the player kernel has already checked the early-outs for this env
+  // k_step_scan has already checked the early-outs for this env; the step ends like every other one (finish_env:
+  // a terminal step takes the prefetched game or goes to the reset pass, which runs after this kernel has joined)
   int d;
   const int act = map_key(actions[env], d);
-  const uint32_t gold_before = st->status[1];
+  st->f_gold_before = st->status[1];
   process_action<false>(c, act, d);
-  uint8_t err = 0;
-  if (c.panic) {
-    st->error = RG_ERR_PANIC;
-    err = RG_ERR_PANIC;
-  } else {
-    st->message = c.msg;
-    if (c.status_upd) refresh_status(c);
-    st->steps += 1;
-    st->is_terminal = (c.dead || (int64_t)st->steps >= b.max_steps) ? 1 : 0;
-    if (st->is_terminal && auto_reset) {
-      reset_env<false>(c);
-      if (c.panic) {
-        st->error = RG_ERR_PANIC;
-        err = RG_ERR_PANIC;
-      }
-      st->is_terminal = 1;
-      c.redraw = 1;
-    }
-    if (c.redraw) compose(c);
-  }
-  const int32_t diff = (int32_t)st->status[1] - (int32_t)gold_before;
-  emit_obs(b, c, env, diff > 0 ? diff : 0, err);
-  maybe_request_spec(b, c, env);
-  close_env(b, c, env);
+  finish_env(b, c, env, auto_reset, parity);
 }
 
 // End of a step: advances the step counter and, on the steps that kick a background pass, fixes the
@@ -948,7 +946,7 @@ __global__ void __launch_bounds__(GEN_WPB * 32) k_step_gen(DevBatch b, const uin
     const int64_t env = (int64_t)(item & 0x7FFFFFFFu);
     Ctx c;
     fill_ctx(b, c, sg, base, env, (item & DEFER_RESET) ? PL_NONE : PL_BOTH);
-    step_env_full(b, c, env, actions, auto_reset, (item & DEFER_RESET) != 0);
+    step_env_full(b, c, env, actions, auto_reset, (item & DEFER_RESET) != 0, parity);
     __syncwarp();
   }
   if (finalize) {
@@ -1466,10 +1464,16 @@ __global__ void k_export_rooms(DevBatch b, int16_t* __restrict__ out) {
   o[7] = st->py;
 }
 
-// Instruction::Seed for every env (python/src/thread_impls.rs:125-128): stored, used by the next reset
-__global__ void k_seed(DevBatch b, const uint64_t* __restrict__ lo, const uint64_t* __restrict__ hi, int seeded) {
+// the state's own terminal flag (Instruction::State, thread_impls.rs:131), as opposed to done[] = what the last step returned
+__global__ void k_state_terminal(DevBatch b, uint8_t* __restrict__ out) {
   const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (env >= b.n) return;
+  if (env < b.n) out[env] = b.st[env].is_terminal;
+}
+
+// Instruction::Seed for every env (python/src/thread_impls.rs:125-128): stored, used by the next reset
+__global__ void k_seed(DevBatch b, const uint64_t* __restrict__ lo, const uint64_t* __restrict__ hi, int seeded, int64_t count) {
+  const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= count) return;
   EnvState* st = b.st + env;
   const uint64_t l = lo[env], h = hi ? hi[env] : 0ull;
   st->seed[0] = (uint32_t)l;
@@ -1724,12 +1728,16 @@ cudaError_t launch_train_reward(const DevBatch& b, float stair_reward, int32_t* 
   k_train_reward<<<(unsigned)((b.n + 255) / 256), 256, 0, s>>>(b, stair_reward, level_seen, reward_out);
   return cudaGetLastError();
 }
-cudaError_t launch_seed(const DevBatch& b, const uint64_t* lo, const uint64_t* hi, int seeded, cudaStream_t s) {
-  k_seed<<<(unsigned)((b.n + 127) / 128), 128, 0, s>>>(b, lo, hi, seeded);
+cudaError_t launch_seed(const DevBatch& b, const uint64_t* lo, const uint64_t* hi, int seeded, int64_t count, cudaStream_t s) {
+  k_seed<<<(unsigned)((count + 127) / 128), 128, 0, s>>>(b, lo, hi, seeded, count);
   return cudaGetLastError();
 }
 cudaError_t launch_unpack_hist(const DevBatch& b, uint8_t* out, cudaStream_t s) {
   k_unpack_hist<<<(unsigned)b.n, 128, 0, s>>>(b, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_state_terminal(const DevBatch& b, uint8_t* out, cudaStream_t s) {
+  k_state_terminal<<<(unsigned)((b.n + 255) / 256), 256, 0, s>>>(b, out);
   return cudaGetLastError();
 }
 cudaError_t launch_export_rooms(const DevBatch& b, int16_t* rooms, cudaStream_t s) {

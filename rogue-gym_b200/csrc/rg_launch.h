@@ -52,8 +52,9 @@ cudaError_t launch_mirror(const DevBatch& b, const MirrorArgs& m, int sm_count, 
 cudaError_t launch_keys_from_index(const DevBatch& b, const void* idx_dev, int index_bytes, uint8_t* keys_dev, cudaStream_t s);
 cudaError_t launch_train_reward(const DevBatch& b, float stair_reward, int32_t* level_seen_dev, float* reward_out_dev,
                                 cudaStream_t s);
-cudaError_t launch_seed(const DevBatch& b, const uint64_t* lo_dev, const uint64_t* hi_dev, int seeded, cudaStream_t s);
+cudaError_t launch_seed(const DevBatch& b, const uint64_t* lo_dev, const uint64_t* hi_dev, int seeded, int64_t count, cudaStream_t s);
 cudaError_t launch_unpack_hist(const DevBatch& b, uint8_t* out_dev, cudaStream_t s);
 cudaError_t launch_state_hash(const DevBatch& b, uint64_t* out_dev, cudaStream_t s);
+cudaError_t launch_state_terminal(const DevBatch& b, uint8_t* out_dev, cudaStream_t s);
 cudaError_t launch_export_rooms(const DevBatch& b, int16_t* rooms_dev, cudaStream_t s);
 }  // namespace rg

@@ -97,6 +97,7 @@ SYMBOLS = {
     "rg_last_error": (C.c_char_p, [_vp]),
     "rg_version": (C.c_char_p, []),
     "rg_seed": (_i, [_vp, _vp, _vp]),
+    "rg_seed_first": (_i, [_vp, _vp, _vp, _i64]),
     "rg_reset": (_i, [_vp]),
     "rg_step": (_i, [_vp, _vp, _i]),
     "rg_step_host": (_i, [_vp, _vp, _i, C.POINTER(HostObs)]),
@@ -106,6 +107,8 @@ SYMBOLS = {
     "rg_trace": (_i, [_vp, _vp, _vp]),
     "rg_views_get": (_i, [_vp, C.POINTER(Views)]),
     "rg_fetch": (_i, [_vp, C.POINTER(HostObs)]),
+    "rg_fetch_terminal": (_i, [_vp, _vp]),
+    "rg_set_panic_policy": (_i, [_vp, _i]),
     "rg_step_train": (_i, [_vp, _vp, _i, _i, _u32, _i, _vp, _vp, C.c_float]),
     "rg_train_reset": (_i, [_vp]),
     "rg_mirror_get": (_i, [_vp, C.POINTER(HostObs), C.POINTER(_vp)]),

@@ -115,7 +115,7 @@ class _Batch:
         self._alive()
         lo = np.array([s & 0xFFFFFFFFFFFFFFFF for s in seeds], np.uint64)
         hi = np.array([(s >> 64) & 0xFFFFFFFFFFFFFFFF for s in seeds], np.uint64)
-        check(self.L.rg_seed(self.h, lo.ctypes.data, hi.ctypes.data), self.h)
+        check(self.L.rg_seed_first(self.h, lo.ctypes.data, hi.ctypes.data, len(seeds)), self.h)
 
     def reset(self):
         self._alive()
@@ -180,9 +180,20 @@ class _Batch:
         bits = np.unpackbits(m["history_bits"], axis=1, bitorder="little")[:, :self.C]
         return bits.reshape(self.n, self.H, self.W)
 
-    def player_state(self, i):
+    def player_state(self, i, terminal=None):
+        """terminal: None = what the last step returned (`done`); else the state's own flag (rg_fetch_terminal)."""
         return PlayerState(self, self.screen[i].copy(), self.history[i].copy(), self.status[i].copy(),
-                           int(self.message[i]), bool(self.done[i]))
+                           int(self.message[i]), bool(self.done[i] if terminal is None else terminal[i]))
+
+    def state_terminal(self):
+        self._alive()
+        out = np.zeros(self.n, np.uint8)
+        check(self.L.rg_fetch_terminal(self.h, out.ctypes.data), self.h)
+        return out
+
+    def set_panic_policy(self, policy):
+        self._alive()
+        check(self.L.rg_set_panic_policy(self.h, {"sticky": 0, "terminal": 1}.get(policy, policy)), self.h)
 
 
 class PlayerState:
@@ -357,15 +368,17 @@ class ParallelGameState:
         return int(self._batch.params.symbols)
 
     def seed(self, seed):
+        """ThreadConductor::seed zips the workers with the seeds (thread_impls.rs:45-50): with fewer seeds than
+        workers the remaining workers keep the seed they have, extra seeds are ignored."""
         seeds = [int(s) for s in seed]
-        n = self._batch.n
-        if len(seeds) < n:  # zip() in ThreadConductor::seed: extra workers keep their seed
-            raise RuntimeError("Error in rogue-gym: expected %d seeds" % n)
-        self._batch.seed(seeds[:n])
+        self._batch.seed(seeds[: self._batch.n])
 
     def states(self):
+        """Instruction::State (thread_impls.rs:51-60,131): every worker's own state - after an auto-reset step that
+        is the fresh game, which is not terminal (only the copy `step` returned was flagged)."""
         self._batch.fetch()
-        return [self._batch.player_state(i) for i in range(self._batch.n)]
+        term = self._batch.state_terminal()
+        return [self._batch.player_state(i, term) for i in range(self._batch.n)]
 
     def step(self, input):
         self._batch.step(np.asarray(list(input) if not isinstance(input, np.ndarray) else input, np.uint8), True)

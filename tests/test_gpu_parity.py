@@ -291,8 +291,16 @@ def test_parallel_semantics(gpu, oracle):
     out = pg.step([ord("h")] * n)
     assert all(s.is_terminal for s in out)
     assert all(s.dungeon == states[0].dungeon for s in out)
+    # only the copy that step() returned is flagged: the workers' own states are the fresh games
+    # (ThreadConductor::step flags `*res`, Instruction::State returns game_state.state(): thread_impls.rs:69-79,131)
     again = pg.states()
-    assert all(s.is_terminal for s in again)
+    assert not any(s.is_terminal for s in again) and all(s.dungeon == states[0].dungeon for s in again)
+    # fewer seeds than workers: zip() seeds the first ones, the others keep theirs (thread_impls.rs:45-50)
+    pg.seed([100, 101])
+    part = pg.reset()
+    assert part[0].dungeon == oracle.OracleEnv(dict(cfg, seed=100)).dungeon()
+    assert part[1].dungeon == oracle.OracleEnv(dict(cfg, seed=101)).dungeon()
+    assert all(s.dungeon == states[0].dungeon for s in part[2:])
     pg.seed(list(range(100, 100 + n)))
     fresh = pg.reset()
     for i, s in enumerate(fresh):
@@ -499,3 +507,48 @@ def test_shards_reproduce_the_single_batch(gpu):
     assert np.array_equal(whole.errors()[n // 2:], parts[1].errors())
     for sh in [whole] + parts:
         sh.close()
+
+
+# ---------------------------------------------------------------- panic policy
+@pytest.mark.gpu
+def test_panic_policy_terminal(gpu, oracle):
+    """A state in which the reference panics (monster at x = 0 probing x = -1, rogue/mod.rs:361) kills the reference's
+    worker and with it the conductor (thread_impls.rs:111-135). Default here ("sticky", covered by every other test):
+    the env is frozen. With the "terminal" policy the step that hits the state reports done = 1 and error 3 once and
+    the env continues with a fresh episode; every other env and every other step is untouched."""
+    n, steps, max_steps = 2048, 150, 400
+    seeds = np.arange(1, n + 1)  # sequential seeds: ~1.5 % of them reach the panic state within a few steps
+    pg, ob = make_pair(gpu, oracle, {}, n, seeds, max_steps=max_steps)
+    b = pg._batch
+    b.set_panic_policy("terminal")
+    ids = np.arange(n)
+    revived_total = 0
+    born_dead = ob.rc == 3  # the seeded game itself starts in the panic state: it ends at its first step
+    for t in range(steps):
+        keys = oracle.synthetic_actions(t, ids)
+        try:
+            b.step(keys, True)
+        except RuntimeError as e:
+            assert getattr(e, "code", None) == 3
+        ob.step(keys, True)
+        hit = (ob.rc == 3)
+        assert np.array_equal(b.error == 3, hit), "step %d: panic events differ: gpu %s oracle %s" % (
+            t, np.nonzero(b.error == 3)[0][:8], np.nonzero(hit)[0][:8])
+        assert (b.done[hit] == 1).all()
+        for i in np.nonzero(hit)[0]:  # what the policy does, on the oracle: a fresh episode of the same seed
+            try:
+                ob.envs[i].reset()
+            except oracle.OracleError:
+                born_dead[i] = True  # the seed's game panics while it is generated: it ends again at every step
+        ob.rc[hit] = 0
+        o = ob.obs()
+        o["done"][hit] = 1
+        bad = diff_obs(b, o, t, b.W, ~born_dead)
+        assert not bad, "\n".join(bad[:4])
+        revived_total += int((hit & ~born_dead).sum())
+    assert revived_total >= 10 and born_dead.sum() < n // 100
+    hashes = np.zeros(n, np.uint64)
+    from rogue_gym_python import _cabi
+    _cabi.check(b.L.rg_state_hash(b.h, hashes.ctypes.data), b.h)
+    assert np.array_equal(hashes[~born_dead], ob.hashes()[~born_dead])
+    pg.close()

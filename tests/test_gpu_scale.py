@@ -95,11 +95,12 @@ def test_full_size_past_the_mass_reset(gpu, cabi, oracle):
 
 
 @pytest.mark.parametrize("max_steps,n", [(2, 4096), (3, 65536)])
-def test_ring_pressure_hits_the_miss_paths(gpu, cabi, oracle, max_steps, n):
-    """Episodes of 2-3 steps drain every env's two-slot ring faster than it is refilled: finish_env's
-    miss path (synchronous reset in k_step_gen), the cancel marks and the stale-slot check all run.
-    Whatever path an episode's game comes from, it must be the game the oracle builds."""
+def test_ring_pressure_hits_the_miss_paths(gpu, cabi, oracle, max_steps, n, monkeypatch):
+    """Episodes of 2-3 steps with a background pass only every 8th step drain every env's two-slot ring faster
+    than it is refilled: finish_env's miss path (synchronous reset in k_step_gen), the cancel marks and the
+    stale-slot check all run. Whatever path an episode's game comes from, it must be the game the oracle builds."""
     import torch
+    monkeypatch.setenv("RG_PREFETCH_EVERY", "8")  # read by rg_create
     steps = 120 if n <= 4096 else 40
     seeds = (np.arange(n, dtype=np.uint64) * np.uint64(2654435761) + np.uint64(17)) % np.uint64(1 << 40)
     L, h = _raw_batch(cabi, {}, n, max_steps, seeds)
