@@ -316,6 +316,16 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    if world > 1:
+        # one process per GPU on one host: give every rank its own cores, so that eight host threads that each launch
+        # and wait once per step (the e2e leg) do not migrate onto each other
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+            per = max(1, len(cores) // max(1, local_world))
+            os.sched_setaffinity(0, cores[local_rank * per:(local_rank + 1) * per] or cores)
+        except (AttributeError, OSError):
+            pass
     dist = None
     if world > 1:
         import torch.distributed as dist

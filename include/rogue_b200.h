@@ -198,8 +198,10 @@ int rg_quiesce(rg_batch* b);
  * [7] env-steps finished by the thread-per-env kernel (k_step_fast). */
 int rg_stats(rg_batch* b, uint64_t* out8);
 /* Timeline of the last 512 steps (only when the batch was created with RG_TRACE=1 in the environment):
- * out[512][8][2] = first start / last end (globaltimer ns) of kernel k of step slot s; k = 0 player,
- * 1 monsters, 2 finish, 3 full-path, 4 synchronous resets, 5 background prefetch. Reading clears the slots. */
+ * out[512][12][2] = first start / last end (globaltimer ns) of kernel k of step slot s; k = 0 player kernel of the
+ * active-monster envs, 1 their monster kernel, 2 thread-per-env kernel, 3 full path, 4 synchronous resets, 5 background
+ * prefetch, 6 / 7 player / monster kernel of the thread kernel's leftovers, 8 / 9 host-mirror passes, 10 scan.
+ * Reading clears the slots. */
 int rg_trace(rg_batch* b, uint64_t* out, int64_t* steps_launched);
 int rg_sync(rg_batch* b);          /* waits for the stream and raises per-env errors like the reference */
 int rg_views_get(rg_batch* b, rg_views* out);
@@ -233,7 +235,8 @@ int rg_train_reset(rg_batch* b);
  * rg_mirror_get allocates (once) pinned host buffers that the device can write, owned by the batch and
  * valid until rg_destroy: out->screen [N][W*H], status, reward, done, message, error as in rg_host_obs;
  * out->history is NULL - the visited map is mirrored bit-packed, *history_bits [N][hist_stride] with
- * bit y*W+x of an env's row = visited (the layout of rg_views.history_bits).
+ * bit y*W+x of an env's row = visited (the layout of rg_views.history_bits), and only from the first call that
+ * passes a non-NULL history_bits on (it costs about a third of a step's PCIe writes).
  * rg_mirror_sync brings the mirror up to date with the device block: kernels compare the block with a
  * device-side shadow of what the host holds and store only the 16-byte pieces that changed, over PCIe,
  * into the mirror; it returns after the stream has drained, so the host may read at once.

@@ -64,7 +64,9 @@ struct rg_batch {
   uint64_t* d_u64 = nullptr;        // [2N] scratch: seeds / hashes
   int* d_out3 = nullptr;
   uint32_t* h_errflag = nullptr;    // pinned
-  uint8_t* h_actions = nullptr;     // pinned [N]: staging for rg_step_mirror's graph
+  uint8_t* h_actions = nullptr;     // pinned + mapped [N]: staging for rg_step_mirror (k_step_scan reads it over PCIe)
+  uint8_t* h_actions_dev = nullptr; // the same buffer as the device addresses it
+  uint32_t* m_ticket = nullptr;     // device: see MirrorArgs::ticket
   int32_t* d_level_seen = nullptr;  // [N] deepest level rg_step_train has seen per env (lazily allocated)
   uint8_t* h_error = nullptr;       // pinned [N]
   // host mirror (rg_mirror_get): pinned + mapped host block, its device alias, and the shadows
@@ -305,8 +307,8 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
     }
   }
   if (const char* tr = getenv("RG_TRACE"); tr && tr[0] == '1') {
-    RG_TRY(dev_alloc(b, &d.trace, 512 * 8 * 2));
-    std::vector<unsigned long long> init(512 * 8 * 2);
+    RG_TRY(dev_alloc(b, &d.trace, 512 * rg::TRACE_KERNELS * 2));
+    std::vector<unsigned long long> init(512 * rg::TRACE_KERNELS * 2);
     for (size_t i = 0; i < init.size(); ++i) init[i] = (i & 1) ? 0ull : ~0ull;
     RG_TRY(cudaMemcpy(d.trace, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
   }
@@ -355,7 +357,9 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
     RG_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     RG_TRY(cudaStreamCreateWithPriority(&b->side, cudaStreamNonBlocking, hi));
     RG_TRY(cudaStreamCreateWithPriority(&b->mon, cudaStreamNonBlocking, hi));
-    RG_TRY(cudaStreamCreateWithFlags(&b->mir, cudaStreamNonBlocking));
+    // the first mirror pass is a light kernel that has to START early (right after k_step_fast) to hide its PCIe
+    // writes behind the rest of the step: high priority, or its blocks queue behind the register-hungry warp kernels
+    RG_TRY(cudaStreamCreateWithPriority(&b->mir, cudaStreamNonBlocking, hi));
     RG_TRY(cudaEventCreateWithFlags(&b->ev_mir, cudaEventDisableTiming));
     RG_TRY(cudaEventCreateWithFlags(&b->ev_mon, cudaEventDisableTiming));
     RG_TRY(cudaEventCreateWithFlags(&b->ev_fast, cudaEventDisableTiming));
@@ -383,8 +387,9 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
   RG_TRY(dev_alloc(b, &b->d_actions, N));
   RG_TRY(dev_alloc(b, &b->d_u64, 2 * N));
   RG_TRY(dev_alloc(b, &b->d_out3, 4));
-  RG_TRY(cudaMallocHost(&b->h_errflag, sizeof(uint32_t)));
-  RG_TRY(cudaMallocHost(&b->h_actions, N));
+  RG_TRY(cudaHostAlloc(&b->h_errflag, sizeof(uint32_t), cudaHostAllocMapped));
+  RG_TRY(cudaHostAlloc(&b->h_actions, N, cudaHostAllocMapped));
+  RG_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&b->h_actions_dev), b->h_actions, 0));
   RG_TRY(cudaMallocHost(&b->h_error, N));
   RG_TRY(cudaMemsetAsync(d.st, 0, N * sizeof(EnvState), b->stream));
   RG_TRY(cudaMemsetAsync(d.screen, ' ', N * d.CP, b->stream));
@@ -411,10 +416,13 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
       std::random_device rd;  // rng::gen_seed (core/src/rng.rs:37-45): thread_rng
       for (size_t i = 0; i < N; ++i) lo[i] = ((uint64_t)rd() << 32) | rd();
     }
-    if (!seeded && P.has_seed_range) {
-      const uint64_t span = P.seed_range_hi - P.seed_range_lo;
-      if (P.seed_range_hi <= P.seed_range_lo) return fail(set_err(b, RG_ERR_SETTING, "empty seed_range"));
-      for (size_t i = 0; i < N; ++i) lo[i] = P.seed_range_lo + lo[i] % span;
+    if (!seeded) {  // GameConfig::seed_range (core/src/lib.rs:157-165), every env from its own config
+      for (size_t i = 0; i < N; ++i) {
+        const rg_params& q = per_env ? (*per_env)[i] : P;
+        if (!q.has_seed_range) continue;
+        if (q.seed_range_hi <= q.seed_range_lo) return fail(set_err(b, RG_ERR_SETTING, "empty seed_range"));
+        lo[i] = q.seed_range_lo + lo[i] % (q.seed_range_hi - q.seed_range_lo);
+      }
     }
     RG_TRY(cudaMemcpyAsync(b->d_u64, lo.data(), N * 8, cudaMemcpyHostToDevice, b->stream));
     RG_TRY(cudaMemcpyAsync(b->d_u64 + N, hi.data(), N * 8, cudaMemcpyHostToDevice, b->stream));
@@ -462,7 +470,10 @@ int kick_prefetch(rg_batch* b) {
   RG_CUDA(b, cudaEventRecord(b->ev_main, b->stream));
   RG_CUDA(b, cudaStreamWaitEvent(b->bg[i], b->ev_main, 0));
   RG_CUDA(b, rg::launch_prefetch(b->d, b->prefetch_warps, (int)(k % 8), b->bg[i]));
-  if (k >= 2) RG_CUDA(b, cudaStreamWaitEvent(b->stream, b->ev_bg[i], 0));  // pass k-2 (same stream, already queued before pass k)
+  if (k >= 2 && cudaEventQuery(b->ev_bg[i]) != cudaSuccess) {  // pass k-2 (same stream, already queued before pass k)
+    (void)cudaGetLastError();
+    RG_CUDA(b, cudaStreamWaitEvent(b->stream, b->ev_bg[i], 0));
+  }
   RG_CUDA(b, cudaEventRecord(b->ev_bg[i], b->bg[i]));
   b->launches += 1;
   b->prefetch_running = true;
@@ -479,7 +490,12 @@ int kick_spec(rg_batch* b, int slot) {
   RG_CUDA(b, cudaEventRecord(b->ev_step, b->stream));
   RG_CUDA(b, cudaStreamWaitEvent(b->spec[i], b->ev_step, 0));
   RG_CUDA(b, rg::launch_spec_build(b->d, slot, b->spec[i]));
-  if (k >= rg_batch::SPEC_STREAMS) RG_CUDA(b, cudaStreamWaitEvent(b->stream, b->ev_spec[i], 0));
+  // (a pass that old has finished long ago as a rule: ask the event on the host and queue a wait - one more operation
+  // for the stream to retire at the end of a synced step - only if it has not)
+  if (k >= rg_batch::SPEC_STREAMS && cudaEventQuery(b->ev_spec[i]) != cudaSuccess) {
+    (void)cudaGetLastError();  // cudaErrorNotReady is an answer, not a failure
+    RG_CUDA(b, cudaStreamWaitEvent(b->stream, b->ev_spec[i], 0));
+  }
   RG_CUDA(b, cudaEventRecord(b->ev_spec[i], b->spec[i]));
   b->launches += 1;
   return RG_OK;
@@ -640,19 +656,10 @@ int step_impl(rg_batch* b, const uint8_t* actions_dev, int auto_reset, bool with
     if (!graphs[auto_reset]) {
       cudaGraph_t g = nullptr;
       RG_CUDA(b, cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
-      cudaError_t le = cudaSuccess;
-      if (with_mirror) {
-        // the host-facing step is one graph launch: actions from the pinned staging buffer, the counter
-        // cleared, the step with its mirror passes, the counter and the error flag back to the host
-        le = cudaMemcpyAsync(b->d_actions, b->h_actions, (size_t)b->n, cudaMemcpyHostToDevice, b->stream);
-        if (le == cudaSuccess) le = cudaMemsetAsync(b->m_count, 0, 8, b->stream);
-      }
-      if (le == cudaSuccess) le = rg::launch_step(d, b->d_actions, auto_reset, b->step_streams(), mirror, b->sm_count);
-      if (with_mirror && le == cudaSuccess) {
-        le = cudaMemcpyAsync(b->h_count, b->m_count, 8, cudaMemcpyDeviceToHost, b->stream);
-        if (le == cudaSuccess)
-          le = cudaMemcpyAsync(b->h_errflag, b->d.errflag, sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream);
-      }
+      // the host-facing step is kernels only: the scan reads the keys straight from the pinned staging buffer (mapped),
+      // the last mirror pass writes the byte counter and the error flag into mapped host memory
+      cudaError_t le = rg::launch_step(d, with_mirror ? b->h_actions_dev : b->d_actions, b->d_actions, auto_reset,
+                                       b->step_streams(), mirror, b->sm_count);
       cudaError_t ce = cudaStreamEndCapture(b->stream, &g);
       if (le != cudaSuccess) return cuda_fail(b, le, "launch_step (capture)");
       if (ce != cudaSuccess) return cuda_fail(b, ce, "cudaStreamEndCapture");
@@ -661,15 +668,8 @@ int step_impl(rg_batch* b, const uint8_t* actions_dev, int auto_reset, bool with
     }
     RG_CUDA(b, cudaGraphLaunch(graphs[auto_reset], b->stream));
   } else {
-    if (with_mirror) {
-      RG_CUDA(b, cudaMemcpyAsync(b->d_actions, b->h_actions, (size_t)b->n, cudaMemcpyHostToDevice, b->stream));
-      RG_CUDA(b, cudaMemsetAsync(b->m_count, 0, 8, b->stream));
-    }
-    RG_CUDA(b, rg::launch_step(d, b->d_actions, auto_reset, b->step_streams(), mirror, b->sm_count));
-    if (with_mirror) {
-      RG_CUDA(b, cudaMemcpyAsync(b->h_count, b->m_count, 8, cudaMemcpyDeviceToHost, b->stream));
-      RG_CUDA(b, cudaMemcpyAsync(b->h_errflag, b->d.errflag, sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
-    }
+    RG_CUDA(b, rg::launch_step(d, with_mirror ? b->h_actions_dev : b->d_actions, b->d_actions, auto_reset, b->step_streams(),
+                               mirror, b->sm_count));
   }
   b->launches += 8 + (with_mirror ? 2 : 0);
   {
@@ -708,9 +708,9 @@ int rg_trace(rg_batch* b, uint64_t* out, int64_t* steps_launched) {
   RG_CUDA(b, cudaStreamSynchronize(b->stream));
   for (int i = 0; i < 2; ++i)
     if (b->bg[i]) RG_CUDA(b, cudaStreamSynchronize(b->bg[i]));
-  RG_CUDA(b, cudaMemcpy(out, b->d.trace, 512 * 8 * 2 * 8, cudaMemcpyDeviceToHost));
+  RG_CUDA(b, cudaMemcpy(out, b->d.trace, 512 * rg::TRACE_KERNELS * 2 * 8, cudaMemcpyDeviceToHost));
   {  // read-and-clear: the slots are min/max accumulators and wrap every 512 steps
-    std::vector<unsigned long long> init(512 * 8 * 2);
+    std::vector<unsigned long long> init(512 * rg::TRACE_KERNELS * 2);
     for (size_t i = 0; i < init.size(); ++i) init[i] = (i & 1) ? 0ull : ~0ull;
     RG_CUDA(b, cudaMemcpy(b->d.trace, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
   }
@@ -888,7 +888,9 @@ int rg_mirror_get(rg_batch* b, rg_host_obs* out, uint8_t** history_bits) {
       if ((e2 = dev_alloc(b, &b->ms_hist, N * d.HB)) != cudaSuccess) return e2;
       if ((e2 = dev_alloc(b, &b->ms_small, N * 16)) != cudaSuccess) return e2;
       if ((e2 = dev_alloc(b, &b->m_count, 1)) != cudaSuccess) return e2;
-      if (!b->h_count && (e2 = cudaMallocHost(&b->h_count, sizeof(uint64_t))) != cudaSuccess) return e2;
+      if (!b->h_count && (e2 = cudaHostAlloc(&b->h_count, sizeof(uint64_t), cudaHostAllocMapped)) != cudaSuccess) return e2;
+      if ((e2 = dev_alloc(b, &b->m_ticket, 1)) != cudaSuccess) return e2;
+      if ((e2 = cudaMemsetAsync(b->m_ticket, 0, 4, b->stream)) != cudaSuccess) return e2;
       if ((e2 = cudaMemsetAsync(b->ms_screen, 0, N * d.CP, b->stream)) != cudaSuccess) return e2;
       if ((e2 = cudaMemsetAsync(b->ms_hist, 0, N * d.HB, b->stream)) != cudaSuccess) return e2;
       if ((e2 = cudaMemsetAsync(b->ms_small, 0, N * 64, b->stream)) != cudaSuccess) return e2;
@@ -905,7 +907,28 @@ int rg_mirror_get(rg_batch* b, rg_host_obs* out, uint8_t** history_bits) {
     m.h_screen = b->m_dev.screen; m.h_hist = b->m_hist_dev; m.h_status = b->m_dev.status; m.h_reward = b->m_dev.reward;
     m.h_done = b->m_dev.done; m.h_message = b->m_dev.message; m.h_error = b->m_dev.error;
     m.s_screen = b->ms_screen; m.s_hist = b->ms_hist; m.s_small = b->ms_small; m.bytes = b->m_count;
+    m.ticket = b->m_ticket;
+    {
+      void *hb = nullptr, *he = nullptr;
+      RG_CUDA(b, cudaHostGetDevicePointer(&hb, b->h_count, 0));
+      RG_CUDA(b, cudaHostGetDevicePointer(&he, b->h_errflag, 0));
+      m.h_bytes = static_cast<unsigned long long*>(hb);
+      m.h_errflag = static_cast<uint32_t*>(he);
+    }
     int rc = rg_mirror_sync(b, nullptr);  // the mirror starts out current
+    if (rc != RG_OK && rc != RG_ERR_PANIC && rc != RG_ERR_INVALID_INPUT && rc != RG_ERR_IGNORED_INPUT) return rc;
+  }
+  if (history_bits && !b->margs.with_hist) {
+    // the visited map is mirrored only once somebody asks for it (a third of the small PCIe writes of a step):
+    // from now on it is; mark every row so that the next pass brings the host copy up to date
+    RG_CUDA(b, cudaStreamSynchronize(b->stream));
+    b->margs.with_hist = 1;
+    for (int i = 0; i < 2; ++i) {  // the captured graphs hold a copy of the mirror arguments
+      if (b->graph_m[i]) cudaGraphExecDestroy(b->graph_m[i]);
+      b->graph_m[i] = nullptr;
+    }
+    RG_CUDA(b, cudaMemsetAsync(b->d.scr_rows, 0xFF, (size_t)b->n * 8, b->stream));
+    int rc = rg_mirror_sync(b, nullptr);
     if (rc != RG_OK && rc != RG_ERR_PANIC && rc != RG_ERR_INVALID_INPUT && rc != RG_ERR_IGNORED_INPUT) return rc;
   }
   *out = b->m_obs;
@@ -917,10 +940,8 @@ int rg_mirror_sync(rg_batch* b, uint64_t* bytes_to_host) {
   if (!b) return set_err(b, RG_ERR_ARG, "rg_mirror_sync: null batch");
   if (!b->m_host) return set_err(b, RG_ERR_ARG, "rg_mirror_sync: call rg_mirror_get first");
   RG_CUDA(b, cudaSetDevice(b->device));
-  RG_CUDA(b, cudaMemsetAsync(b->m_count, 0, 8, b->stream));
-  RG_CUDA(b, rg::launch_mirror(b->d, b->margs, b->sm_count, b->stream));
+  RG_CUDA(b, rg::launch_mirror(b->d, b->margs, b->sm_count, b->stream));  // publishes the byte counter itself
   b->launches += 1;
-  RG_CUDA(b, cudaMemcpyAsync(b->h_count, b->m_count, 8, cudaMemcpyDeviceToHost, b->stream));
   int rc = rg_sync(b);  // drains the stream: the mirror is readable now
   if (bytes_to_host) *bytes_to_host = *b->h_count;
   return rc;

@@ -183,7 +183,7 @@ RG_DEV void emit_obs(const DevBatch& b, Ctx& c, int64_t env, int32_t reward, uin
 // Optional timeline (RG_TRACE=1): first start / last end of every kernel of a step over all its blocks,
 // read back with rg_trace.
 enum { TK_PLAYER = 0, TK_MONSTERS = 1, TK_FINISH = 2, TK_FULL = 3, TK_RESETS = 4, TK_PREFETCH = 5, TK_PLAYER_B = 6,
-       TK_MONSTERS_B = 7 };
+       TK_MONSTERS_B = 7, TK_MIRROR1 = 8, TK_MIRROR2 = 9, TK_SCAN = 10 };
 RG_DEV unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -195,7 +195,7 @@ struct TraceScope {
     slot = nullptr;
     // every block reports (tracing is a diagnostic mode): the last block to finish is what the next kernel waits for
     if (b.trace && threadIdx.x == 0) {
-      slot = b.trace + ((size_t)(kernel == TK_PREFETCH ? b.trace_step : (int)(*b.dstep % 512u)) * 8 + kernel) * 2;
+      slot = b.trace + ((size_t)(kernel == TK_PREFETCH ? b.trace_step : (int)(*b.dstep % 512u)) * TRACE_KERNELS + kernel) * 2;
       atomicMin(slot, gtime());
     }
   }
@@ -689,8 +689,9 @@ RG_DEV int fast_env(const DevBatch& b, int64_t env, uint8_t key, int auto_reset)
 // warp kernels whatever else happens - the full path (descents, MoveUntil) and the envs with an active monster
 // (player phase, then monster phase) - are listed at once, so that both chains start ~6 us into the step and run
 // beside k_step_fast instead of after it. Everything else is left to k_step_fast (full_path[] = FP_FAST so far).
-__global__ void __launch_bounds__(256) k_step_scan(DevBatch b, const uint8_t* __restrict__ actions) {
+__global__ void __launch_bounds__(256) k_step_scan(DevBatch b, const uint8_t* __restrict__ actions, uint8_t* __restrict__ actions_out) {
   const int parity = (int)(*b.dstep & 1u);
+  TraceScope trace(b, TK_SCAN);
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // next step's counters
     b.defer_count[parity ^ 1] = 0;
     b.reset_count[parity ^ 1] = 0;
@@ -711,7 +712,9 @@ __global__ void __launch_bounds__(256) k_step_scan(DevBatch b, const uint8_t* __
     const uint32_t mon_active = hot[4].x >> 16;
     const uint32_t ui_dead = (h0.y >> 8) & 0xFFu, serr = (h0.y >> 16) & 0xFFu;
     int d;
-    const int act = map_key(actions[env], d);
+    const uint8_t key = actions[env];
+    if (actions_out != actions) actions_out[env] = key;  // the host-facing step reads the keys from mapped host memory once
+    const int act = map_key(key, d);
     cls = CL_FAST;
     const bool early = serr == RG_ERR_PANIC || serr == RG_ERR_SETTING || (int64_t)h0.z > b.max_steps || act < 0 || ui_dead;
     if (!early) {
@@ -1508,8 +1511,13 @@ RG_DEV bool differs(const uint4& a, const uint4& b) { return ((a.x ^ b.x) | (a.y
 // `pass`: 0 every env; 1 only the envs whose step was finished by the player kernel (full_path[] == 0) -
 // this pass runs beside the monster, full-path and reset kernels, which own the other envs; 2 only those others.
 __global__ void __launch_bounds__(256) k_mirror(DevBatch b, MirrorArgs m, int pass, int64_t env_lo, int64_t env_hi) {
+  // (the second pass runs after the step counter has advanced: it reports into the slot of the step it belongs to)
+  DevBatch tb = b;
+  uint32_t prev_step = *b.dstep - (pass == 2 ? 1u : 0u);
+  tb.dstep = &prev_step;
+  TraceScope trace(tb, pass == 2 ? TK_MIRROR2 : TK_MIRROR1);
   const int lane = threadIdx.x & 31;
-  const int n_scr = b.CP / 16, n_hist = b.HB / 16;
+  const int n_scr = b.CP / 16, n_hist = m.with_hist ? b.HB / 16 : 0;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   uint32_t sent = 0;
   for (int64_t env = env_lo + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); env < env_hi; env += warps) {
@@ -1569,6 +1577,20 @@ __global__ void __launch_bounds__(256) k_mirror(DevBatch b, MirrorArgs m, int pa
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sent += __shfl_xor_sync(RG_FULL, sent, o);
   if (lane == 0 && sent) atomicAdd(m.bytes, (unsigned long long)sent);
+  if (pass != 1) {  // the pass that ends the call: the last block to finish hands the counters to the host
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(m.ticket, 1u) == gridDim.x - 1) {
+        __threadfence();
+        *m.h_bytes = *reinterpret_cast<volatile unsigned long long*>(m.bytes);
+        *m.h_errflag = *reinterpret_cast<volatile uint32_t*>(b.errflag);
+        *m.bytes = 0ull;
+        *m.ticket = 0u;
+        __threadfence_system();
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------- launchers
@@ -1615,7 +1637,7 @@ cudaError_t launch_reset(const DevBatch& b, cudaStream_t s) {
 // `side` beside the player and monster kernels, the synchronous-reset pass, the join, and the step counter. No
 // per-step arguments (the step parity lives on the device, the actions are read from a fixed buffer), so
 // the whole sequence is captured once into a CUDA graph and replayed with one launch per step.
-cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_reset, const StepStreams& q,
+cudaError_t launch_step(const DevBatch& b, const uint8_t* actions_src, uint8_t* actions, int auto_reset, const StepStreams& q,
                         const MirrorArgs* mirror, int sm_count) {
   cudaStream_t s = q.main;
   const size_t sm = block_smem(b);
@@ -1624,7 +1646,7 @@ cudaError_t launch_step(const DevBatch& b, const uint8_t* actions, int auto_rese
   const int pblocks = (int)std::min<int64_t>(b.player_blocks > 0 ? b.player_blocks : (int64_t)sm_count * RG_HOT_MIN_BLOCKS, b.n);
   const int mon_blocks = (int)std::min<int64_t>(b.mon_warps / WARPS_PER_BLOCK, (b.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
   cudaError_t e;
-  k_step_scan<<<(unsigned)((b.n + 255) / 256), 256, 0, s>>>(b, actions);
+  k_step_scan<<<(unsigned)((b.n + 255) / 256), 256, 0, s>>>(b, actions_src, actions);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if ((e = cudaEventRecord(q.ev_fork, s)) != cudaSuccess) return e;
   // branch 1, high-priority side stream: full-path steps (descents, MoveUntil) - a few long serial chains

@@ -20,6 +20,11 @@ struct MirrorArgs {
   uint8_t* s_hist;       // [N][HB]
   uint32_t* s_small;     // [N][16]: status[10], reward, message, done | error << 8, 3 spare
   unsigned long long* bytes;  // [1] bytes stored to the host since the counter was last cleared
+  // the pass that ends a host-facing step publishes its results itself (no copy-engine nodes in the step's graph):
+  unsigned long long* h_bytes;  // mapped host: bytes stored by the step
+  uint32_t* h_errflag;          // mapped host: OR of the errors raised
+  uint32_t* ticket;             // device: blocks of the publishing pass that have finished
+  int with_hist;         // 0 = the visited map is not mirrored (nobody asked for it: rg_mirror_get without history_bits)
 };
 
 // streams and events one env-step is enqueued on (all owned by the batch)
@@ -33,7 +38,9 @@ struct StepStreams {
 // one env-step = scan, then three branches side by side (full path | active-monster envs | thread-per-env kernel
 // and its leftovers), reset pass, end
 // `mirror` != nullptr adds the two host-mirror passes to the step (rg_step_mirror)
-cudaError_t launch_step(const DevBatch& b, const uint8_t* actions_dev, int auto_reset, const StepStreams& q,
+// actions_src: where k_step_scan reads the keys (device memory, or mapped host memory for the host-facing step);
+// it leaves them in actions_dev, which every later kernel reads
+cudaError_t launch_step(const DevBatch& b, const uint8_t* actions_src, uint8_t* actions_dev, int auto_reset, const StepStreams& q,
                         const MirrorArgs* mirror, int sm_count);
 // background generation of next-episode games into the sp_* buffers; serves window `slot` of refill_win
 cudaError_t launch_prefetch(const DevBatch& b, int warps, int slot, cudaStream_t s);

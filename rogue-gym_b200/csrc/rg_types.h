@@ -21,6 +21,7 @@ namespace rg {
 
 constexpr int MAX_ROOMS = RG_MAX_ROOMS;
 constexpr int NCACHE = RG_DIST_CACHE;
+constexpr int TRACE_KERNELS = 12;  // kernels per step slot of the RG_TRACE timeline
 constexpr int SP_DEPTH = 2;  // prefetched next-episode games kept per env
 
 // Surface codes follow the reference's declaration order (rogue/mod.rs:137-146).
@@ -172,7 +173,7 @@ struct DevBatch {
   uint32_t* sp_walk;      // [N][SP_DEPTH][H][WW]
   EnvState* sp_st;        // [N][SP_DEPTH]  (slot of episode e = e % SP_DEPTH)
   uint8_t* sp_state;      // [N][SP_DEPTH]
-  unsigned long long* trace;  // optional (RG_TRACE=1): [512 steps][8 kernels][2] first start / last end, globaltimer ns
+  unsigned long long* trace;  // optional (RG_TRACE=1): [512 steps][TRACE_KERNELS][2] first start / last end, globaltimer ns
   int32_t trace_step;         // slot of a background pass (step kernels use *dstep)
   uint32_t* dstep;            // [0] steps executed so far (low bit selects the work-list buffers), [1] auto-reset steps
   unsigned long long* stats;  // [8] RGS_* event counters since creation (observability)

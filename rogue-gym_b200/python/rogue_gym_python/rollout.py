@@ -79,10 +79,11 @@ class Shard:
         if rc not in (_cabi.RG_OK, _cabi.RG_ERR_PANIC):
             _cabi.check(rc, self.h)
 
-    def mirror(self):
-        """Host mirror of the observation block (rg_mirror_get): HostObs of pinned pointers."""
+    def mirror(self, with_history=False):
+        """Host mirror of the observation block (rg_mirror_get): HostObs of pinned pointers. The bit-packed visited
+        map is kept current only if asked for."""
         obs, hist = _cabi.HostObs(), C.c_void_p()
-        rc = self.L.rg_mirror_get(self.h, C.byref(obs), C.byref(hist))
+        rc = self.L.rg_mirror_get(self.h, C.byref(obs), C.byref(hist) if with_history else None)
         if rc not in (_cabi.RG_OK, _cabi.RG_ERR_PANIC):
             _cabi.check(rc, self.h)
         return obs, hist

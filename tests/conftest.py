@@ -9,6 +9,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 sys.path.insert(0, os.path.join(ROOT, "rogue-gym_b200", "python"))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from helpers import CONFIGS, DEFAULT, MINI, MINI_NOMON  # noqa: E402,F401  (shared constants live in helpers.py)
 
 
 def pytest_configure(config):
@@ -45,17 +47,3 @@ def gpu(cabi):
         pytest.skip("no CUDA device")
     from rogue_gym_python import _rogue_gym
     return _rogue_gym
-
-
-MINI = {"width": 32, "height": 16, "seed": 4,
-        "dungeon": {"style": "rogue", "room_num_x": 2, "room_num_y": 2, "min_room_size": {"x": 4, "y": 4}}}
-MINI_NOMON = dict(MINI, enemies={"enemies": []})
-DEFAULT = {}
-CONFIGS = {"default": DEFAULT, "mini": MINI, "mini_nomon": MINI_NOMON,
-           "default_clear": {"hide_dungeon": False, "enemies": {"enemies": []}},
-           "wide": {"width": 160, "height": 48},
-           "odd": {"width": 50, "height": 19, "dungeon": {"style": "rogue", "room_num_x": 2, "room_num_y": 2}},
-           "deep": {"dungeon": {"style": "rogue", "dark_level": 2, "maze_rate_inv": 2, "hidden_passage_rate_inv": 4,
-                                "locked_door_rate_inv": 2, "amulet_level": 1}},
-           "grid4": {"width": 128, "height": 40, "dungeon": {"style": "rogue", "room_num_x": 4, "room_num_y": 4,
-                                                           "max_empty_rooms": 6}}}

@@ -52,10 +52,23 @@ out = {
                    "dungeon": {"style": "rogue", "room_num_x": 2, "room_num_y": 2}},
         "from": [9, 9], "to": [28, 4], "expect": [10, 9],
     },
+    # The reference's only known answers WITH MONSTERS ENABLED (default config, seed 1): the screens after CMD_STR and
+    # after CMD_STR5. SURVEY.md 8c-3 filed them under "stale" together with SEED1_DUNGEON; they are not - the oracle and
+    # the GPU reproduce both screens cell for cell, including the monster 'S' next to the player. They pin: the enemy
+    # stream's gen_enemy draws on level 1 (which room gets which kind, where), MoveUntil through a dark room, the
+    # 9-neighbour visibility of a dark room, monster drawing (Dungeon::draw_enemy), the item stream's init draws.
+    "seed1_with_monsters": {
+        "cite": "python/tests/data.py:25-81 (CMD_STR, CMD_STR5, SEED1_DUNGEON2, SEED1_DUNGEON3), used by "
+                "python/tests/test_rogue_env.py:21-25 and test_parallel.py:27-40",
+        "config": {"seed": 1},
+        "cases": [{"keys": data.CMD_STR, "screen": data.SEED1_DUNGEON2},
+                  {"keys": data.CMD_STR5, "screen": data.SEED1_DUNGEON3}],
+    },
     "stale": {
-        "note": "SEED1_DUNGEON/2/3 + CMD_STR/CMD_STR5 are stale in the reference (21 rows vs 24; SURVEY §8c-3); "
-                "kept only as inputs",
-        "cmd_str": data.CMD_STR, "cmd_str5": data.CMD_STR5,
+        "note": "SEED1_DUNGEON (21 rows; the API returns 24, and the start room sits one row lower than in the live golden) "
+                "is stale in the reference itself (SURVEY 8c-3): test_rogue_env.py::test_screen and the test_parallel.py "
+                "cases that first compare with it cannot pass against the reference's own code",
+        "seed1_dungeon_rows": len(data.SEED1_DUNGEON),
     },
 }
 # A recorded episode the reference ships (RunTime::saved_inputs_as_json format, core/src/lib.rs:357-375):

@@ -1,7 +1,25 @@
 """Shared helpers of the GPU parity tests: canonical state dumps of both sides and diffs."""
 import ctypes as C
+import os
 
 import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# (shared constants are here, not in conftest.py: tests/golden/ref_tests has a conftest of its own, and `conftest` as a
+# module name resolves to whichever was imported last)
+MINI = {"width": 32, "height": 16, "seed": 4,
+        "dungeon": {"style": "rogue", "room_num_x": 2, "room_num_y": 2, "min_room_size": {"x": 4, "y": 4}}}
+MINI_NOMON = dict(MINI, enemies={"enemies": []})
+DEFAULT = {}
+CONFIGS = {"default": DEFAULT, "mini": MINI, "mini_nomon": MINI_NOMON,
+           "default_clear": {"hide_dungeon": False, "enemies": {"enemies": []}},
+           "wide": {"width": 160, "height": 48},
+           "odd": {"width": 50, "height": 19, "dungeon": {"style": "rogue", "room_num_x": 2, "room_num_y": 2}},
+           "deep": {"dungeon": {"style": "rogue", "dark_level": 2, "maze_rate_inv": 2, "hidden_passage_rate_inv": 4,
+                                "locked_door_rate_inv": 2, "amulet_level": 1}},
+           "grid4": {"width": 128, "height": 40, "dungeon": {"style": "rogue", "room_num_x": 4, "room_num_y": 4,
+                                                           "max_empty_rooms": 6}}}
+
 
 SCALAR_FIELDS = ("level", "px", "py", "hp", "hp_max", "exp", "plevel", "food_left", "quiet", "gold", "ui_dead", "steps",
                  "is_terminal", "message", "error", "n_monsters", "n_items", "n_cache", "status", "rng")

@@ -9,7 +9,7 @@ import subprocess
 
 import pytest
 
-from conftest import CONFIGS, ROOT
+from helpers import CONFIGS, ROOT
 
 
 def _declared_symbols():

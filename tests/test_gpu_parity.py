@@ -8,7 +8,7 @@ import json
 import numpy as np
 import pytest
 
-from conftest import CONFIGS
+from helpers import CONFIGS
 from helpers import KEYS19, diff_dumps, diff_obs, gpu_dump, oracle_dump
 
 pytestmark = pytest.mark.gpu
@@ -147,6 +147,17 @@ def test_reference_goldens_through_the_api(gpu, fixtures):
     assert list(img.shape) == fx["expect_image_shape"]
     assert img[17][0][0] == fx["expect_img_17_0_0"] and img[18][0][0] == fx["expect_img_18_0_0"]
     assert st.status_vec(0x1FF) == fx["expect_full_status_vec"]
+
+
+def test_reference_screens_with_monsters(gpu, fixtures):
+    """The reference's known answers with monsters enabled (python/tests/data.py SEED1_DUNGEON2 / SEED1_DUNGEON3, default
+    config, seed 1), through GameState.react like test_rogue_env.py::test_action drives them."""
+    fx = fixtures["seed1_with_monsters"]
+    for case in fx["cases"]:
+        g = gpu.GameState(1000, json.dumps(fx["config"]))
+        for k in case["keys"]:
+            g.react(ord(k))
+        assert g.prev().dungeon == case["screen"], case["keys"]
 
 
 def test_move_enemy_known_answer(gpu, fixtures):
@@ -388,7 +399,7 @@ def test_host_mirror_equals_full_copy(gpu, cfg_name):
     across auto-resets, stair descents and explicit resets, while moving far fewer bytes."""
     import json
 
-    from conftest import CONFIGS
+    from helpers import CONFIGS
     from helpers import KEYS19
     n, steps = 192, 150
     cfg = CONFIGS[cfg_name]

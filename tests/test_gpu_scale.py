@@ -18,7 +18,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import ROOT
+from helpers import ROOT
 from helpers import KEYS19, diff_dumps, diff_obs, gpu_dump, oracle_dump
 
 pytestmark = pytest.mark.gpu

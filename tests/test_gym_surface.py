@@ -130,16 +130,16 @@ def test_noaction_and_max_steps(envs, fixtures):  # test_rogue_env.py:31-41
     assert after.dungeon == before.dungeon and after.status == before.status
     assert reward == 0 and not done and info == {}
     env = envs.RogueEnv(seed=1, max_steps=5)
-    _, _, done, _ = env.step(fixtures["stale"]["cmd_str"])
+    _, _, done, _ = env.step(fixtures["seed1_with_monsters"]["cases"][0]["keys"])
     assert done
     with pytest.raises(ValueError):
         env.step(11)
 
 
 @pytest.mark.gpu
-def test_action_string_against_oracle(envs, fixtures, oracle):  # test_rogue_env.py:25-28 (vector is stale there)
+def test_action_string_against_oracle(envs, fixtures, oracle):  # test_rogue_env.py:21-25 (its golden, SEED1_DUNGEON2, is live)
     env = envs.RogueEnv(seed=1)
-    keys = fixtures["stale"]["cmd_str"]
+    keys = fixtures["seed1_with_monsters"]["cases"][0]["keys"]
     res, *_ = env.step(keys)
     o = oracle.OracleBatch({"seed": 1}, 1)
     o.reset()
@@ -147,7 +147,7 @@ def test_action_string_against_oracle(envs, fixtures, oracle):  # test_rogue_env
         o.step(np.array([ord(k)], np.uint8), False)
     W = 80
     want = [bytes(o.obs()["screen"][0][i:i + W]).decode("latin-1") for i in range(0, 24 * W, W)]
-    assert res.dungeon == want
+    assert res.dungeon == want == fixtures["seed1_with_monsters"]["cases"][0]["screen"]
 
 
 @pytest.mark.gpu
@@ -243,7 +243,7 @@ NUM_WORKERS = 8
 
 @pytest.mark.gpu
 def test_parallel_configs_seed_and_cycle(envs, fixtures):  # test_parallel.py:27-62
-    cmd, cmd5 = fixtures["stale"]["cmd_str"], fixtures["stale"]["cmd_str5"]
+    cmd, cmd5 = fixtures["seed1_with_monsters"]["cases"][0]["keys"], fixtures["seed1_with_monsters"]["cases"][1]["keys"]
     env = envs.ParallelRogueEnv(config_dicts=[{"seed": 1}] * NUM_WORKERS)
     first = env.states[0].dungeon
     assert all(s.dungeon == first for s in env.states)

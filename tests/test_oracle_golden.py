@@ -46,6 +46,19 @@ def test_stair_reward_env(oracle, fixtures):
     assert [int(st[i]) for i in (0, 2, 3, 4, 5, 6, 7, 8, 9)] == fx["expect_full_status_vec"]
 
 
+def test_seed1_screens_with_monsters(oracle, fixtures):
+    """python/tests/data.py SEED1_DUNGEON2 / SEED1_DUNGEON3: the reference's known answers with the default monster
+    table - the screens after 'kHhhKK' and after 'llljln' on seed 1, a snake ('S') beside the player."""
+    fx = fixtures["seed1_with_monsters"]
+    for case in fx["cases"]:
+        e = oracle.OracleEnv(fx["config"])
+        e.react_str(case["keys"])
+        assert e.dungeon() == case["screen"], case["keys"]
+        assert any("S" in row for row in case["screen"])
+        mons, _ = e.entities()
+        assert len(mons) >= 1
+
+
 def test_move_enemy_tie_break(oracle, fixtures):
     fx = fixtures["move_enemy"]
     env = oracle.OracleEnv(fx["config"])

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from conftest import ROOT  # noqa: F401  (sets sys.path)
+from helpers import ROOT  # noqa: F401  (sets sys.path)
 
 
 def _free_port():

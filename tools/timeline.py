@@ -11,16 +11,23 @@ n, steps = 65536, int(sys.argv[1]) if len(sys.argv) > 1 else 300
 sh = Shard("{}", 0, n)
 acts = np.stack([synthetic_actions(t, sh.env_ids) for t in range(steps)])
 d = torch.from_numpy(acts).cuda()
-out = np.zeros((512, 8, 2), np.uint64)
+out = np.zeros((512, 12, 2), np.uint64)
 launched = C.c_int64()
+MIRROR = os.environ.get("TL_MIRROR") == "1"  # time the host-facing step (rg_step_mirror, synced every step) instead
+if MIRROR:
+    hacts = torch.from_numpy(acts).pin_memory()
+    sh.mirror()
 for t in range(steps):
     if t == steps - 200:  # the slots wrap every 512 steps: clear them shortly before the end
         sh.sync()
         _cabi.check(sh.L.rg_trace(sh.h, out.ctypes.data, C.byref(launched)), sh.h)
-    sh.step_device(d.data_ptr() + t * n)
+    if MIRROR:
+        sh.step_mirror(hacts.data_ptr() + t * n)
+    else:
+        sh.step_device(d.data_ptr() + t * n)
 sh.sync()
 _cabi.check(sh.L.rg_trace(sh.h, out.ctypes.data, C.byref(launched)), sh.h)
-names = ["playerA", "monstersA", "fast", "full", "resets", "prefetch", "playerB", "monstersB"]
+names = ["playerA", "monstersA", "fast", "full", "resets", "prefetch", "playerB", "monstersB", "mirror1", "mirror2", "scan"]
 last = (launched.value - 1) % 512
 order = [(last - k) % 512 for k in range(12, 0, -1)]
 t0 = int(out[order[0], 0, 0])
