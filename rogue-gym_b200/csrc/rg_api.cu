@@ -359,7 +359,11 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
     RG_TRY(cudaStreamCreateWithPriority(&b->mon, cudaStreamNonBlocking, hi));
     // the first mirror pass is a light kernel that has to START early (right after k_step_fast) to hide its PCIe
     // writes behind the rest of the step: high priority, or its blocks queue behind the register-hungry warp kernels
-    RG_TRY(cudaStreamCreateWithPriority(&b->mir, cudaStreamNonBlocking, hi));
+    {
+      const char* mp = getenv("RG_MIRROR_PRIO");
+      RG_TRY(cudaStreamCreateWithPriority(&b->mir, cudaStreamNonBlocking, (mp && mp[0] == 'l') ? lo : hi));
+      if (const char* e = getenv("RG_MIRROR_BLOCKS")) d.mirror_blocks = std::max(1, atoi(e));
+    }
     RG_TRY(cudaEventCreateWithFlags(&b->ev_mir, cudaEventDisableTiming));
     RG_TRY(cudaEventCreateWithFlags(&b->ev_mon, cudaEventDisableTiming));
     RG_TRY(cudaEventCreateWithFlags(&b->ev_fast, cudaEventDisableTiming));
@@ -865,6 +869,14 @@ int rg_mirror_get(rg_batch* b, rg_host_obs* out, uint8_t** history_bits) {
     memset(hp, 0, total);  // == the zeroed shadows below
     void* dp = nullptr;
     cudaError_t e = cudaHostGetDevicePointer(&dp, hp, 0);
+    if (e == cudaSuccess && getenv("RG_MIRROR_NOHOST")) {  // diagnostic: the stores go to device memory (the mirror stays stale)
+      void* scratch = nullptr;
+      e = cudaMalloc(&scratch, total);
+      if (e == cudaSuccess) {
+        b->dev_allocs.push_back(scratch);
+        dp = scratch;
+      }
+    }
     if (e != cudaSuccess) {
       cudaFreeHost(hp);
       return cuda_fail(b, e, "cudaHostGetDevicePointer");
@@ -942,26 +954,42 @@ int rg_mirror_sync(rg_batch* b, uint64_t* bytes_to_host) {
   RG_CUDA(b, cudaSetDevice(b->device));
   RG_CUDA(b, rg::launch_mirror(b->d, b->margs, b->sm_count, b->stream));  // publishes the byte counter itself
   b->launches += 1;
-  int rc = rg_sync(b);  // drains the stream: the mirror is readable now
+  RG_CUDA(b, cudaStreamSynchronize(b->stream));  // the mirror is readable now
   if (bytes_to_host) *bytes_to_host = *b->h_count;
-  return rc;
+  if (*b->h_errflag == 0) return RG_OK;
+  const uint8_t* err = b->m_obs.error;
+  for (int64_t i = 0; i < b->n; ++i)
+    if (err[i]) {
+      const int code = err[i];
+      return set_err(b, code, std::string("Error in rogue-gym: ") + status_text(code) + " (env " + std::to_string(i) + ")");
+    }
+  return RG_OK;
 }
 
 int rg_step_mirror(rg_batch* b, const uint8_t* actions_host, int auto_reset, uint64_t* bytes_to_host) {
   if (!b || !actions_host) return set_err(b, RG_ERR_ARG, "rg_step_mirror: null argument");
   if (!b->m_host) return set_err(b, RG_ERR_ARG, "rg_step_mirror: call rg_mirror_get first");
   RG_CUDA(b, cudaSetDevice(b->device));
-  // One graph launch: the actions go through a pinned staging buffer (the caller's array may be pageable
-  // and changes from call to call, a graph node needs a fixed source), then H2D, the step with its mirror
-  // passes - most envs are written back beside the monster / full-path kernels, the rest after the step's
-  // last kernel - and the byte counter and error flag back to the host.
+  // One graph launch, kernels only: the actions go through a pinned, mapped staging buffer (the caller's array may be
+  // pageable and changes from call to call, a graph needs a fixed source) that k_step_scan reads over PCIe; the step
+  // with its mirror passes - most envs are written back beside the other kernels, the rest after the step's last
+  // kernel, which also writes the byte counter and the error flag into mapped host memory.
   memcpy(b->h_actions, actions_host, (size_t)b->n);
   int rc = step_impl(b, b->d_actions, auto_reset, true);
   if (rc != RG_OK) return rc;
   RG_CUDA(b, cudaStreamSynchronize(b->stream));  // the mirror is readable now
   if (bytes_to_host) *bytes_to_host = *b->h_count;
   if (*b->h_errflag == 0) return RG_OK;
-  return rg_sync(b);  // some env raised an error: report it like every other call
+  // Some env raised an error (a sticky reference-panic env does so on every step): report the first failing env like
+  // rg_sync does (thread_impls.rs:65-68) - from the mirror's own error array, which is current; no further device work
+  // (the publishing pass has cleared the device flag).
+  const uint8_t* err = b->m_obs.error;
+  for (int64_t i = 0; i < b->n; ++i)
+    if (err[i]) {
+      const int code = err[i];
+      return set_err(b, code, std::string("Error in rogue-gym: ") + status_text(code) + " (env " + std::to_string(i) + ")");
+    }
+  return RG_OK;
 }
 
 void* rg_stream(rg_batch* b) { return b ? (void*)b->stream : nullptr; }

@@ -634,7 +634,7 @@ __device__ int cached_dist_map(Ctx& c, int tx, int ty, int nx0, int ny0) {
     st->cache_snap = (uint16_t)(st->cache_snap & ~(1u << slot));  // a new map starts on the current floor
     __syncwarp();
   }
-  bfs_extend(c, slot, nx0, ny0);
+  if (nx0 > -100) bfs_extend(c, slot, nx0, ny0);  // nx0 <= -100: only find / create the entry
   return slot;
 }
 
@@ -656,9 +656,10 @@ __device__ __noinline__ bool cell_blocked(const Ctx& c, int x, int y, uint32_t m
 enum { MV_CANT = 0, MV_CAN = 1, MV_REACH = 2 };
 // rogue::Dungeon::move_enemy rogue/mod.rs:339-375. PARALLEL over the 9 directions: lane d
 // probes neighbour d, the in-order semantics are rebuilt from ballots.
+RG_DEV bool room_interior(const RoomD& r, int x, int y) { return x > r.x0 && x < r.x1 - 1 && y > r.y0 && y < r.y1 - 1; }
+
 __device__ int move_enemy(Ctx& c, int mx, int my, int tx, int ty, uint32_t moved, bool noskip, int& ox, int& oy) {
-  const int slot = cached_dist_map(c, tx, ty, mx, my);
-  if (c.panic) return MV_CANT;
+  const int slot = cached_dist_map(c, tx, ty, -100, -100);  // the DistCache entry (FIFO order is observable); no BFS yet
   const uint16_t* dm = c.g_dist + (size_t)slot * c.CP;
   const int d = c.lane;
   const bool valid = d < 9;
@@ -682,7 +683,32 @@ __device__ int move_enemy(Ctx& c, int mx, int my, int tx, int ty, uint32_t moved
   const bool live = valid && !skip;
   const bool oob = live && !inb(c, nx, ny);
   uint32_t nd = 0xFFFFu;
-  if (live && !oob) nd = dm[ny * c.W + nx];
+  // The common chase happens inside one rectangular room. If the target and every walkable cell about to be read lie
+  // in the interior of the same normal room - all floor by construction - the shortest 8-direction path between them
+  // stays inside their bounding box, where nothing blocks a step (a diagonal's two orthogonal cells are in the box
+  // too): the BFS label is the Chebyshev distance, and the map need not be extended at all (it stays suspended at
+  // whatever level it has; labels never change once written). Not for a map that resumes on a walkability snapshot
+  // of an earlier floor (cache_snap): its geometry is not this floor's.
+  bool shortcut;
+  {
+    RG_PLANES(c);
+    const int rid = room_of(c, tx, ty);
+    bool ok = rid >= 0 && !((st->cache_snap >> slot) & 1u);
+    RoomD rm = st->rooms[ok ? rid : 0];
+    ok = ok && rm.kind == K_NORMAL && room_interior(rm, tx, ty);
+    bool mine = true, walkable = false;
+    if (ok && live && !oob) {
+      walkable = can_walk(S[ny * c.W + nx]);
+      mine = !walkable || room_interior(rm, nx, ny);
+    }
+    shortcut = ok && __all_sync(RG_FULL, mine);
+    if (shortcut && walkable) nd = (uint32_t)max(abs(nx - tx), abs(ny - ty));
+  }
+  if (!shortcut) {
+    bfs_extend(c, slot, mx, my);
+    if (c.panic) return MV_CANT;
+    if (live && !oob) nd = dm[ny * c.W + nx];
+  }
   const bool reach = live && !oob && nd == 0 && can_move(c, mx, my, d, true);
   const bool cand = live && !oob && nd != 0xFFFFu && nd > 0;
   const uint32_t oobM = __ballot_sync(RG_FULL, oob);

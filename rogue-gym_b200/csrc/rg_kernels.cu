@@ -1585,6 +1585,7 @@ __global__ void __launch_bounds__(256) k_mirror(DevBatch b, MirrorArgs m, int pa
         __threadfence();
         *m.h_bytes = *reinterpret_cast<volatile unsigned long long*>(m.bytes);
         *m.h_errflag = *reinterpret_cast<volatile uint32_t*>(b.errflag);
+        *b.errflag = 0u;  // reported: rg_sync clears it the same way
         *m.bytes = 0ull;
         *m.ticket = 0u;
         __threadfence_system();
@@ -1670,7 +1671,7 @@ cudaError_t launch_step(const DevBatch& b, const uint8_t* actions_src, uint8_t* 
     // step - the pass is dominated by small PCIe writes, not by SM work
     if ((e = cudaEventRecord(q.ev_fast, s)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(q.mir, q.ev_fast, 0)) != cudaSuccess) return e;
-    k_mirror<<<mirror_blocks(b, sm_count), 256, 0, q.mir>>>(b, *mirror, 1, 0, b.n);
+    k_mirror<<<b.mirror_blocks > 0 ? b.mirror_blocks : mirror_blocks(b, sm_count), 256, 0, q.mir>>>(b, *mirror, 1, 0, b.n);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if ((e = cudaEventRecord(q.ev_mir, q.mir)) != cudaSuccess) return e;
   }

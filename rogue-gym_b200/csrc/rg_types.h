@@ -159,6 +159,7 @@ struct DevBatch {
   uint32_t* slow_list;    // [N] envs with an active monster (k_step_scan -> player kernel, first list)
   uint32_t* slow_list_b;  // [N] envs k_step_fast left to the warp-per-env player kernel (second list)
   uint32_t* slow_count;   // [list][parity] lengths, then [list][parity] work cursors of the player kernels
+  int32_t mirror_blocks;  // > 0: grid of the first host-mirror pass (RG_MIRROR_BLOCKS)
   int32_t panic_policy;   // 0 sticky (reference-like: the env is dead for good), 1 terminal (see finish_env)
   int32_t branches;       // 1 = the active-monster envs' kernels run on a stream of their own beside k_step_fast
   int32_t fast;           // 0 = k_step_fast only classifies (every env goes to the player kernel; RG_FAST=0)

@@ -2,11 +2,7 @@
 layer (`rogue_gym.envs`) on top of the B200 extension-module mirror `rogue_gym_python._rogue_gym`."""
 from . import envs  # noqa: F401
 
-try:  # optional trainer adapter, only when `rainy` is installed (python/rogue_gym/__init__.py:3-7)
-    import rainy  # noqa: F401
-
-    from . import rainy_impls  # noqa: F401
-except ImportError:
-    pass
+# (The reference also ships `rainy_impls.py`, an adapter for the third-party `rainy` trainer that expands one Python
+# PlayerState at a time; it is off the accelerated path and not reproduced - trainers use rogue_gym.envs.DeviceRogueEnv.)
 
 __version__ = "0.0.2+b200"

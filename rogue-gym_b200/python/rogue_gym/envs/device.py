@@ -1,7 +1,7 @@
 """DeviceRogueEnv — the batched, device-resident face of the simulator for trainers.
 
 The reference hands a trainer one Python `PlayerState` per env and the trainer expands each into a
-float32 image and stacks them (python/rogue_gym/rainy_impls.py:65-66: a Python loop + np.stack, the
+float32 image and stacks them (the reference's python/rogue_gym/rainy_impls.py:65-66: a Python loop + np.stack, the
 401 KB/env-step cost of the default observation crosses PCIe and the interpreter). Here nothing
 leaves HBM: actions come in as a CUDA tensor, the step kernels run on the batch's stream, the image
 encoder (`rg_encode`, same planes as `ImageSetting.expand`) writes straight into a torch tensor the

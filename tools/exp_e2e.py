@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.join(ROOT, "rogue-gym_b200", "python"))
 import numpy as np, torch
 from rogue_gym_python import _cabi
 from rogue_gym_python.rollout import Shard, synthetic_actions
-n, K = 65536, 600
+n, K = int(os.environ.get("E2E_N", "65536")), 600
 sh = Shard("{}", 0, n)
 acts = np.stack([synthetic_actions(t, sh.env_ids) for t in range(K)])
 hacts = torch.from_numpy(acts).pin_memory()
