@@ -78,7 +78,7 @@ struct rg_batch {
   uint8_t* m_hist_dev = nullptr;
   uint8_t* ms_screen = nullptr;
   uint8_t* ms_hist = nullptr;
-  uint32_t* ms_small = nullptr;
+  uint8_t* ms_flat = nullptr;
   unsigned long long* m_count = nullptr;  // device counter of bytes stored to the host
   uint64_t* h_count = nullptr;            // pinned
   int sm_count = 148;
@@ -252,11 +252,12 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
   RG_TRY(dev_alloc(b, &d.bfs, N * (size_t)rg::NCACHE * 2 * d.H * d.WW));
   RG_TRY(dev_alloc(b, &d.wsnap, N * (size_t)rg::NCACHE * d.H * d.WW));
   RG_TRY(dev_alloc(b, &d.st, N));
-  RG_TRY(dev_alloc(b, &d.status, N * 10));
-  RG_TRY(dev_alloc(b, &d.reward, N));
-  RG_TRY(dev_alloc(b, &d.done, N));
-  RG_TRY(dev_alloc(b, &d.message, N));
-  RG_TRY(dev_alloc(b, &d.error, N));
+  // (+ one 64-byte line each: the host mirror reads these arrays in whole lines)
+  RG_TRY(dev_alloc(b, &d.status, N * 10 + 16));
+  RG_TRY(dev_alloc(b, &d.reward, N + 16));
+  RG_TRY(dev_alloc(b, &d.done, N + 64));
+  RG_TRY(dev_alloc(b, &d.message, N + 16));
+  RG_TRY(dev_alloc(b, &d.error, N + 64));
   RG_TRY(dev_alloc(b, &d.errflag, 1));
   RG_TRY(dev_alloc(b, &d.scr_rows, N));
   RG_TRY(cudaMemsetAsync(d.scr_rows, 0xFF, N * 8, b->stream));
@@ -898,14 +899,15 @@ int rg_mirror_get(rg_batch* b, rg_host_obs* out, uint8_t** history_bits) {
       cudaError_t e2;
       if ((e2 = dev_alloc(b, &b->ms_screen, N * d.CP)) != cudaSuccess) return e2;
       if ((e2 = dev_alloc(b, &b->ms_hist, N * d.HB)) != cudaSuccess) return e2;
-      if ((e2 = dev_alloc(b, &b->ms_small, N * 16)) != cudaSuccess) return e2;
+      const size_t flat = (N * 40 + 63) / 64 * 64 + 2 * ((N * 4 + 63) / 64 * 64) + 2 * ((N + 63) / 64 * 64);
+      if ((e2 = dev_alloc(b, &b->ms_flat, flat)) != cudaSuccess) return e2;
       if ((e2 = dev_alloc(b, &b->m_count, 1)) != cudaSuccess) return e2;
       if (!b->h_count && (e2 = cudaHostAlloc(&b->h_count, sizeof(uint64_t), cudaHostAllocMapped)) != cudaSuccess) return e2;
       if ((e2 = dev_alloc(b, &b->m_ticket, 1)) != cudaSuccess) return e2;
       if ((e2 = cudaMemsetAsync(b->m_ticket, 0, 4, b->stream)) != cudaSuccess) return e2;
       if ((e2 = cudaMemsetAsync(b->ms_screen, 0, N * d.CP, b->stream)) != cudaSuccess) return e2;
       if ((e2 = cudaMemsetAsync(b->ms_hist, 0, N * d.HB, b->stream)) != cudaSuccess) return e2;
-      if ((e2 = cudaMemsetAsync(b->ms_small, 0, N * 64, b->stream)) != cudaSuccess) return e2;
+      if ((e2 = cudaMemsetAsync(b->ms_flat, 0, flat, b->stream)) != cudaSuccess) return e2;
       return cudaMemsetAsync(b->m_count, 0, 8, b->stream);
     };
     e = setup();
@@ -918,8 +920,10 @@ int rg_mirror_get(rg_batch* b, rg_host_obs* out, uint8_t** history_bits) {
     rg::MirrorArgs& m = b->margs;
     m.h_screen = b->m_dev.screen; m.h_hist = b->m_hist_dev; m.h_status = b->m_dev.status; m.h_reward = b->m_dev.reward;
     m.h_done = b->m_dev.done; m.h_message = b->m_dev.message; m.h_error = b->m_dev.error;
-    m.s_screen = b->ms_screen; m.s_hist = b->ms_hist; m.s_small = b->ms_small; m.bytes = b->m_count;
+    m.s_screen = b->ms_screen; m.s_hist = b->ms_hist; m.s_flat = b->ms_flat; m.bytes = b->m_count;
     m.ticket = b->m_ticket;
+    m.wide = 1;
+    if (const char* e = getenv("RG_MIRROR_WIDE")) m.wide = e[0] != '0';
     {
       void *hb = nullptr, *he = nullptr;
       RG_CUDA(b, cudaHostGetDevicePointer(&hb, b->h_count, 0));

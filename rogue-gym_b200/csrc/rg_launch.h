@@ -18,12 +18,13 @@ struct MirrorArgs {
   uint8_t* h_error;      // host [N]
   uint8_t* s_screen;     // shadows, device: [N][CP]
   uint8_t* s_hist;       // [N][HB]
-  uint32_t* s_small;     // [N][16]: status[10], reward, message, done | error << 8, 3 spare
+  uint8_t* s_flat;       // shadows of status, reward, message, done, error, each rounded up to whole 64-byte lines
   unsigned long long* bytes;  // [1] bytes stored to the host since the counter was last cleared
   // the pass that ends a host-facing step publishes its results itself (no copy-engine nodes in the step's graph):
   unsigned long long* h_bytes;  // mapped host: bytes stored by the step
   uint32_t* h_errflag;          // mapped host: OR of the errors raised
   uint32_t* ticket;             // device: blocks of the publishing pass that have finished
+  int wide;              // 1 = a changed screen piece is sent with its whole 64-byte line (RG_MIRROR_WIDE)
   int with_hist;         // 0 = the visited map is not mirrored (nobody asked for it: rg_mirror_get without history_bits)
 };
 
