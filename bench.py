@@ -33,9 +33,11 @@ CONFIG = {}  # config-default: every field at its default ("{}" => default, core
 #   read  grid 2C (3840) + small state 1536 + action 1
 #   write screen C (1920) + small state 512 + status/reward/done/msg 49
 BYTES_PER_ENV_STEP = 7858
-# dram__bytes_read.sum + dram__bytes_write.sum of one steady-state step (scan + player + monsters + full-path
-# kernels) at 65 536 envs, from the ncu --set full capture summarised in profiles/r1_ncu_summary.md
-NCU_DRAM_BYTES_PER_STEP = 404.9e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one step of the light phase (step ~1900) over the step path's kernels
+# (scan, thread-per-env, 2 x player, 2 x monsters, 2 x full-path / reset pass) at 65 536 envs, from the
+# `ncu --replay-mode application` pass in profiles/r2_light_dram_appreplay.csv (100.2 MB read + 1.5 MB written: the
+# 126 MB L2 absorbs the small per-step writes; kernel-replay captures cannot be used for writes, see profiles/r2_ncu_summary.md)
+NCU_DRAM_BYTES_PER_STEP = 101.7e6
 WORKLOAD = "65536 envs/GPU, config-default 80x24 (3x3 rooms, monsters, gold, visibility), random 11-action rollout, max_steps 1000, auto-reset"
 
 
@@ -361,6 +363,8 @@ def main():
     shard.sync()
     launches0 = shard.launches()
     sampler = ClockSampler(local_rank)
+    if os.environ.get("BENCH_NO_SAMPLER") == "1":  # experiments only: does NVML polling disturb the timed region?
+        sampler.ok = False
     barrier()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -514,12 +518,16 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_BYTES_PER_STEP if (n == ENVS_PER_GPU and not args.config_json) else None,
-                         "kernel": "one step = CUDA graph of rg::k_step_scan -> k_step_player -> k_step_monsters (+ k_step_gen beside them); "
-                                   "k_step_player is the dominant kernel (ncu: 121 us of the ~173 us serial chain, 382 MB of the step's DRAM traffic)",
+                         "kernel": "one step = CUDA graph: rg::k_step_scan, then side by side k_step_gen (descents) | k_step_player -> "
+                                   "k_step_monsters (envs with an active monster) | k_step_fast (one thread per env: 88 % of env-steps) -> "
+                                   "k_step_player -> k_step_monsters (its leftovers), then the reset pass; k_step_fast is the dominant kernel "
+                                   "(58 of the step's 102 MB of DRAM traffic, ~30 us: bound by scattered 32-byte sector reads)",
                          "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_source": peak_src,
-                         "note": "achieved = algorithmic bytes of one step (7858 B x envs) / average step duration over the timed region "
-                                 "(CUDA events on the batch's stream); traffic = dram read+write of the step's kernels from ncu --set full "
-                                 "(profiles/r1_ncu_summary.md). The step is bound by per-env serial game logic and instruction fetch, not by HBM"},
+                         "note": "achieved = algorithmic bytes of one step (SURVEY 8d: 7858 B x envs) / average step duration over the "
+                                 "timed region (CUDA events on the batch's stream); traffic = dram read+write of the step path's kernels for "
+                                 "one step (ncu, application replay, profiles/r2_light_dram_appreplay.csv): a fifth of the algorithmic figure, "
+                                 "because a step touches a few cells and state words per env, not the env's whole grid. The step is bound by "
+                                 "latency chains (descents, monster chases) and random-sector DRAM access, not by streaming bandwidth"},
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)
