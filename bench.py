@@ -400,7 +400,7 @@ def main():
     # actions come from pinned host memory and the whole observation block (screen u8[N,H,W], status,
     # reward, done, message) is current in host memory before the next step starts.
     #   e2e            rg_step_mirror: the block lives in a pinned host mirror; kernels compare it with a
-    #                  device-side shadow and store only the 16-byte pieces that changed, over PCIe
+    #                  device-side shadow and store only the 64-byte lines that changed, over PCIe
     #   e2e_full_copy  rg_step_host: the block is copied whole (129 MB per step) - the straightforward path
     e2e_ms, full_ms, h2d, d2h, d2h_full = None, None, n, 0, 0
     if not args.no_e2e:
@@ -508,8 +508,9 @@ def main():
                 "value": live_all * K / (e2e_ms_all * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": int(d2h_all), "ms_per_step": e2e_ms_all / K,
                 "what": "rg_step_mirror per step: actions from pinned host memory, step kernels, delta write-back of the observation "
-                        "block (screen u8[N,24,80] + status + reward + done + message) into the pinned host mirror - only the 16-byte "
-                        "pieces that changed cross PCIe (measured average in d2h_bytes_per_step) - then stream sync; the host block is "
+                        "block (screen u8[N,24,80] + status + reward + done + message) into the pinned host mirror - only the 64-byte "
+                        "lines that changed cross PCIe (measured average in d2h_bytes_per_step) - and the call returns once the last "
+                        "write has landed; the host block is "
                         "byte-identical to a full copy (tests/test_gpu_parity.py::test_host_mirror_equals_full_copy)"},
             "e2e_full_copy": None if full_ms is None else {
                 "value": live_all * K / (full_ms_all * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d * world,

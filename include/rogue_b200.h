@@ -238,8 +238,8 @@ int rg_train_reset(rg_batch* b);
  * bit y*W+x of an env's row = visited (the layout of rg_views.history_bits), and only from the first call that
  * passes a non-NULL history_bits on (it costs about a third of a step's PCIe writes).
  * rg_mirror_sync brings the mirror up to date with the device block: kernels compare the block with a
- * device-side shadow of what the host holds and store only the 16-byte pieces that changed, over PCIe,
- * into the mirror; it returns after the stream has drained, so the host may read at once.
+ * device-side shadow of what the host holds and store only the 64-byte lines that changed, over PCIe,
+ * into the mirror; it returns once the last of those writes has landed, so the host may read at once.
  * rg_step_mirror = actions H2D + rg_step + rg_mirror_sync: the host-facing step of rg_step_host
  * (python/src/lib.rs:315-321) at a fraction of its PCIe traffic. *bytes_to_host (nullable) receives the
  * bytes the call stored into the mirror. The caller must not write to the mirror. */

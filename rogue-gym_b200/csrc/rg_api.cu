@@ -80,7 +80,10 @@ struct rg_batch {
   uint8_t* ms_hist = nullptr;
   uint8_t* ms_flat = nullptr;
   unsigned long long* m_count = nullptr;  // device counter of bytes stored to the host
-  uint64_t* h_count = nullptr;            // pinned
+  uint64_t* h_count = nullptr;            // pinned [2]: bytes stored by the last call; publishing passes completed
+  unsigned long long* m_seq = nullptr;    // device: publishing passes completed
+  uint64_t m_seq_expected = 0;            // publishing passes launched
+  bool mirror_spin = true;                // wait for a pass by spinning on h_count[1] (RG_MIRROR_SPIN=0: cudaStreamSynchronize)
   int sm_count = 148;
   std::vector<void*> dev_allocs;
   std::string err;
@@ -377,8 +380,8 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
   RG_TRY(cudaMemsetAsync(d.mon_count, 0, 32, b->stream));
   RG_TRY(dev_alloc(b, &d.fast_list_m, N));
   RG_TRY(dev_alloc(b, &d.fast_list_l, N));
-  RG_TRY(dev_alloc(b, &d.fast_count, 4));
-  RG_TRY(cudaMemsetAsync(d.fast_count, 0, 16, b->stream));
+  RG_TRY(dev_alloc(b, &d.fast_count, 8));
+  RG_TRY(cudaMemsetAsync(d.fast_count, 0, 32, b->stream));
   RG_TRY(dev_alloc(b, &d.slow_list, N));
   RG_TRY(dev_alloc(b, &d.slow_list_b, N));
   RG_TRY(dev_alloc(b, &d.slow_count, 8));
@@ -902,9 +905,18 @@ int rg_mirror_get(rg_batch* b, rg_host_obs* out, uint8_t** history_bits) {
       const size_t flat = (N * 40 + 63) / 64 * 64 + 2 * ((N * 4 + 63) / 64 * 64) + 2 * ((N + 63) / 64 * 64);
       if ((e2 = dev_alloc(b, &b->ms_flat, flat)) != cudaSuccess) return e2;
       if ((e2 = dev_alloc(b, &b->m_count, 1)) != cudaSuccess) return e2;
-      if (!b->h_count && (e2 = cudaHostAlloc(&b->h_count, sizeof(uint64_t), cudaHostAllocMapped)) != cudaSuccess) return e2;
+      if (!b->h_count && (e2 = cudaHostAlloc(&b->h_count, 2 * sizeof(uint64_t), cudaHostAllocMapped)) != cudaSuccess) return e2;
+      b->h_count[0] = b->h_count[1] = 0;
+      if ((e2 = dev_alloc(b, &b->m_seq, 1)) != cudaSuccess) return e2;
+      if ((e2 = cudaMemsetAsync(b->m_seq, 0, 8, b->stream)) != cudaSuccess) return e2;
+      if (const char* v = getenv("RG_MIRROR_SPIN")) b->mirror_spin = v[0] != '0';
       if ((e2 = dev_alloc(b, &b->m_ticket, 1)) != cudaSuccess) return e2;
       if ((e2 = cudaMemsetAsync(b->m_ticket, 0, 4, b->stream)) != cudaSuccess) return e2;
+      // k_mirror_lines on a few SMs (default) | k_mirror on every SM (RG_MIRROR_MODE=direct)
+      b->margs.mode = 1;
+      b->margs.confined_sms = 16;
+      if (const char* v = getenv("RG_MIRROR_MODE")) b->margs.mode = !strcmp(v, "direct") ? 0 : 1;
+      if (const char* v = getenv("RG_MIRROR_SMS")) b->margs.confined_sms = std::max(1, atoi(v));
       if ((e2 = cudaMemsetAsync(b->ms_screen, 0, N * d.CP, b->stream)) != cudaSuccess) return e2;
       if ((e2 = cudaMemsetAsync(b->ms_hist, 0, N * d.HB, b->stream)) != cudaSuccess) return e2;
       if ((e2 = cudaMemsetAsync(b->ms_flat, 0, flat, b->stream)) != cudaSuccess) return e2;
@@ -922,6 +934,7 @@ int rg_mirror_get(rg_batch* b, rg_host_obs* out, uint8_t** history_bits) {
     m.h_done = b->m_dev.done; m.h_message = b->m_dev.message; m.h_error = b->m_dev.error;
     m.s_screen = b->ms_screen; m.s_hist = b->ms_hist; m.s_flat = b->ms_flat; m.bytes = b->m_count;
     m.ticket = b->m_ticket;
+    m.h_base = static_cast<uint8_t*>(dp);
     m.wide = 1;
     if (const char* e = getenv("RG_MIRROR_WIDE")) m.wide = e[0] != '0';
     {
@@ -929,6 +942,8 @@ int rg_mirror_get(rg_batch* b, rg_host_obs* out, uint8_t** history_bits) {
       RG_CUDA(b, cudaHostGetDevicePointer(&hb, b->h_count, 0));
       RG_CUDA(b, cudaHostGetDevicePointer(&he, b->h_errflag, 0));
       m.h_bytes = static_cast<unsigned long long*>(hb);
+      m.h_seq = m.h_bytes + 1;
+      m.seq = b->m_seq;
       m.h_errflag = static_cast<uint32_t*>(he);
     }
     int rc = rg_mirror_sync(b, nullptr);  // the mirror starts out current
@@ -952,13 +967,42 @@ int rg_mirror_get(rg_batch* b, rg_host_obs* out, uint8_t** history_bits) {
   return RG_OK;
 }
 
+}  // extern "C"
+namespace {
+// Waits for the publishing mirror pass launched last. Its last block writes the pass counter into mapped host memory
+// after everything else (system-scope fences in between), so the host can spin on that word: the mirror is readable
+// ~5 us earlier than cudaStreamSynchronize reports the stream idle. A failed launch or a device fault never publishes:
+// the stream is polled now and then.
+int wait_mirror(rg_batch* b) {
+  const uint64_t want = ++b->m_seq_expected;
+  if (b->mirror_spin) {
+    volatile uint64_t* seq = b->h_count + 1;
+    for (uint32_t spins = 1; *seq < want; ++spins) {
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#endif
+      if ((spins & 0x3FFFu) == 0) {
+        cudaError_t q = cudaStreamQuery(b->stream);
+        if (q == cudaSuccess) break;  // drained: the word is there (or the pass never ran - caught below)
+        if (q != cudaErrorNotReady) return cuda_fail(b, q, "host mirror pass");
+      }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    if (*seq >= want) return RG_OK;
+  }
+  RG_CUDA(b, cudaStreamSynchronize(b->stream));
+  return RG_OK;
+}
+}  // namespace
+extern "C" {
+
 int rg_mirror_sync(rg_batch* b, uint64_t* bytes_to_host) {
   if (!b) return set_err(b, RG_ERR_ARG, "rg_mirror_sync: null batch");
   if (!b->m_host) return set_err(b, RG_ERR_ARG, "rg_mirror_sync: call rg_mirror_get first");
   RG_CUDA(b, cudaSetDevice(b->device));
   RG_CUDA(b, rg::launch_mirror(b->d, b->margs, b->sm_count, b->stream));  // publishes the byte counter itself
   b->launches += 1;
-  RG_CUDA(b, cudaStreamSynchronize(b->stream));  // the mirror is readable now
+  if (int rc = wait_mirror(b)) return rc;  // the mirror is readable now
   if (bytes_to_host) *bytes_to_host = *b->h_count;
   if (*b->h_errflag == 0) return RG_OK;
   const uint8_t* err = b->m_obs.error;
@@ -981,7 +1025,7 @@ int rg_step_mirror(rg_batch* b, const uint8_t* actions_host, int auto_reset, uin
   memcpy(b->h_actions, actions_host, (size_t)b->n);
   int rc = step_impl(b, b->d_actions, auto_reset, true);
   if (rc != RG_OK) return rc;
-  RG_CUDA(b, cudaStreamSynchronize(b->stream));  // the mirror is readable now
+  if (int rc2 = wait_mirror(b)) return rc2;  // the mirror is readable now
   if (bytes_to_host) *bytes_to_host = *b->h_count;
   if (*b->h_errflag == 0) return RG_OK;
   // Some env raised an error (a sticky reference-panic env does so on every step): report the first failing env like

@@ -757,6 +757,7 @@ __global__ void __launch_bounds__(128) k_step_fast(DevBatch b, const uint8_t* __
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const uint32_t n_move = b.fast_count[parity * 2], n_light = b.fast_count[parity * 2 + 1];
+  if (blockIdx.x == 0 && threadIdx.x == 0) b.fast_count[4] = n_move;  // (the mirror pass may outlive the step's parity)
   int cls = -1;
   int64_t env = -1;
   if (t < (int64_t)n_move) env = (int64_t)b.fast_list_m[t];
@@ -1627,6 +1628,224 @@ __global__ void __launch_bounds__(256) k_mirror(DevBatch b, MirrorArgs m, int pa
         *m.bytes = 0ull;
         *m.ticket = 0u;
         __threadfence_system();
+        const unsigned long long seq = *m.seq + 1ull;
+        *m.seq = seq;
+        *reinterpret_cast<volatile unsigned long long*>(m.h_seq) = seq;  // everything above is in host memory before this
+        __threadfence_system();
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- host mirror by lines (confined to a few SMs)
+// Stores into mapped host memory back up behind PCIe, and an SM's memory pipeline serves its requests in order: while
+// k_mirror's stores drain, every other kernel on the same SM waits behind them (timeline: the monster kernel beside the
+// pass 45 -> 100 us, the player kernel 13 -> 40 us). With that pass confined to 16 SMs the other kernels run at full
+// speed - but its one-warp-per-env loops of dependent loads then take 540 us. k_mirror_lines does the same compare with
+// every thread busy (a work list of candidate 64-byte lines per chunk of envs), so that a few SMs (RG_MIRROR_SMS, one
+// 1024-thread block each) are enough to keep PCIe full, and only those SMs see the back-pressure. The pass is bound by
+// the number of PCIe writes (~45 k lines in 65-70 us, whether a write carries 64, 32 or 16 bytes). Tried and dropped
+// (profiles/r2_mirror_modes.log): a line log in device memory written by every SM and streamed out by a few blocks
+// (the extra kernel boundary costs more than the compare on few SMs), k_step_fast in two launches with the first
+// half's pass beside the second (the split costs what the earlier start gains), 32-byte half-line writes.
+// Used when the screen is a whole number of 64-byte lines per env; other sizes keep k_mirror.
+enum : uint32_t { LINE_PIECE = 0x80000000u };  // line index flag: one 16-byte piece (visited map), index in 16-byte units
+
+// A line has to leave as ONE 64-byte write (four adjacent lanes, 16 bytes each, in the same store instruction): a
+// thread storing its own line piece by piece would send four partial-line writes (measured: the pass 2x slower). So
+// the warp transposes: eight changed lines per round, lane l stores piece l & 3 of the (l >> 2)-th of them.
+// Called by whole warps.
+RG_DEV void emit_line(const MirrorArgs& m, bool changed, uint32_t off, const uint4 (&data)[4], uint32_t& sent) {
+  const bool piece = (off & LINE_PIECE) != 0u;
+  const int lane = threadIdx.x & 31;
+  if (changed && piece) {
+    *reinterpret_cast<uint4*>(m.h_base + (size_t)(off & ~LINE_PIECE) * 16) = data[0];
+    sent += 16;
+  }
+  uint32_t todo = __ballot_sync(RG_FULL, changed && !piece);
+  while (todo) {
+    const uint32_t src = __fns(todo, 0, (lane >> 2) + 1);  // the lane that holds "my" line (0xFFFFFFFF: fewer than that are left)
+    const int from = src == 0xFFFFFFFFu ? 0 : (int)src;
+    const int q = lane & 3;
+    uint4 v = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t x = __shfl_sync(RG_FULL, data[k].x, from), y = __shfl_sync(RG_FULL, data[k].y, from);
+      const uint32_t z = __shfl_sync(RG_FULL, data[k].z, from), w = __shfl_sync(RG_FULL, data[k].w, from);
+      if (k == q) v = make_uint4(x, y, z, w);
+    }
+    const uint32_t line = __shfl_sync(RG_FULL, off, from);
+    if (src != 0xFFFFFFFFu) {
+      reinterpret_cast<uint4*>(m.h_base + (size_t)line * 64)[q] = v;
+      sent += 16;
+    }
+    const uint32_t eighth = __fns(todo, 0, 8);  // drop the eight lowest set bits
+    todo = eighth == 0xFFFFFFFFu ? 0u : (eighth == 31u ? 0u : todo & (0xFFFFFFFFu << (eighth + 1)));
+  }
+}
+
+// Chunks of `epb` envs, grid-stride. Phase 1, one thread per env: which 64-byte lines of the screen (16-byte pieces of
+// the visited map) overlap the rows the step rewrote -> a work list in shared memory. Phase 2, one thread per list
+// entry: compare with the shadow, update it, send. Then (`flat`) the small arrays (status, reward, message, done,
+// error), one thread per line. `pass`: 1 = beside the step's other kernels: the envs k_step_fast finished, taken from
+// positions [pos_lo, pos_hi) of its list of moves (the only envs that kernel redraws); 2 = after the step, 0 = on
+// request (rg_mirror_sync): every env that still has rows marked. `publish`: the last block hands byte counter and
+// error flag to the host.
+__global__ void __launch_bounds__(1024) k_mirror_lines(DevBatch b, MirrorArgs m, int pass, int epb, int env_chunks, int flat,
+                                                       int publish, int64_t pos_lo, int64_t pos_hi) {
+  DevBatch tb = b;
+  uint32_t prev_step = *b.dstep - (pass == 2 ? 1u : 0u);
+  tb.dstep = &prev_step;
+  TraceScope trace(tb, pass == 2 ? TK_MIRROR2 : TK_MIRROR1);
+  extern __shared__ uint32_t smem_u32[];
+  uint32_t* const envs = smem_u32;         // [epb] the chunk's envs
+  uint32_t* const items = smem_u32 + epb;  // (index into envs << 16) | line, or | 0x8000 | piece of the visited map
+  __shared__ uint32_t warp_tot[32];
+  __shared__ uint32_t total_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lpe = b.C >> 6, ppe = m.with_hist ? b.HB >> 4 : 0;
+  const uint32_t scr_line0 = (uint32_t)((m.h_screen - m.h_base) >> 6), hist_piece0 = (uint32_t)((m.h_hist - m.h_base) >> 4);
+  uint32_t sent = 0;
+  uint4 cur[4];
+  if (pass == 1) pos_hi = min(pos_hi, (int64_t)b.fast_count[4]);  // the moves come first in the list
+  for (int chunk = blockIdx.x; chunk < env_chunks; chunk += gridDim.x) {
+    int64_t env = (int64_t)chunk * epb + threadIdx.x;
+    if (pass == 1) {
+      const int64_t pos = pos_lo + env;
+      if (pos_lo + (int64_t)chunk * epb >= pos_hi) break;  // (block-uniform)
+      env = (int)threadIdx.x < epb && pos < pos_hi ? (int64_t)b.fast_list_m[pos] : b.n;
+    }
+    if ((int)threadIdx.x < epb) envs[threadIdx.x] = (uint32_t)min(env, b.n);
+    uint64_t rows = 0;
+    if ((int)threadIdx.x < epb && env < b.n) {
+      // pass 1: what k_step_fast finished (its leftovers are with the player kernel right now); passes 2 and 0 run after
+      // everything else and take every env that still has rows marked (also from steps that were not mirrored)
+      if (pass != 1 || b.full_path[env] == 0) {
+        rows = b.scr_rows[env];
+        if (rows) b.scr_rows[env] = 0ull;
+        if (b.H < 64) rows &= (1ull << b.H) - 1ull;
+      }
+    }
+    // lines / pieces are taken in ascending row order; consecutive rows share their boundary line: `last` dedupes
+    auto walk = [&](uint32_t* out) -> uint32_t {
+      uint32_t n = 0;
+      int last_l = -1, last_p = -1;
+      for (uint64_t r = rows; r; r &= r - 1) {
+        const int y = __ffsll((long long)r) - 1;
+        const int c0 = y * b.W, c1 = c0 + b.W - 1;
+        for (int j = max(c0 >> 6, last_l + 1); j <= min(c1 >> 6, lpe - 1); ++j) {
+          if (out) out[n] = (threadIdx.x << 16) | (uint32_t)j;
+          ++n;
+          last_l = j;
+        }
+        if (ppe)
+          for (int p = max(c0 >> 7, last_p + 1); p <= min(c1 >> 7, ppe - 1); ++p) {
+            if (out) out[n] = (threadIdx.x << 16) | 0x8000u | (uint32_t)p;
+            ++n;
+            last_p = p;
+          }
+      }
+      return n;
+    };
+    const uint32_t cnt = walk(nullptr);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(RG_FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0;
+    for (int w = 0; w < warp; ++w) before += warp_tot[w];
+    if (threadIdx.x == blockDim.x - 1) total_s = before + incl;
+    if (cnt) walk(items + before + incl - cnt);
+    __syncthreads();
+    const uint32_t total = total_s;
+    for (uint32_t i0 = 0; i0 < total; i0 += blockDim.x) {
+      const uint32_t i = i0 + threadIdx.x;
+      bool changed = false;
+      uint32_t off = 0;
+      if (i < total) {
+        const uint32_t it = items[i];
+        const int64_t e = (int64_t)envs[it >> 16];
+        if (it & 0x8000u) {
+          const uint32_t p = it & 0x7FFFu;
+          cur[0] = *reinterpret_cast<const uint4*>(b.hist + e * b.HB + p * 16);
+          uint4* sh = reinterpret_cast<uint4*>(m.s_hist + e * b.HB + p * 16);
+          changed = differs(cur[0], *sh);
+          if (changed) *sh = cur[0];
+          off = LINE_PIECE | (hist_piece0 + (uint32_t)(e * (b.HB >> 4)) + p);
+        } else {
+          const uint32_t j = it & 0x7FFFu;
+          const uint4* cp = reinterpret_cast<const uint4*>(b.screen + e * b.CP + j * 64);
+          uint4* sh = reinterpret_cast<uint4*>(m.s_screen + e * b.CP + j * 64);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) cur[k] = cp[k];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (differs(cur[k], sh[k])) { sh[k] = cur[k]; changed = true; }
+          off = scr_line0 + (uint32_t)(e * lpe) + j;
+        }
+      }
+      emit_line(m, changed, off, cur, sent);
+    }
+    __syncthreads();  // the work list is reused by the next chunk
+  }
+  if (flat) {
+    const uint8_t* src[5] = {reinterpret_cast<const uint8_t*>(b.status), reinterpret_cast<const uint8_t*>(b.reward),
+                             reinterpret_cast<const uint8_t*>(b.message), b.done, b.error};
+    uint8_t* dst[5] = {reinterpret_cast<uint8_t*>(m.h_status), reinterpret_cast<uint8_t*>(m.h_reward),
+                       reinterpret_cast<uint8_t*>(m.h_message), m.h_done, m.h_error};
+    const int64_t bytes[5] = {b.n * 40, b.n * 4, b.n * 4, b.n, b.n};
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t sh_off = 0;
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+      const int64_t lines = (bytes[a] + 63) / 64;  // whole lines (the arrays and their shadows are padded)
+      for (int64_t l0 = 0; l0 < lines; l0 += stride) {
+        const int64_t l = l0 + t0;
+        bool changed = false;
+        if (l < lines) {
+          const uint4* cp = reinterpret_cast<const uint4*>(src[a] + l * 64);
+          uint4* sh = reinterpret_cast<uint4*>(m.s_flat + sh_off + l * 64);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            cur[k] = cp[k];
+            if (l * 64 + k * 16 + 16 > bytes[a]) {  // the tail beyond the array: never compare or send garbage
+              uint32_t w[4] = {cur[k].x, cur[k].y, cur[k].z, cur[k].w};
+              for (int q = 0; q < 16; ++q)
+                if (l * 64 + k * 16 + q >= bytes[a]) w[q >> 2] &= ~(0xFFu << (8 * (q & 3)));
+              cur[k] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            if (differs(cur[k], sh[k])) { sh[k] = cur[k]; changed = true; }
+          }
+        }
+        emit_line(m, changed, (uint32_t)(((dst[a] - m.h_base) >> 6) + l), cur, sent);
+      }
+      sh_off += lines * 64;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sent += __shfl_xor_sync(RG_FULL, sent, o);
+  if (lane == 0 && sent) atomicAdd(m.bytes, (unsigned long long)sent);
+  if (publish) {  // the pass that ends the call: the last block to finish hands the counters to the host
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(m.ticket, 1u) == gridDim.x - 1) {
+        __threadfence();
+        *m.h_bytes = *reinterpret_cast<volatile unsigned long long*>(m.bytes);
+        *m.h_errflag = *reinterpret_cast<volatile uint32_t*>(b.errflag);
+        *b.errflag = 0u;  // reported: rg_sync clears it the same way
+        *m.bytes = 0ull;
+        *m.ticket = 0u;
+        __threadfence_system();
+        const unsigned long long seq = *m.seq + 1ull;
+        *m.seq = seq;
+        *reinterpret_cast<volatile unsigned long long*>(m.h_seq) = seq;  // everything above is in host memory before this
+        __threadfence_system();
       }
     }
   }
@@ -1635,6 +1854,19 @@ __global__ void __launch_bounds__(256) k_mirror(DevBatch b, MirrorArgs m, int pa
 // ---------------------------------------------------------------- launchers
 static int mirror_blocks(const DevBatch& b, int sm_count) {
   return (int)std::min<int64_t>((b.n + 7) / 8, (int64_t)sm_count * 8);  // a warp per env, grid-stride, 64 warps per SM
+}
+static bool mirror_by_lines(const DevBatch& b, const MirrorArgs& m) { return m.mode != 0 && (b.C & 63) == 0 && b.CP == b.C; }
+static const int MIRROR_ITEMS_MAX = 16000;  // words of k_mirror_lines' work list + env table (64 KB of shared memory at most)
+// One 1024-thread block per SM: on a few SMs beside the step's other kernels (pass 1, over k_step_fast's list of moves),
+// on every SM when the pass runs alone.
+static cudaError_t launch_lines(const DevBatch& b, const MirrorArgs& m, int pass, int publish, int sm_count, cudaStream_t s) {
+  const int lpe = b.C >> 6, ppe = m.with_hist ? b.HB >> 4 : 0;
+  const int threads = 1024;
+  const int epb = std::max(32, std::min(threads, MIRROR_ITEMS_MAX / (lpe + ppe + 1)) / 32 * 32);
+  const int env_chunks = (int)((b.n + epb - 1) / epb);
+  const int blocks = std::max(1, std::min(env_chunks, pass == 1 ? m.confined_sms : sm_count));
+  k_mirror_lines<<<blocks, threads, (size_t)epb * (lpe + ppe + 1) * 4, s>>>(b, m, pass, epb, env_chunks, pass != 1, publish, 0, b.n);
+  return cudaGetLastError();
 }
 static size_t one_warp_smem(const DevBatch& b) { return 2 * (size_t)b.CP + sizeof(EnvState) + 16; }
 static size_t block_smem(const DevBatch& b) { return (size_t)WARPS_PER_BLOCK * one_warp_smem(b); }
@@ -1662,6 +1894,8 @@ cudaError_t configure_kernels(const DevBatch& b) {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_spec_build, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(SPEC_WPB * (one_warp_smem(b) + (size_t)b.CP)));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_mirror_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, MIRROR_ITEMS_MAX * 4);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_complete_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one_warp_smem(b));
   if (e != cudaSuccess) return e;
@@ -1709,8 +1943,12 @@ cudaError_t launch_step(const DevBatch& b, const uint8_t* actions_src, uint8_t* 
     // step - the pass is dominated by small PCIe writes, not by SM work
     if ((e = cudaEventRecord(q.ev_fast, s)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(q.mir, q.ev_fast, 0)) != cudaSuccess) return e;
-    k_mirror<<<b.mirror_blocks > 0 ? b.mirror_blocks : mirror_blocks(b, sm_count), 256, 0, q.mir>>>(b, *mirror, 1, 0, b.n);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (mirror_by_lines(b, *mirror)) {
+      if ((e = launch_lines(b, *mirror, 1, 0, sm_count, q.mir)) != cudaSuccess) return e;
+    } else {
+      k_mirror<<<b.mirror_blocks > 0 ? b.mirror_blocks : mirror_blocks(b, sm_count), 256, 0, q.mir>>>(b, *mirror, 1, 0, b.n);
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
     if ((e = cudaEventRecord(q.ev_mir, q.mir)) != cudaSuccess) return e;
   }
   k_step_player<<<pblocks, 32, one_warp_smem(b), s>>>(b, actions, auto_reset, 1);
@@ -1729,7 +1967,10 @@ cudaError_t launch_step(const DevBatch& b, const uint8_t* actions_src, uint8_t* 
   }
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (mirror) {  // second pass: the envs that were finished by the player, monster, full-path and reset kernels
+    // (the second pass takes every env that still has rows marked: it must not start before the first has ended; nor
+    // may the publishing pass end before the first one's stores have landed)
     if ((e = cudaStreamWaitEvent(s, q.ev_mir, 0)) != cudaSuccess) return e;
+    if (mirror_by_lines(b, *mirror)) return launch_lines(b, *mirror, 2, 2, sm_count, s);
     k_mirror<<<mirror_blocks(b, sm_count), 256, 0, s>>>(b, *mirror, 2, 0, b.n);
   }
   return cudaGetLastError();
@@ -1778,6 +2019,7 @@ cudaError_t launch_complete_maps(const DevBatch& b, int64_t env_lo, int64_t env_
   return cudaGetLastError();
 }
 cudaError_t launch_mirror(const DevBatch& b, const MirrorArgs& m, int sm_count, cudaStream_t s) {
+  if (mirror_by_lines(b, m)) return launch_lines(b, m, 0, 1, sm_count, s);
   k_mirror<<<mirror_blocks(b, sm_count), 256, 0, s>>>(b, m, 0, 0, b.n);
   return cudaGetLastError();
 }

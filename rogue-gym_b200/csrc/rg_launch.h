@@ -24,8 +24,14 @@ struct MirrorArgs {
   unsigned long long* h_bytes;  // mapped host: bytes stored by the step
   uint32_t* h_errflag;          // mapped host: OR of the errors raised
   uint32_t* ticket;             // device: blocks of the publishing pass that have finished
+  unsigned long long* seq;      // device: publishing passes so far
+  unsigned long long* h_seq;    // mapped host: the same, written last - the host may spin on it instead of waiting for the stream
   int wide;              // 1 = a changed screen piece is sent with its whole 64-byte line (RG_MIRROR_WIDE)
   int with_hist;         // 0 = the visited map is not mirrored (nobody asked for it: rg_mirror_get without history_bits)
+  // mirror by lines (k_mirror_lines): mode 0 = k_mirror on every SM; 1 (default) = a few SMs (confined_sms) compare
+  // whole 64-byte lines and store them to the host; only those SMs wait behind PCIe
+  int mode, confined_sms;
+  uint8_t* h_base;       // device alias of the host block (every h_* pointer above lies inside it)
 };
 
 // streams and events one env-step is enqueued on (all owned by the batch)

@@ -155,7 +155,7 @@ struct DevBatch {
   uint8_t* full_path;     // [N] who finishes this step of the env (FP_*), written by k_step_fast every step
   uint32_t* fast_list_m;  // [N] k_step_fast's envs whose action is a move (k_step_scan groups them: no divergence)
   uint32_t* fast_list_l;  // [N] k_step_fast's other envs
-  uint32_t* fast_count;   // [parity][move, other] list lengths
+  uint32_t* fast_count;   // [parity][move, other] list lengths; [4] = moves of the step under way (for the host mirror's first pass)
   uint32_t* slow_list;    // [N] envs with an active monster (k_step_scan -> player kernel, first list)
   uint32_t* slow_list_b;  // [N] envs k_step_fast left to the warp-per-env player kernel (second list)
   uint32_t* slow_count;   // [list][parity] lengths, then [list][parity] work cursors of the player kernels

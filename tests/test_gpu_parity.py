@@ -393,16 +393,19 @@ def test_full_size_batch_properties(gpu, oracle):
 
 # ---------------------------------------------------------------- host mirror (delta write-back)
 @pytest.mark.gpu
-@pytest.mark.parametrize("cfg_name", ["default", "mini", "odd"])
-def test_host_mirror_equals_full_copy(gpu, cfg_name):
+@pytest.mark.parametrize("cfg_name", ["default", "mini", "odd", "default-direct", "mini-direct"])
+def test_host_mirror_equals_full_copy(gpu, cfg_name, monkeypatch):
     """rg_step_mirror must leave the host mirror byte-identical to what rg_fetch copies, every step,
-    across auto-resets, stair descents and explicit resets, while moving far fewer bytes."""
+    across auto-resets, stair descents and explicit resets, while moving far fewer bytes.
+    default / mini go through k_mirror_lines (whole 64-byte lines, on a few SMs), "odd" (a screen that is not a whole
+    number of 64-byte lines) and "-direct" (RG_MIRROR_MODE=direct) through k_mirror."""
     import json
 
     from helpers import CONFIGS
     from helpers import KEYS19
     n, steps = 192, 150
-    cfg = CONFIGS[cfg_name]
+    monkeypatch.setenv("RG_MIRROR_MODE", (cfg_name.split("-") + ["lines"])[1])
+    cfg = CONFIGS[cfg_name.split("-")[0]]
     pg = gpu.ParallelGameState(25, [json.dumps(cfg)] * n)
     pg.seed(list(range(3, n + 3)))
     pg.reset()
@@ -414,6 +417,11 @@ def test_host_mirror_equals_full_copy(gpu, cfg_name):
     sent = []
     for t in range(steps):
         keys = KEYS19[rng.randint(0, len(KEYS19), size=n)]
+        if t % 40 == 39:  # a step that is not mirrored: the next mirrored step has to bring its changes along
+            try:
+                b.step(KEYS19[rng.randint(0, len(KEYS19), size=n)], True)
+            except RuntimeError as e:
+                assert getattr(e, "code", None) in (2, 3), e  # per-env errors (input after death, reference panic)
         sent.append(b.step_mirror(keys, True))
         b.fetch()  # the full D2H copy of the same block
         assert np.array_equal(m["screen"].reshape(n, -1), b.screen), "screen differs at step %d" % t

@@ -325,3 +325,48 @@ def test_baseline_config1_scripted(gpu, oracle, seed):
         o.react(int(k))
     assert g.prev().dungeon == o.dungeon()
     assert len(json.loads(g.dump_history())) == 200
+
+
+@pytest.mark.parametrize("mode", ["lines", "direct"])
+def test_host_mirror_at_full_size(gpu, cabi, oracle, monkeypatch, mode):
+    """The host mirror at 65 536 envs: ~50 k changed lines per step, and the simultaneous end of every episode at step
+    60 (every screen is redrawn). The mirror must equal a full copy of the block."""
+    monkeypatch.setenv("RG_MIRROR_MODE", mode)
+    n, max_steps = 65536, 60
+    seeds = np.arange(n, dtype=np.uint64) + np.uint64(1)
+    L, h = _raw_batch(cabi, {}, n, max_steps, seeds)
+    obs, hist = cabi.HostObs(), C.c_void_p()
+    rc = L.rg_mirror_get(h, C.byref(obs), C.byref(hist))
+    assert rc in (0, 3), L.rg_last_error(h)
+
+    def view(ptr, ctype, count):
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(count,))
+
+    v = cabi.Views()
+    cabi.check(L.rg_views_get(h, C.byref(v)), h)
+    m_screen, m_status = view(obs.screen, C.c_uint8, n * 1920), view(obs.status, C.c_uint32, n * 10)
+    m_reward, m_done = view(obs.reward, C.c_int32, n), view(obs.done, C.c_uint8, n)
+    m_message, m_error = view(obs.message, C.c_uint32, n), view(obs.error, C.c_uint8, n)
+    m_hist = view(hist, C.c_uint8, n * v.hist_stride).reshape(n, v.hist_stride)
+    screen, history = np.zeros((n, 1920), np.uint8), np.zeros((n, 1920), np.uint8)
+    status, reward = np.zeros((n, 10), np.uint32), np.zeros(n, np.int32)
+    done, message, error = np.zeros(n, np.uint8), np.zeros(n, np.uint32), np.zeros(n, np.uint8)
+    full = cabi.HostObs(screen.ctypes.data, history.ctypes.data, status.ctypes.data, reward.ctypes.data, done.ctypes.data,
+                        message.ctypes.data, error.ctypes.data)
+    ids = np.arange(n, dtype=np.uint64)
+    nbytes = C.c_uint64()
+    sent = []
+    for t in range(75):
+        keys = oracle.synthetic_actions(t, ids)
+        rc = L.rg_step_mirror(h, keys.ctypes.data, 1, C.byref(nbytes))
+        assert rc in (0, 3), L.rg_last_error(h)
+        sent.append(nbytes.value)
+        if t % 10 == 9 or t in (58, 59, 60, 61):
+            L.rg_fetch(h, C.byref(full))
+            assert np.array_equal(m_screen.reshape(n, -1), screen), "screen differs at step %d" % t
+            bits = np.unpackbits(m_hist, axis=1, bitorder="little")[:, :1920]
+            assert np.array_equal(bits, history), "visited map differs at step %d" % t
+            assert np.array_equal(m_status.reshape(n, 10), status) and np.array_equal(m_reward, reward), t
+            assert np.array_equal(m_done, done) and np.array_equal(m_message, message) and np.array_equal(m_error, error), t
+    assert max(sent) > 8e6 and np.median(sent) < 8e6, (max(sent), np.median(sent))  # the mass reset; a normal step
+    L.rg_destroy(h)

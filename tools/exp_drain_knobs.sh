@@ -1,0 +1,9 @@
+#!/bin/bash
+# Host-facing step (rg_step_mirror, synced every step) under the staged mirror's knobs: wall clock per step
+# (tools/exp_e2e.py) and one timeline line (tools/timeline.py, TL_MIRROR=1).
+run() {
+  echo "== $*"
+  env "$@" timeout 100 python tools/exp_e2e.py 2>&1 | grep "rg_step_mirror"
+  env "$@" TL_MIRROR=1 timeout 90 python tools/timeline.py 700 2>&1 | grep "^slot" | tail -2 | head -1 | cut -c1-900
+}
+for k in "$@"; do run $k; done
