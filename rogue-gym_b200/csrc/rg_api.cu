@@ -917,6 +917,8 @@ int rg_mirror_get(rg_batch* b, rg_host_obs* out, uint8_t** history_bits) {
       b->margs.confined_sms = 16;
       if (const char* v = getenv("RG_MIRROR_MODE")) b->margs.mode = !strcmp(v, "direct") ? 0 : 1;
       if (const char* v = getenv("RG_MIRROR_SMS")) b->margs.confined_sms = std::max(1, atoi(v));
+      b->margs.fast_first = 1;
+      if (const char* v = getenv("RG_MIRROR_FAST_FIRST")) b->margs.fast_first = v[0] != '0';
       if ((e2 = cudaMemsetAsync(b->ms_screen, 0, N * d.CP, b->stream)) != cudaSuccess) return e2;
       if ((e2 = cudaMemsetAsync(b->ms_hist, 0, N * d.HB, b->stream)) != cudaSuccess) return e2;
       if ((e2 = cudaMemsetAsync(b->ms_flat, 0, flat, b->stream)) != cudaSuccess) return e2;

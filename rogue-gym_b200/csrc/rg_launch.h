@@ -31,6 +31,7 @@ struct MirrorArgs {
   // mirror by lines (k_mirror_lines): mode 0 = k_mirror on every SM; 1 (default) = a few SMs (confined_sms) compare
   // whole 64-byte lines and store them to the host; only those SMs wait behind PCIe
   int mode, confined_sms;
+  int fast_first;        // host-facing step: the active-monster branch starts after k_step_fast instead of beside it (RG_MIRROR_FAST_FIRST)
   uint8_t* h_base;       // device alias of the host block (every h_* pointer above lies inside it)
 };
 
