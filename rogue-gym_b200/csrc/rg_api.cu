@@ -175,7 +175,12 @@ int create_impl(const rg_params& P, const std::vector<rg_params>* per_env, int64
     if (e__ != cudaSuccess) return fail(cuda_fail(b, e__, #call));   \
   } while (0)
   RG_TRY(cudaSetDevice(device));
-  RG_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  {  // RG_MAIN_PRIO=h: the batch's stream (scan, thread-per-env kernel, its leftovers) at the branches' priority
+    int lo = 0, hi = 0;
+    RG_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    const char* mp = getenv("RG_MAIN_PRIO");
+    RG_TRY(cudaStreamCreateWithPriority(&b->stream, cudaStreamNonBlocking, (mp && mp[0] == 'h') ? hi : lo));
+  }
   DevBatch& d = b->d;
   d.n = n_envs;
   d.W = P.width;
