@@ -24,6 +24,12 @@ def fixtures():
 
 
 @pytest.fixture(scope="session")
+def gif_frames():
+    with open(os.path.join(ROOT, "tests", "golden", "reference_gif_frames.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
 def oracle():
     import oracle_py
     oracle_py.build()

@@ -117,3 +117,49 @@ def diff_obs(batch, ob, step, W, live=None):
                 msg += ": gpu %s oracle %s" % (g[i].tolist(), o[i].tolist())
             out.append(msg)
     return out
+
+
+# ---- the reference's rendered recordings (tests/golden/reference_gif_frames.json, made by make_gif_golden.py)
+def status_line(st, width):
+    """impl Display for Status (core/src/character/player.rs:433-449), cut at the screen width like the recording."""
+    hunger = {0: "", 1: "Hungry", 2: "Weak"}.get(int(st[9]), "")
+    s = "Level: %2d Gold: %5d Hp: %2d(%2d) Str: %2d(%2d) Arm: %2d Exp: %2d/%2d " % tuple(int(v) for v in st[:9]) + hunger
+    return s[:width].ljust(width)
+
+
+def check_against_recording(react, screen, status, msg_flags, keys, frames):
+    """act2gif (act2gif/src/draw.rs:44-68) emits one frame per Reaction::Redraw; the terminal it renders is persistent.
+    `react(key)` steps the game under test, `screen()` gives its rows, `status()` its 10-vector, `msg_flags()` the
+    PlayerState message bits of the last action. Checks, frame by frame:
+      * rows 1 .. H-2 (the dungeon) equal the game's screen after the action that produced the frame; an action that
+        produced no frame (a blocked move) must have left the screen as it was;
+      * the status line is the status before or after that action (StatusUpdated comes after Redraw in the reaction list,
+        so the line lags by one frame), blank before the first update;
+      * the messages shown, in order, are the ones the game's events call for (gold pick-ups, secret door, no downstair).
+    Returns the number of frames matched."""
+    H, W = len(frames[0]), len(frames[0][0])
+    fi, shown, events = 0, [], []
+    prev_screen, prev_status = screen(), [int(v) for v in status()]
+    blank = " " * W
+    for k in keys:
+        react(k)
+        scr, st, mf = screen(), [int(v) for v in status()], int(msg_flags())
+        if st[1] > prev_status[1]:
+            events.append(("You got %d Gold" % (st[1] - prev_status[1]))[:W])
+        if mf & 32:  # MessageFlag SECRET_DOOR (python/src/flags.rs)
+            events.append("You found a secret door"[:W])
+        if mf & 64:  # NO_DOWNSTAIR
+            events.append("Hmm... there seems to be no downstair"[:W])
+        if fi < len(frames) and frames[fi][1:H - 1] == scr[1:H - 1] and (scr != prev_screen or k in b"s>" or fi == 0):
+            fr = frames[fi]
+            assert fr[H - 1] in (blank, status_line(prev_status, W), status_line(st, W)), (fi, fr[H - 1])
+            if fr[0] != blank and (not shown or shown[-1] != fr[0].rstrip()):
+                shown.append(fr[0].rstrip())
+            fi += 1
+        else:
+            assert scr == prev_screen, "action %r changed the screen but matches no frame (frame %d)" % (chr(k), fi)
+        prev_screen, prev_status = scr, st
+    # every message that was displayed was called for, in order (the last event may have had no later frame to show it)
+    it = iter(events)
+    assert all(any(m == e for e in it) for m in shown), (shown, events)
+    return fi

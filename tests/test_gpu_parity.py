@@ -160,6 +160,21 @@ def test_reference_screens_with_monsters(gpu, fixtures):
         assert g.prev().dungeon == case["screen"], case["keys"]
 
 
+def test_reference_recordings_through_the_api(gpu, fixtures, gif_frames):
+    """The reference's rendered recordings (data/gif/*.gif, decoded into tests/golden/reference_gif_frames.json): 28 + 48
+    frames of two real runs of the 32x16 game, reproduced frame by frame through GameState on the GPU - dungeon rows,
+    status line, messages (see tests/test_oracle_golden.py::test_reference_recordings_frame_by_frame)."""
+    from helpers import check_against_recording
+    from test_oracle_golden import _ddqn_keys
+    for name, keys in (("ddqn_small", _ddqn_keys(fixtures, gif_frames["ddqn_small"]["n_actions"])),
+                       ("ppo_cog19", gif_frames["ppo_cog19"]["keys"].encode())):
+        frames = gif_frames[name]["frames"]
+        g = gpu.GameState(2000, json.dumps(gif_frames["config"]))
+        b = g._batch
+        n = check_against_recording(g.react, lambda: g.prev().dungeon, lambda: b.status[0], lambda: b.message[0], keys, frames)
+        assert n == len(frames), (name, n, len(frames))
+
+
 def test_move_enemy_known_answer(gpu, fixtures):
     """core/src/dungeon/rogue/mod.rs:566-578: BFS chase with the Right/RightDown tie."""
     import ctypes as C

@@ -150,3 +150,30 @@ def test_inclusive_edges_known_answer(oracle):
     # the non-inclusive form (maze exits, passages.rs:160-176) keeps the corners
     assert oracle.edges(5, 10, 6, 9, DOWN, False) == [(x, 8) for x in range(5, 10)]
     assert oracle.edges(5, 10, 6, 9, LEFT, False) == [(5, y) for y in range(6, 9)]
+
+
+def _ddqn_keys(fixtures, n):
+    import json
+
+    from rogue_gym_python._rogue_gym import keys_from_history
+    acts = [a for a, k in fixtures["recorded_episode"]["actions_rle"] for _ in range(k)][:n]
+    return keys_from_history(json.dumps(acts))
+
+
+def test_reference_recordings_frame_by_frame(oracle, fixtures, gif_frames):
+    """data/gif/*.gif are renderings of the reference's own runs (act2gif), decoded glyph by glyph into
+    tests/golden/reference_gif_frames.json. 28 frames of the shipped DDQN episode's first 30 actions and 48 frames of a
+    second agent on the same 32x16 game: two gold pick-ups with their amounts, a walk through a passage into a second
+    room, the descent, the level-2 floor, three searches of which the third finds the hidden door (the search draws),
+    more gold and passages on level 2 - every frame's dungeon rows, status line and messages."""
+    from helpers import check_against_recording
+    cfg = gif_frames["config"]
+    for name, keys in (("ddqn_small", _ddqn_keys(fixtures, gif_frames["ddqn_small"]["n_actions"])),
+                       ("ppo_cog19", gif_frames["ppo_cog19"]["keys"].encode())):
+        frames = gif_frames[name]["frames"]
+        e = oracle.OracleEnv(cfg, max_steps=2000)
+        n = check_against_recording(e.react, e.dungeon, lambda: e.obs()["status"], lambda: e.obs()["message"], keys, frames)
+        assert n == len(frames), (name, n, len(frames))
+        assert min(gif_frames[name]["worst_glyph_score"]) > 0.6
+    last = gif_frames["ppo_cog19"]["frames"][-1]
+    assert last[0].startswith("Hmm... there seems to be no down") and last[-1].startswith("Level:  2 Gold:    12 Hp: 12(12)")
