@@ -583,6 +583,13 @@ struct Item {
   uint32_t amount;
 };
 
+// Damage for Dice<HitPoint>::random (character/mod.rs:229-235): `times` draws of 1..=max on the given stream
+static int64_t dice_roll(Rng& rng, int times, int64_t mx) {
+  int64_t acc = 0;
+  for (int i = 0; i < times; ++i) acc += rng.range_i64(1, mx + 1);
+  return acc;
+}
+
 struct Floor {
   std::vector<Room> rooms;
   std::set<Coord> doors;
@@ -1117,11 +1124,7 @@ struct Env {
   static constexpr int64_t PLAYER_STR = 16;  // player.rs:286
   static constexpr int64_t ENEMY_STR = 10;   // enemies.rs:173
 
-  int64_t dice_random(int times, int64_t mx) {  // character/mod.rs:229-235
-    int64_t acc = 0;
-    for (int i = 0; i < times; ++i) acc += rng_enemy.range_i64(1, mx + 1);
-    return acc;
-  }
+  int64_t dice_random(int times, int64_t mx) { return dice_roll(rng_enemy, times, mx); }
   // fight.rs:52-72 ; nullopt = miss
   std::optional<int64_t> roll(const int32_t* times, const int32_t* maxs, int n, uint32_t rate, int64_t dam_plus) {
     bool did_hit = false;
@@ -1779,6 +1782,27 @@ int64_t orc_test_ordset(uint64_t cap, const uint64_t* members, const uint8_t* op
   if (len_out) *len_out = s.len();
   auto v = s.nth((size_t)k);
   return v ? (int64_t)*v : -1;
+}
+// character/mod.rs:277-285 `test_dice`: `count` rolls of `times` d `mx` on a stream seeded with `seed`
+void orc_test_dice(uint64_t seed, int times, int64_t mx, int64_t count, int64_t* out) {
+  Rng r;
+  r.seed(seed, 0);
+  for (int64_t i = 0; i < count; ++i) out[i] = dice_roll(r, times, mx);
+}
+// floor.rs:490-505 `select_cell`: a floor of `level`, then select_cell(false) + set_obj until no cell is left or
+// `tries` are used up. Returns how many cells were handed out, -1 if set_obj refused one of them.
+int64_t orc_test_select_cell(const orc_params* p, uint32_t level, uint64_t seed, int64_t tries) {
+  Rng r;
+  r.seed(seed, 0);
+  Floor f = Floor::gen_floor(level, *p, r);
+  int64_t cnt = 0;
+  for (int64_t i = 0; i < tries; ++i) {
+    auto cd = f.select_cell(r, false);
+    if (!cd) break;
+    if (!f.set_obj(*cd, false)) return -1;
+    ++cnt;
+  }
+  return cnt;
 }
 int orc_test_ordset_from_range_contains(uint64_t lo, uint64_t hi, uint64_t e) {
   return OrdSet::from_range((size_t)lo, (size_t)hi).contains((size_t)e) ? 1 : 0;

@@ -293,6 +293,10 @@ def lib():
         L.orc_test_ordset.argtypes = [C.c_uint64, vp, vp, vp, C.c_int64, C.c_int64, C.POINTER(C.c_uint64)]
         L.orc_test_ordset_from_range_contains.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
         L.orc_test_edges.argtypes = [C.c_int] * 6 + [vp, C.c_int]
+        L.orc_test_dice.restype = None
+        L.orc_test_dice.argtypes = [C.c_uint64, C.c_int, C.c_int64, C.c_int64, vp]
+        L.orc_test_select_cell.restype = C.c_int64
+        L.orc_test_select_cell.argtypes = [C.POINTER(Params), C.c_uint32, C.c_uint64, C.c_int64]
         _lib = L
     return _lib
 
@@ -312,6 +316,19 @@ def edges(x0, x1, y0, y1, direction, inclusive):
     out = np.zeros((512, 2), np.int32)
     n = lib().orc_test_edges(x0, x1, y0, y1, direction, int(inclusive), out.ctypes.data, 512)
     return [tuple(int(v) for v in p) for p in out[:n]]
+
+
+def dice(seed, times, mx, count):
+    """`count` rolls of `times` d `mx` (Dice::random, character/mod.rs:229-235) on a stream seeded with `seed`."""
+    out = np.zeros(count, np.int64)
+    lib().orc_test_dice(seed, times, mx, count, out.ctypes.data)
+    return out
+
+
+def select_cells(config, level, seed, tries=1000):
+    """floor.rs:490-505: cells Floor::select_cell hands out on a fresh floor of `level` before it runs dry (-1: set_obj refused)."""
+    params, _ = params_from_config(config)
+    return int(lib().orc_test_select_cell(C.byref(params), level, seed, tries))
 
 
 class OracleError(RuntimeError):

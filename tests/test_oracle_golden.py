@@ -177,3 +177,22 @@ def test_reference_recordings_frame_by_frame(oracle, fixtures, gif_frames):
         assert min(gif_frames[name]["worst_glyph_score"]) > 0.6
     last = gif_frames["ppo_cog19"]["frames"][-1]
     assert last[0].startswith("Hmm... there seems to be no down") and last[-1].startswith("Level:  2 Gold:    12 Hp: 12(12)")
+
+
+def test_dice_range(oracle):
+    """core/src/character/mod.rs:277-285 `test_dice`: 2d4 stays in 2..=8 (here also: reaches both ends, and the mean of
+    a fair 2d4 is 5)."""
+    for seed in (1, 2, 12345, 2**63 + 7):
+        r = oracle.dice(seed, 2, 4, 100)
+        assert r.min() >= 2 and r.max() <= 8
+    r = oracle.dice(9, 2, 4, 20000)
+    assert r.min() == 2 and r.max() == 8 and abs(r.mean() - 5.0) < 0.05
+    assert (oracle.dice(3, 0, 4, 10) == 0).all()  # no dice, no damage
+
+
+def test_select_cell_runs_dry(oracle):
+    """core/src/dungeon/rogue/floor.rs:490-505 `select_cell`: on a level-10 floor of the default config, select_cell
+    + set_obj hands out more than 15 cells before it returns None, and set_obj never refuses a selected cell."""
+    for seed in range(1, 41):
+        n = oracle.select_cells({}, 10, seed)
+        assert 15 < n < 1000, (seed, n)
