@@ -196,3 +196,25 @@ def test_select_cell_runs_dry(oracle):
     for seed in range(1, 41):
         n = oracle.select_cells({}, 10, seed)
         assert 15 < n < 1000, (seed, n)
+
+
+def test_gif_fixture_regenerates_from_the_reference(gif_frames):
+    """Where the reference tree and PIL are present (this container, not the GPU box): decoding data/gif/*.gif again
+    gives the committed frames, the 16 px and 24 px renderings agree, and the inferred key sequence comes out the same."""
+    import importlib.util
+    import os
+
+    import pytest
+    if not os.path.isdir("/root/reference/data/gif") or importlib.util.find_spec("PIL") is None:
+        pytest.skip("needs /root/reference and PIL")
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_gif_golden.py")
+    spec = importlib.util.spec_from_file_location("make_gif_golden", here)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    gif = os.path.join(m.REF, "data/gif")
+    f16, _ = m.decode(os.path.join(gif, "ddqn-small-16.gif"), 16)
+    f24, _ = m.decode(os.path.join(gif, "ddqn-small-24.gif"), 24)
+    assert f16 == f24 == gif_frames["ddqn_small"]["frames"]
+    ppo, _ = m.decode(os.path.join(gif, "pporesnet-cog19-10seed.gif"), 16)
+    assert ppo == gif_frames["ppo_cog19"]["frames"]
+    assert m.infer_actions(gif_frames["config"], ppo) == gif_frames["ppo_cog19"]["keys"]
