@@ -160,3 +160,27 @@ def test_dump_config_round_trip():
     assert json.loads(dump_config("{}", 9)) == {"seed": 9, "hide_dungeon": True}
     d = json.loads(dump_config(json.dumps({"dungeon": {"style": "rogue", "room_num_x": 2}})))
     assert d["dungeon"]["room_num_x"] == 2 and d["dungeon"]["room_num_y"] == 3 and d["dungeon"]["amulet_level"] == 25
+
+
+def test_builtin_defaults_equal_the_shipped_default_config(cabi):
+    """data/config-default.json is what GameConfig::default() serialises to (core/src/lib.rs:438-445 `print_default`):
+    every built-in table of the product's parser - the 26 monsters, weapons, armors, item rates, player and dungeon
+    parameters - must equal it field for field. One known difference: the file's level table ends in 0 where the
+    source has u32::max_value() (character/player.rs:336; the file predates it)."""
+    def parse(cfg):
+        p = cabi.Params()
+        err = C.create_string_buffer(256)
+        assert cabi.lib().rg_parse_config(json.dumps(cfg).encode(), C.byref(p), err, 256) == 0, err.value
+        return _fields(p)
+
+    with open(os.path.join(ROOT, "tests", "golden", "config_default.json")) as f:
+        shipped = parse(json.load(f))
+    builtin = parse({})
+    assert len(builtin) >= 40
+    for k in builtin:
+        if k == "exps":
+            n = [i for i, v in enumerate(builtin[k]) if v == 4294967295]
+            assert len(n) == 1 and shipped[k][n[0]] == 0
+            assert builtin[k][:n[0]] == shipped[k][:n[0]] and builtin[k][n[0] + 1:] == shipped[k][n[0] + 1:]
+        else:
+            assert builtin[k] == shipped[k], k
