@@ -408,11 +408,12 @@ def test_full_size_batch_properties(gpu, oracle):
 
 # ---------------------------------------------------------------- host mirror (delta write-back)
 @pytest.mark.gpu
-@pytest.mark.parametrize("cfg_name", ["default", "mini", "odd", "default-direct", "mini-direct"])
+@pytest.mark.parametrize("cfg_name", ["default", "mini", "wide", "odd", "default-direct", "mini-direct"])
 def test_host_mirror_equals_full_copy(gpu, cfg_name, monkeypatch):
     """rg_step_mirror must leave the host mirror byte-identical to what rg_fetch copies, every step,
     across auto-resets, stair descents and explicit resets, while moving far fewer bytes.
-    default / mini go through k_mirror_lines (whole 64-byte lines, on a few SMs), "odd" (a screen that is not a whole
+    default / mini / wide (160x48: 120 lines and 60 visited-map pieces per env) go through k_mirror_lines (whole
+    64-byte lines, on a few SMs), "odd" (a screen that is not a whole
     number of 64-byte lines) and "-direct" (RG_MIRROR_MODE=direct) through k_mirror."""
     import json
 
